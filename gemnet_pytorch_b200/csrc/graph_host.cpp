@@ -1,0 +1,242 @@
+// H0: native host index builder — replaces DataContainer.__getitem__ / get_triplets / get_quadruplets
+// (reference gemnet/training/data_container.py:156-408, 411-489; numba helpers :520-565) which go through
+// scipy.sparse fancy indexing, np.argsort and numba.  Plain C++: per-molecule dense distance test in fp64
+// (as the reference, :258-267), then counting-sort style emission that is already grouped by the reduce edge,
+// so no argsort is needed.  Semantics documented in include/gemnet_b200.h.
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gemnet_b200.h"
+
+namespace gemnet {
+void set_error(const char* fmt, ...);
+}
+
+struct gemnet_graph {
+  std::map<std::string, std::vector<int32_t>> arrays;
+};
+
+namespace {
+
+using ivec = std::vector<int32_t>;
+
+// all directed pairs (t, s), t != s, |R_t - R_s| <= cutoff, molecule by molecule, row-major
+void directed_pairs(const double* R, const int32_t* n_per_mol, int64_t n_mol, double cutoff, ivec& T, ivec& S) {
+  int64_t off = 0;
+  for (int64_t m = 0; m < n_mol; ++m) {
+    const int32_t n = n_per_mol[m];
+    for (int32_t i = 0; i < n; ++i) {
+      const double* ri = R + 3 * (off + i);
+      for (int32_t j = 0; j < n; ++j) {
+        if (i == j) continue;
+        const double* rj = R + 3 * (off + j);
+        const double dx = ri[0] - rj[0], dy = ri[1] - rj[1], dz = ri[2] - rj[2];
+        // same operation order as np.linalg.norm(..., axis=-1): sqrt((dx^2 + dy^2) + dz^2), no FMA contraction
+        volatile double sx = dx * dx, sy = dy * dy, sz = dz * dz;
+        const double d = std::sqrt((sx + sy) + sz);
+        if (d <= cutoff) {
+          T.push_back((int32_t)(off + i));
+          S.push_back((int32_t)(off + j));
+        }
+      }
+    }
+    off += n;
+  }
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int gemnet_graph_build_host(const double* R, const int32_t* n_per_mol,
+                                                                               int64_t n_mol, double cutoff,
+                                                                               double int_cutoff, int32_t triplets_only,
+                                                                               gemnet_graph** out) {
+  if (!out || n_mol < 0 || (n_mol > 0 && (!R || !n_per_mol))) {
+    gemnet::set_error("gemnet_graph_build_host: bad arguments");
+    return 1;
+  }
+  auto* g = new gemnet_graph();
+  auto& A = g->arrays;
+  int64_t n_atoms = 0;
+  for (int64_t m = 0; m < n_mol; ++m) {
+    if (n_per_mol[m] < 0) {
+      delete g;
+      gemnet::set_error("gemnet_graph_build_host: negative molecule size");
+      return 1;
+    }
+    n_atoms += n_per_mol[m];
+  }
+  ivec& batch_seg = A["batch_seg"];
+  batch_seg.reserve(n_atoms);
+  for (int64_t m = 0; m < n_mol; ++m)
+    for (int32_t i = 0; i < n_per_mol[m]; ++i) batch_seg.push_back((int32_t)m);
+
+  const char* keys3[] = {"id_undir", "id_swap", "id_c", "id_a", "id3_expand_ba", "id3_reduce_ca", "Kidx3"};
+  const char* keys4[] = {"id4_int_b", "id4_int_a", "id4_reduce_ca", "id4_expand_db", "id4_reduce_cab",
+                         "id4_expand_abd", "Kidx4", "id4_reduce_intm_ca", "id4_expand_intm_db",
+                         "id4_reduce_intm_ab", "id4_expand_intm_ab"};
+  for (const char* k : keys3) A[k];
+  if (!triplets_only)
+    for (const char* k : keys4) A[k];
+
+  ivec pt, ps;
+  directed_pairs(R, n_per_mol, n_mol, cutoff, pt, ps);
+  if (pt.empty()) {  // data_container.py:282-285: every index array empty
+    *out = g;
+    return 0;
+  }
+
+  // ---- edges: [upper triangle (t < s), row-major] ++ [reversed]   (:289-308)
+  ivec ut, us;
+  for (size_t p = 0; p < pt.size(); ++p)
+    if (pt[p] < ps[p]) {
+      ut.push_back(pt[p]);
+      us.push_back(ps[p]);
+    }
+  const int32_t nu = (int32_t)ut.size();
+  const int32_t nE = 2 * nu;
+  ivec& id_a = A["id_a"];
+  ivec& id_c = A["id_c"];
+  ivec& id_undir = A["id_undir"];
+  ivec& id_swap = A["id_swap"];
+  id_a.resize(nE); id_c.resize(nE); id_undir.resize(nE); id_swap.resize(nE);
+  for (int32_t p = 0; p < nu; ++p) {
+    id_a[p] = ut[p]; id_c[p] = us[p];
+    id_a[nu + p] = us[p]; id_c[nu + p] = ut[p];
+    id_undir[p] = p; id_undir[nu + p] = p;
+    id_swap[p] = nu + p; id_swap[nu + p] = p;
+  }
+
+  // ---- incoming edge lists per atom, ascending source atom (row x of the reference's edge_ids CSR, :311-315)
+  std::vector<int32_t> ptr(n_atoms + 1, 0);
+  for (int32_t e = 0; e < nE; ++e) ptr[id_a[e] + 1]++;
+  for (int64_t x = 0; x < n_atoms; ++x) ptr[x + 1] += ptr[x];
+  ivec inc(nE);
+  {
+    std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
+    for (int32_t p = 0; p < nu; ++p) inc[cur[us[p]]++] = nu + p;  // sources k < x (second-half edges), ascending k
+    for (int32_t p = 0; p < nu; ++p) inc[cur[ut[p]]++] = p;       // sources k > x (first-half edges), ascending k
+  }
+
+  // ---- triplets c -> a <- b, b != c, grouped by the reduce edge (c -> a)   (:411-425, :318-332)
+  {
+    ivec& exp = A["id3_expand_ba"];
+    ivec& red = A["id3_reduce_ca"];
+    ivec& kidx = A["Kidx3"];
+    size_t total = 0;
+    for (int32_t r = 0; r < nE; ++r) total += (size_t)(ptr[id_a[r] + 1] - ptr[id_a[r]]) - 1;
+    exp.reserve(total); red.reserve(total); kidx.reserve(total);
+    for (int32_t r = 0; r < nE; ++r) {
+      const int32_t a = id_a[r], c = id_c[r];
+      int32_t k = 0;
+      for (int32_t q = ptr[a]; q < ptr[a + 1]; ++q) {
+        const int32_t eb = inc[q];
+        if (id_c[eb] == c) continue;
+        exp.push_back(eb); red.push_back(r); kidx.push_back(k++);
+      }
+    }
+  }
+  if (triplets_only) {
+    *out = g;
+    return 0;
+  }
+
+  // ---- quadruplets c -> a - b <- d   (:428-489, :354-379)
+  ivec it, is;
+  directed_pairs(R, n_per_mol, n_mol, int_cutoff, it, is);
+  const int64_t nI = (int64_t)it.size();
+  A["id4_int_a"] = it;
+  A["id4_int_b"] = is;
+  ivec& intm_ca = A["id4_reduce_intm_ca"];
+  ivec& intm_db = A["id4_expand_intm_db"];
+  ivec& red_intm_ab = A["id4_reduce_intm_ab"];
+  ivec& exp_intm_ab = A["id4_expand_intm_ab"];
+  std::vector<int64_t> off_t(nI + 1, 0), off_s(nI + 1, 0);
+  for (int64_t i = 0; i < nI; ++i) {
+    off_t[i + 1] = off_t[i] + (ptr[it[i] + 1] - ptr[it[i]]);
+    off_s[i + 1] = off_s[i] + (ptr[is[i] + 1] - ptr[is[i]]);
+  }
+  intm_ca.resize(off_t[nI]); red_intm_ab.resize(off_t[nI]);
+  intm_db.resize(off_s[nI]); exp_intm_ab.resize(off_s[nI]);
+  for (int64_t i = 0; i < nI; ++i) {
+    for (int32_t q = ptr[it[i]], j = 0; q < ptr[it[i] + 1]; ++q, ++j) {
+      intm_ca[off_t[i] + j] = inc[q];
+      red_intm_ab[off_t[i] + j] = (int32_t)i;
+    }
+    for (int32_t q = ptr[is[i]], j = 0; q < ptr[is[i] + 1]; ++q, ++j) {
+      intm_db[off_s[i] + j] = inc[q];
+      exp_intm_ab[off_s[i] + j] = (int32_t)i;
+    }
+  }
+  // pass 1: count quadruplets per reduce edge
+  std::vector<int64_t> qptr(nE + 1, 0);
+  auto valid = [&](int64_t i, int32_t ec, int32_t ed) {
+    const int32_t c = id_c[ec], a = it[i], b = is[i], d = id_c[ed];
+    return c != b && a != d && c != d;
+  };
+  for (int64_t i = 0; i < nI; ++i)
+    for (int64_t jd = off_s[i]; jd < off_s[i + 1]; ++jd)
+      for (int64_t jc = off_t[i]; jc < off_t[i + 1]; ++jc)
+        if (valid(i, intm_ca[jc], intm_db[jd])) qptr[intm_ca[jc] + 1]++;
+  for (int32_t r = 0; r < nE; ++r) qptr[r + 1] += qptr[r];
+  const int64_t nQ = qptr[nE];
+  if (nQ > INT32_MAX) {
+    delete g;
+    gemnet::set_error("gemnet_graph_build_host: more than 2^31-1 quadruplets in one batch");
+    return 1;
+  }
+  ivec& red_ca = A["id4_reduce_ca"];
+  ivec& exp_db = A["id4_expand_db"];
+  ivec& red_cab = A["id4_reduce_cab"];
+  ivec& exp_abd = A["id4_expand_abd"];
+  ivec& kidx4 = A["Kidx4"];
+  red_ca.resize(nQ); exp_db.resize(nQ); red_cab.resize(nQ); exp_abd.resize(nQ); kidx4.resize(nQ);
+  {
+    std::vector<int64_t> cur(qptr.begin(), qptr.end() - 1);
+    for (int64_t i = 0; i < nI; ++i)
+      for (int64_t jd = off_s[i]; jd < off_s[i + 1]; ++jd)
+        for (int64_t jc = off_t[i]; jc < off_t[i + 1]; ++jc) {
+          const int32_t ec = intm_ca[jc], ed = intm_db[jd];
+          if (!valid(i, ec, ed)) continue;
+          const int64_t pos = cur[ec]++;
+          red_ca[pos] = ec; exp_db[pos] = ed;
+          red_cab[pos] = (int32_t)jc; exp_abd[pos] = (int32_t)jd;
+          kidx4[pos] = (int32_t)(pos - qptr[ec]);
+        }
+  }
+  *out = g;
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t gemnet_graph_size(const gemnet_graph* g, const char* name) {
+  if (!g || !name) return -1;
+  auto it = g->arrays.find(name);
+  return it == g->arrays.end() ? -1 : (int64_t)it->second.size();
+}
+
+extern "C" __attribute__((visibility("default"))) int gemnet_graph_copy_host(const gemnet_graph* g, const char* name,
+                                                                              int32_t* dst) {
+  if (!g || !name) {
+    gemnet::set_error("gemnet_graph_copy_host: null argument");
+    return 1;
+  }
+  auto it = g->arrays.find(name);
+  if (it == g->arrays.end()) {
+    gemnet::set_error("gemnet_graph_copy_host: unknown array '%s'", name);
+    return 1;
+  }
+  if (!it->second.empty()) {
+    if (!dst) {
+      gemnet::set_error("gemnet_graph_copy_host: null destination");
+      return 1;
+    }
+    std::memcpy(dst, it->second.data(), it->second.size() * sizeof(int32_t));
+  }
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) void gemnet_graph_free(gemnet_graph* g) { delete g; }

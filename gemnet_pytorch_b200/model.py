@@ -1,0 +1,189 @@
+"""GemNet with the reference's public interface, running its hot path on the sm_100a kernels.
+
+Drop-in boundary: same constructor kwargs as gemnet/model/gemnet.py:82-113, same
+`forward(inputs: dict) -> (E (nMol, num_targets), F (nAtoms, 3) | (nAtoms, num_targets, 3))` contract
+(gemnet.py:453-615) including the `inputs["R"].requires_grad` side effect (:493-494,613), `predict`,
+`load_weights`, `save_weights` (:780-790), the attributes `Trainer` touches (trainer.py:118-129,263-278,417) and a
+state_dict that strict-loads the shipped checkpoints.
+
+What differs inside: no zero-padded (E,Kmax,·) tensors, no gathered (T,C)/(Q,C) operands, angles are never
+materialised (cos/sin go straight into the Legendre / Y_lm recurrences), spherical Bessel functions are evaluated in
+fp64, scatters are CSR segment sums without atomics, and scale factors are folded into kernel epilogues.
+"""
+import torch
+
+from . import graph, layers, ops
+from .layers import (AtomEmbedding, BesselBasisLayer, Dense, EdgeEmbedding, EfficientInteractionDownProjection,
+                     InteractionBlock, InteractionBlockTripletsOnly, OutputBlock, SphericalBasisLayer,
+                     TensorBasisLayer)
+
+
+class GemNet(torch.nn.Module):
+    def __init__(
+        self,
+        num_spherical: int,
+        num_radial: int,
+        num_blocks: int,
+        emb_size_atom: int,
+        emb_size_edge: int,
+        emb_size_trip: int,
+        emb_size_quad: int,
+        emb_size_rbf: int,
+        emb_size_cbf: int,
+        emb_size_sbf: int,
+        emb_size_bil_quad: int,
+        emb_size_bil_trip: int,
+        num_before_skip: int,
+        num_after_skip: int,
+        num_concat: int,
+        num_atom: int,
+        triplets_only: bool,
+        num_targets: int = 1,
+        direct_forces: bool = False,
+        cutoff: float = 5.0,
+        int_cutoff: float = 10.0,
+        envelope_exponent: int = 5,
+        extensive=True,
+        forces_coupled: bool = False,
+        output_init="HeOrthogonal",
+        activation: str = "swish",
+        scale_file=None,
+        name="gemnet",
+        **kwargs,
+    ):
+        super().__init__()
+        assert num_blocks > 0
+        self.num_targets = num_targets
+        self.num_blocks = num_blocks
+        self.extensive = extensive
+        self.forces_coupled = forces_coupled
+        self.direct_forces = direct_forces
+        self.triplets_only = triplets_only
+        self.num_spherical, self.num_radial = num_spherical, num_radial
+        self.bilinear_algo = int(kwargs.get("bilinear_algo", 0))
+
+        # basis layers (no random state)
+        self.rbf_basis = BesselBasisLayer(num_radial, cutoff=cutoff, envelope_exponent=envelope_exponent)
+        if not self.triplets_only:
+            self.cbf_basis = SphericalBasisLayer(num_spherical, num_radial, cutoff=int_cutoff,
+                                                 envelope_exponent=envelope_exponent, efficient=False)
+            self.sbf_basis = TensorBasisLayer(num_spherical, num_radial, cutoff=cutoff,
+                                              envelope_exponent=envelope_exponent, efficient=True)
+        self.cbf_basis3 = SphericalBasisLayer(num_spherical, num_radial, cutoff=cutoff,
+                                              envelope_exponent=envelope_exponent, efficient=True)
+
+        # shared down projections (construction order = reference, for seeded-init parity)
+        if not self.triplets_only:
+            self.mlp_rbf4 = Dense(num_radial, emb_size_rbf, activation=None, bias=False)
+            self.mlp_cbf4 = Dense(num_radial * num_spherical, emb_size_cbf, activation=None, bias=False)
+            self.mlp_sbf4 = EfficientInteractionDownProjection(num_spherical ** 2, num_radial, emb_size_sbf)
+        self.mlp_rbf3 = Dense(num_radial, emb_size_rbf, activation=None, bias=False)
+        self.mlp_cbf3 = EfficientInteractionDownProjection(num_spherical, num_radial, emb_size_cbf)
+        self.mlp_rbf_h = Dense(num_radial, emb_size_rbf, activation=None, bias=False)
+        self.mlp_rbf_out = Dense(num_radial, emb_size_rbf, activation=None, bias=False)
+
+        self.atom_emb = AtomEmbedding(emb_size_atom)
+        self.edge_emb = EdgeEmbedding(emb_size_atom, num_radial, emb_size_edge, activation=activation)
+
+        block_cls = InteractionBlockTripletsOnly if self.triplets_only else InteractionBlock
+        int_blocks = [
+            block_cls(emb_size_atom=emb_size_atom, emb_size_edge=emb_size_edge, emb_size_trip=emb_size_trip,
+                      emb_size_quad=emb_size_quad, emb_size_rbf=emb_size_rbf, emb_size_cbf=emb_size_cbf,
+                      emb_size_sbf=emb_size_sbf, emb_size_bil_trip=emb_size_bil_trip,
+                      emb_size_bil_quad=emb_size_bil_quad, num_before_skip=num_before_skip,
+                      num_after_skip=num_after_skip, num_concat=num_concat, num_atom=num_atom, activation=activation,
+                      scale_file=scale_file, name=f"IntBlock_{i + 1}")
+            for i in range(num_blocks)
+        ]
+        out_blocks = [
+            OutputBlock(emb_size_atom=emb_size_atom, emb_size_edge=emb_size_edge, emb_size_rbf=emb_size_rbf,
+                        nHidden=num_atom, num_targets=num_targets, activation=activation, output_init=output_init,
+                        direct_forces=direct_forces, scale_file=scale_file, name=f"OutBlock_{i}")
+            for i in range(num_blocks + 1)
+        ]
+        self.out_blocks = torch.nn.ModuleList(out_blocks)
+        self.int_blocks = torch.nn.ModuleList(int_blocks)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, inputs):
+        Z, R = inputs["Z"], inputs["R"]
+        plan = graph.get_plan(inputs, self.triplets_only)
+        S, nR = self.num_spherical, self.num_radial
+        dev = R.device
+
+        if not self.direct_forces:
+            inputs["R"].requires_grad = True
+
+        # H1: distances and unit vectors
+        D_ca, V_ca = ops.edge_geometry(R, plan.id_c, plan.id_a)
+        basis = {}
+
+        if not self.triplets_only:
+            # H2/H4/H5 for quadruplets: intermediate triplets, then per-quadruplet Y_lm
+            D_ab, _ = ops.edge_geometry(R, plan.id4_int_b, plan.id4_int_a)
+            sph_abd, bd_proj = ops.quad_intermediate(R, plan.abd_center, plan.abd_first, plan.abd_second, S, True)
+            cs_cab, ac_proj = ops.quad_intermediate(R, plan.cab_center, plan.cab_first, plan.cab_second, S, False)
+            ylm = ops.quad_ylm(cs_cab, ac_proj, bd_proj, plan.id4_reduce_cab, plan.id4_expand_abd, S)  # (Q, S^2)
+            # cbf4 = non-efficient 2-D basis on the interaction edges (basis_layers.py:133-144): (M, S*R)
+            rad_int = self.cbf_basis.radial(D_ab)  # (nInt, S, R)
+            cbf4 = (rad_int[plan.abd_int_edge.long()] * sph_abd[:, :, None]).reshape(-1, S * nR)
+
+        rbf = self.rbf_basis(D_ca)                                                   # H3  (E, R)
+        rad = self.cbf_basis3.radial(D_ca)                                           # H4  (E, S, R), shared with H5
+        sph3 = ops.triplet_sph(R, plan.id_c, plan.id_a, plan.id3_reduce, plan.id3_expand, S)  # H2+H4 (T, S)
+
+        h = self.atom_emb(Z)
+        m = self.edge_emb(h, rbf, plan.id_c64, plan.id_a64)
+
+        if not self.triplets_only:
+            basis["rbf4"] = self.mlp_rbf4(rbf)
+            basis["cbf4"] = self.mlp_cbf4(cbf4)
+            basis["rbf_W1_4"] = self.mlp_sbf4(rad, layers.l_of_s_tensor(S, True, dev))      # H6 (E, I4, S^2)
+            basis["ylm"] = ylm
+        basis["rbf3"] = self.mlp_rbf3(rbf)
+        basis["rbf_W1_3"] = self.mlp_cbf3(rad, layers.l_of_s_tensor(S, False, dev))          # H6 (E, I3, S)
+        basis["sph3"] = sph3
+        basis["rbf_h"] = self.mlp_rbf_h(rbf)
+        rbf_out = self.mlp_rbf_out(rbf)
+
+        E_a, F_ca = self.out_blocks[0](h, m, rbf_out, plan)
+        for i in range(self.num_blocks):
+            h, m = self.int_blocks[i](h, m, basis, plan, self.bilinear_algo)
+            E, F = self.out_blocks[i + 1](h, m, rbf_out, plan)
+            F_ca = F_ca + F
+            E_a = E_a + E
+
+        # H12: read-out
+        E_mol = ops.molecule_sum(E_a, plan.batch_seg, plan.mol_rowptr, mean=not self.extensive)
+
+        if self.direct_forces:
+            if self.forces_coupled:  # enforce |F_ac| = |F_ca| (gemnet.py:588-592)
+                nE = plan.n_edges
+                id_undir = inputs["id_undir"]
+                summed = torch.zeros(int(nE / 2), F_ca.shape[1], dtype=F_ca.dtype, device=dev).index_add(0, id_undir, F_ca)
+                cnt = torch.zeros(int(nE / 2), dtype=F_ca.dtype, device=dev).index_add(
+                    0, id_undir, torch.ones(nE, dtype=F_ca.dtype, device=dev)).clamp(min=1)
+                F_ca = (summed / cnt[:, None])[id_undir]
+            F_j = ops.force_readout(F_ca, V_ca, plan.id_a, plan.atom_perm, plan.atom_rowptr)  # (A, T, 3)
+        else:
+            # first-order kernels only: create_graph (double backward) is not available
+            if self.num_targets > 1:
+                forces = [-torch.autograd.grad(E_mol[:, i].sum(), inputs["R"], retain_graph=True)[0]
+                          for i in range(self.num_targets)]
+                F_j = torch.stack(forces, dim=1)
+            else:
+                F_j = -torch.autograd.grad(E_mol.sum(), inputs["R"], retain_graph=self.training)[0]
+            inputs["R"].requires_grad = False
+            if not self.training:
+                E_mol = E_mol.detach()
+        return E_mol, F_j
+
+    def predict(self, inputs):
+        E, F = self(inputs)
+        return E.detach().cpu(), F.detach().cpu()
+
+    def load_weights(self, path):
+        self.load_state_dict(torch.load(path))
+
+    def save_weights(self, path):
+        torch.save(self.state_dict(), path)

