@@ -1,0 +1,365 @@
+"""GPU parity tests, one per hot-path row: the CUDA kernels (through the C-ABI) against the
+CPU oracle evaluated in float64 on the same seeded inputs, forward values and gradients.
+
+Tolerances: index work bit-exact; float32 kernels within a few float32 ulps of the float64 oracle, stated per test
+(relative to the largest magnitude of the compared tensor, as the north_star's 1e-4 relative gate is).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+from oracle import basis_oracle as bo  # noqa: E402
+from oracle import gemnet_oracle as go  # noqa: E402
+from oracle import graph_oracle as gr  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gemnet_pytorch_b200 import ops as _ops
+    return _ops
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def batch(ids, trip_only, dev):
+    d = H.oracle_batch(ids, trip_only)
+    cpu = gr.to_torch_inputs(d)
+    gpu = {k: (v.to(dev) if k == "R" else v.to(dev).to(torch.int32).contiguous()) for k, v in cpu.items()}
+    return cpu, gpu
+
+
+def oracle_grads(fn, inputs, g):
+    """d <g, fn(*inputs)> / d inputs in float64 on CPU."""
+    xs = [x.detach().double().cpu().requires_grad_(True) for x in inputs]
+    out = fn(*xs)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    gs = g if isinstance(g, (tuple, list)) else (g,)
+    tot = sum((o * gg.detach().double().cpu()).sum() for o, gg in zip(outs, gs))
+    return torch.autograd.grad(tot, xs, allow_unused=True)
+
+
+def kernel_grads(fn, inputs, g):
+    xs = [x.detach().clone().requires_grad_(True) for x in inputs]
+    out = fn(*xs)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    gs = g if isinstance(g, (tuple, list)) else (g,)
+    tot = sum((o * gg).sum() for o, gg in zip(outs, gs))
+    return torch.autograd.grad(tot, xs, allow_unused=True)
+
+
+# ----------------------------------------------------------------------------- index preparation (bit-exact)
+def test_csr_preparation_bit_exact(ops, dev):
+    rng = np.random.default_rng(0)
+    for n, rows in ((0, 5), (1, 1), (1000, 37), (50000, 700), (300000, 150001)):
+        ids = np.sort(rng.integers(0, rows, size=n)).astype(np.int32)
+        rowptr, flag = ops.csr_from_sorted(torch.tensor(ids, device=dev), rows)
+        want = np.searchsorted(ids, np.arange(rows + 1), side="left").astype(np.int32)
+        assert np.array_equal(rowptr.cpu().numpy(), want) and flag.item() == 0
+        ids2 = rng.integers(0, rows, size=n).astype(np.int32)
+        rp, perm = ops.csr_by_key(torch.tensor(ids2, device=dev), rows)
+        order = np.argsort(ids2, kind="stable").astype(np.int32)
+        assert np.array_equal(perm.cpu().numpy(), order)
+        assert np.array_equal(rp.cpu().numpy(), np.searchsorted(ids2[order], np.arange(rows + 1)).astype(np.int32))
+    bad = torch.tensor([0, 2, 1], dtype=torch.int32, device=dev)
+    assert ops.csr_from_sorted(bad, 3)[1].item() == 1
+    assert ops.csr_from_sorted(torch.tensor([0, 7], dtype=torch.int32, device=dev), 3)[1].item() == 1
+
+
+# ----------------------------------------------------------------------------- H1
+def test_edge_geometry(ops, dev):
+    cpu, gpu = batch(list(range(12)), True, dev)
+    D, V = ops.edge_geometry(gpu["R"], gpu["id_c"], gpu["id_a"])
+    D0, V0 = go.edge_vectors(cpu["R"].double(), cpu["id_c"], cpu["id_a"])
+    assert relerr(D, D0) < 3e-7 and relerr(V, V0) < 3e-7
+    fx = H.load_npz("ops.npz")
+    c2, g2 = batch(fx["mol_ids"].tolist(), False, dev)
+    D2, V2 = ops.edge_geometry(g2["R"], g2["id_c"], g2["id_a"])
+    assert relerr(D2, torch.tensor(fx["D_ca"])) < 3e-7 and relerr(V2, torch.tensor(fx["V_ca"])) < 3e-7
+    gD, gV = torch.randn_like(D), torch.randn_like(V)
+    (gR,) = kernel_grads(lambda R: ops.edge_geometry(R, gpu["id_c"], gpu["id_a"]), [gpu["R"]], (gD, gV))
+    (gR0,) = oracle_grads(lambda R: go.edge_vectors(R, cpu["id_c"], cpu["id_a"]), [cpu["R"]], (gD, gV))
+    assert relerr(gR, gR0) < 2e-5
+
+
+# ----------------------------------------------------------------------------- H3
+def test_bessel_rbf(ops, dev):
+    fx = H.load_npz("ops.npz")
+    D = torch.tensor(fx["D_ca"], dtype=torch.float32, device=dev)
+    f = torch.tensor(fx["frequencies"], device=dev)
+    out = ops.bessel_rbf(D, f, 5.0, 5)
+    assert relerr(out, torch.tensor(fx["rbf64"])) < 1e-6          # vs the reference layer in float64
+    assert relerr(torch.tensor(fx["rbf32"]), torch.tensor(fx["rbf64"])) < 1e-5  # the reference's own fp32 error
+    g = torch.randn_like(out)
+    gD, gf = kernel_grads(lambda d, fr: ops.bessel_rbf(d, fr, 5.0, 5), [D, f], g)
+    gD0, gf0 = oracle_grads(lambda d, fr: bo.bessel_rbf(d, fr, 5.0, 5), [D, f], g)
+    assert relerr(gD, gD0) < 1e-5 and relerr(gf, gf0) < 1e-5
+    # beyond the cutoff the envelope is exactly zero
+    far = torch.tensor([5.0, 5.5, 9.0], device=dev)
+    assert ops.bessel_rbf(far, f, 5.0, 5).abs().max().item() == 0.0
+
+
+# ----------------------------------------------------------------------------- H4/H5 radial
+@pytest.mark.parametrize("cutoff,key", [(5.0, "D_ca"), (10.0, "D_ab")])
+def test_sph_bessel_radial(ops, dev, cutoff, key):
+    fx = H.load_npz("ops.npz")
+    D = torch.tensor(fx[key], dtype=torch.float32, device=dev)
+    out = ops.sph_bessel_radial(D, 7, 6, cutoff, 5)  # (E,7,6)
+    want = bo.radial_sph_bessel(D.double().cpu(), 7, 6, cutoff, 5)
+    # fp64 evaluation inside the kernel: limited by float32 storage and the ~1e-7 normaliser quirk
+    assert relerr(out, want) < 5e-7
+    if key == "D_ca":
+        ref64 = torch.tensor(fx["cbf3_rbf_env64"]).permute(1, 0, 2)
+        ref32 = torch.tensor(fx["cbf3_rbf_env32"]).permute(1, 0, 2)
+        assert relerr(out, ref64) < 5e-7
+        assert relerr(out, ref64) < relerr(ref32, ref64)  # closer to the truth than the reference's own fp32
+    g = torch.randn_like(out)
+    (gD,) = kernel_grads(lambda d: ops.sph_bessel_radial(d, 7, 6, cutoff, 5), [D], g)
+    (gD0,) = oracle_grads(lambda d: bo.radial_sph_bessel(d, 7, 6, cutoff, 5), [D], g)
+    assert relerr(gD, gD0) < 1e-5
+    # small arguments (series branch) and beyond the cutoff
+    tiny = torch.tensor([1e-3, 0.02, 0.3, cutoff, cutoff * 1.5], device=dev)
+    t = ops.sph_bessel_radial(tiny, 7, 6, cutoff, 5)
+    w = bo.radial_sph_bessel(tiny.double().cpu(), 7, 6, cutoff, 5)
+    assert torch.isfinite(t).all() and t[3:].abs().max().item() == 0.0
+    # the oracle's upward recurrence loses digits at tiny arguments; compare the low orders only
+    assert relerr(t[:, :2], w[:, :2]) < 1e-6
+
+
+# ----------------------------------------------------------------------------- H2 + H4 angular (triplets)
+def test_triplet_sph(ops, dev):
+    fx = H.load_npz("ops.npz")
+    cpu, gpu = batch(fx["mol_ids"].tolist(), False, dev)
+    args = (gpu["id_c"], gpu["id_a"], gpu["id3_reduce_ca"], gpu["id3_expand_ba"])
+    ang = ops.triplet_angles(gpu["R"], *args)
+    assert (ang.double().cpu() - torch.tensor(fx["Angles3"])).abs().max() < 2e-6  # H2
+    sph = ops.triplet_sph(gpu["R"], *args, 7)
+    assert relerr(sph, torch.tensor(fx["cbf3_sph64"])) < 2e-6  # H4 angular, float64 reference layer
+    g = torch.randn_like(sph)
+    (gR,) = kernel_grads(lambda R: ops.triplet_sph(R, *args, 7), [gpu["R"]], g)
+
+    def oracle(R):
+        a = go.triplet_angles(R, cpu["id_c"], cpu["id_a"], cpu["id3_reduce_ca"], cpu["id3_expand_ba"])
+        return bo.legendre_y_l0(a, 7)
+
+    (gR0,) = oracle_grads(oracle, [cpu["R"]], g)
+    assert relerr(gR, gR0) < 2e-5
+
+
+def test_triplet_sph_collinear_clamp(ops, dev):
+    # three atoms on a line: |u x v| = 0 -> y clamped to 1e-9 (gemnet.py:309); values finite, gradient finite
+    R = torch.tensor([[0.0, 0, 0], [1.1, 0, 0], [2.3, 0, 0]], device=dev)
+    d = gr.build_batch([R.cpu().numpy().astype(np.float64)], [np.array([6, 8, 6])], 5.0, 10.0, True)
+    g = {k: torch.tensor(np.asarray(v), device=dev).to(torch.int32) for k, v in d.items() if k.startswith("id")}
+    Rg = R.clone().requires_grad_(True)
+    sph = ops.triplet_sph(Rg, g["id_c"], g["id_a"], g["id3_reduce_ca"], g["id3_expand_ba"], 7)
+    sph.sum().backward()
+    assert torch.isfinite(sph).all() and torch.isfinite(Rg.grad).all()
+    a = go.triplet_angles(R.double().cpu(), *[torch.tensor(np.asarray(d[k])).long() for k in
+                                               ("id_c", "id_a", "id3_reduce_ca", "id3_expand_ba")])
+    assert relerr(sph, bo.legendre_y_l0(a, 7)) < 2e-6
+
+
+# ----------------------------------------------------------------------------- H2 + H4 (cbf4) / H5 (quadruplets)
+def _quad_plan(gpu):
+    from gemnet_pytorch_b200.graph import GraphPlan
+    inputs = {k: (v.long() if k != "R" else v) for k, v in gpu.items()}
+    return GraphPlan(inputs, False)
+
+
+def test_quadruplet_geometry_and_ylm(ops, dev):
+    fx = H.load_npz("ops.npz")
+    cpu, gpu = batch(fx["mol_ids"].tolist(), False, dev)
+    plan = _quad_plan(gpu)
+    R = gpu["R"]
+    sph_abd, bd_proj = ops.quad_intermediate(R, plan.abd_center, plan.abd_first, plan.abd_second, 7, True)
+    cs_cab, ac_proj = ops.quad_intermediate(R, plan.cab_center, plan.cab_first, plan.cab_second, 7, False)
+    assert relerr(sph_abd, bo.legendre_y_l0(torch.tensor(fx["Phi_abd"]), 7)) < 2e-6
+    tp = ops.quad_angles(cs_cab, ac_proj, bd_proj, plan.id4_reduce_cab, plan.id4_expand_abd, 7)
+    assert (tp[:, 0].double().cpu() - torch.tensor(fx["Phi_cab"])).abs().max() < 3e-6      # H2
+    dphi = (tp[:, 1].double().cpu() - torch.tensor(fx["Theta_cabd"])).abs()
+    assert dphi.max() < 2e-4 and dphi.mean() < 2e-6   # dihedral of near-degenerate projections is ill-conditioned in fp32
+    ylm = ops.quad_ylm(cs_cab, ac_proj, bd_proj, plan.id4_reduce_cab, plan.id4_expand_abd, 7)
+    ref64, ref32 = torch.tensor(fx["sbf_sph64"]), torch.tensor(fx["sbf_sph32"])
+    assert relerr(ylm, ref64) < max(2e-4, 2 * relerr(ref32, ref64))
+    assert (ylm.double().cpu() - ref64).abs().mean() < 1e-6
+
+    # backward of the whole geometry chain R -> (cbf4 angular part, Y_lm)
+    g1, g2 = torch.randn_like(sph_abd), torch.randn_like(ylm)
+
+    def kern(Rr):
+        s, bd = ops.quad_intermediate(Rr, plan.abd_center, plan.abd_first, plan.abd_second, 7, True)
+        cs, ac = ops.quad_intermediate(Rr, plan.cab_center, plan.cab_first, plan.cab_second, 7, False)
+        return s, ops.quad_ylm(cs, ac, bd, plan.id4_reduce_cab, plan.id4_expand_abd, 7)
+
+    def oracle(Rr):
+        pc, pa, th = go.quad_angles(Rr, cpu["id_c"], cpu["id_a"], cpu["id4_int_b"], cpu["id4_int_a"],
+                                    cpu["id4_expand_abd"], cpu["id4_reduce_cab"], cpu["id4_expand_intm_db"],
+                                    cpu["id4_reduce_intm_ca"], cpu["id4_expand_intm_ab"], cpu["id4_reduce_intm_ab"])
+        return bo.legendre_y_l0(pa, 7), bo.real_sph_harm_all(pc, th, 7)
+
+    (gR,) = kernel_grads(kern, [R], (g1, g2))
+    (gR0,) = oracle_grads(oracle, [cpu["R"]], (g1, g2))
+    assert relerr(gR, gR0) < 1e-3  # float32 sums of ~1e4 ill-conditioned dihedral terms per atom
+
+
+# ----------------------------------------------------------------------------- H6
+@pytest.mark.parametrize("tensor_basis,I", [(False, 16), (True, 32)])
+def test_down_projection(ops, dev, tensor_basis, I):
+    from gemnet_pytorch_b200 import basis_consts
+    torch.manual_seed(1)
+    E, L, R = 777, 7, 6
+    S = 49 if tensor_basis else 7
+    rad = torch.randn(E, L, R, device=dev)
+    Wd = torch.randn(S, R, I, device=dev)
+    los = torch.tensor(basis_consts.l_of_s(7, tensor_basis), device=dev)
+
+    def oracle(r, w):
+        r2 = r[:, los.long().cpu(), :]  # repeat_interleave (basis_layers.py:251-253)
+        rbf_W1, _ = go.down_projection(r2.transpose(0, 1), torch.zeros(E, 1, S, dtype=r.dtype), w)
+        return rbf_W1
+
+    out = ops.down_projection(rad, Wd, los)
+    assert relerr(out, oracle(rad.double().cpu(), Wd.double().cpu())) < 1e-6
+    g = torch.randn_like(out)
+    gr_, gw = kernel_grads(lambda r, w: ops.down_projection(r, w, los), [rad, Wd], g)
+    gr0, gw0 = oracle_grads(oracle, [rad, Wd], g)
+    assert relerr(gr_, gr0) < 1e-5 and relerr(gw, gw0) < 2e-5
+
+
+# ----------------------------------------------------------------------------- H7
+def _bilinear_oracle(x, sph, rbf_W1, W, expand, reduce_ids, kidx, scale):
+    basis = (rbf_W1, go.pad_by_segment(sph, reduce_ids, kidx, rbf_W1.shape[0]).transpose(1, 2))
+    return go.efficient_bilinear(basis, x[expand], reduce_ids, kidx, W) * scale
+
+
+@pytest.mark.parametrize("tag", ["trip", "quad"])
+def test_segmented_bilinear_golden(ops, dev, tag):
+    """forward against the reference layer's float64 output stored in the fixture (efficient.py:159-189)."""
+    fx = H.load_npz("ops.npz")
+    cpu, gpu = batch(fx["mol_ids"].tolist(), False, dev)
+    red = cpu["id3_reduce_ca"] if tag == "trip" else cpu["id4_reduce_ca"]
+    sph = torch.tensor(fx["cbf3_sph64" if tag == "trip" else "sbf_sph64"], dtype=torch.float32, device=dev)
+    nE = len(cpu["id_c"])
+    rowptr, _ = ops.csr_from_sorted(red.to(dev).to(torch.int32), nE)
+    m = torch.tensor(fx[f"{tag}_m"], device=dev)          # already gathered (U,C): identity expand
+    expand = torch.arange(m.shape[0], dtype=torch.int32, device=dev)
+    rbf_W1 = torch.tensor(fx[f"{tag}_rbf_W1"], dtype=torch.float32, device=dev)
+    W = torch.tensor(fx[f"{tag}_Wbil"], dtype=torch.float32, device=dev)
+    out = ops.segmented_bilinear(m, sph, rbf_W1, W, expand, rowptr, 1.0)
+    ref64, ref32 = torch.tensor(fx[f"{tag}_out64"]), torch.tensor(fx[f"{tag}_out32"])
+    assert relerr(out, ref64) < 2e-6
+    assert relerr(out, ref64) < 4 * relerr(ref32, ref64) + 1e-6
+
+
+@pytest.mark.parametrize("tag,S,C,I,O", [("trip", 7, 64, 16, 64), ("quad", 49, 32, 32, 32)])
+def test_segmented_bilinear_gather_and_backward(ops, dev, tag, S, C, I, O):
+    torch.manual_seed(3)
+    cpu, gpu = batch([1, 4, 7, 9, 16], tag == "trip", dev) if tag == "trip" else batch([1, 4, 7], False, dev)
+    nE = len(cpu["id_c"])
+    if tag == "trip":
+        red, kidx, expand_cpu, n_x = cpu["id3_reduce_ca"], cpu["Kidx3"], cpu["id3_expand_ba"], nE
+    else:
+        red, kidx, expand_cpu = cpu["id4_reduce_ca"], cpu["Kidx4"], cpu["id4_expand_abd"]
+        n_x = len(cpu["id4_expand_intm_db"])
+    U = len(red)
+    x = torch.randn(n_x, C, device=dev)
+    sph = torch.randn(U, S, device=dev)
+    rbf_W1 = torch.randn(nE, I, S, device=dev) * 0.3
+    W = torch.randn(C, I, O, device=dev) / (C * I) ** 0.5
+    expand = expand_cpu.to(dev).to(torch.int32)
+    rowptr, _ = ops.csr_from_sorted(red.to(dev).to(torch.int32), nE)
+    scale = 1.7
+
+    out = ops.segmented_bilinear(x, sph, rbf_W1, W, expand, rowptr, scale)
+    want = _bilinear_oracle(x.double().cpu(), sph.double().cpu(), rbf_W1.double().cpu(), W.double().cpu(),
+                            expand_cpu, red, kidx, scale)
+    assert relerr(out, want) < 3e-6
+    g = torch.randn_like(out)
+    got = kernel_grads(lambda a, b, c, d: ops.segmented_bilinear(a, b, c, d, expand, rowptr, scale),
+                       [x, sph, rbf_W1, W], g)
+    ref = oracle_grads(lambda a, b, c, d: _bilinear_oracle(a, b, c, d, expand_cpu, red, kidx, scale),
+                       [x, sph, rbf_W1, W], g)
+    for name, a, b in zip(("g_x", "g_sph", "g_rbf_W1", "g_W"), got, ref):
+        assert relerr(a, b) < 2e-5, name
+
+
+def test_segmented_bilinear_empty_segments_and_errors(ops, dev):
+    # edges without any triplet (two-atom molecules) give exactly zero rows; empty inputs are accepted
+    E = 40
+    rowptr = torch.zeros(E + 1, dtype=torch.int32, device=dev)
+    rowptr[20:] = 5  # only edge 19 has a segment of 5 units
+    x = torch.randn(E, 64, device=dev)
+    sph = torch.randn(5, 7, device=dev)
+    expand = torch.tensor([0, 3, 3, 39, 7], dtype=torch.int32, device=dev)
+    out = ops.segmented_bilinear(x, sph, torch.randn(E, 16, 7, device=dev), torch.randn(64, 16, 64, device=dev),
+                                 expand, rowptr, 1.0)
+    assert out[:19].abs().max().item() == 0 and out[20:].abs().max().item() == 0 and out[19].abs().max().item() > 0
+    from gemnet_pytorch_b200._lib import GemnetB200Error
+    with pytest.raises(GemnetB200Error, match="unsupported"):
+        ops.segmented_bilinear(torch.randn(E, 48, device=dev), sph, torch.randn(E, 16, 7, device=dev),
+                               torch.randn(48, 16, 64, device=dev), expand, rowptr, 1.0)
+
+
+# ----------------------------------------------------------------------------- H10 / H11
+def test_edge_to_atom(ops, dev):
+    torch.manual_seed(5)
+    cpu, gpu = batch(list(range(20, 40)), True, dev)
+    E, A, F = len(cpu["id_c"]), len(cpu["Z"]), 128
+    m, r = torch.randn(E, F, device=dev), torch.randn(E, F, device=dev)
+    rowptr, perm = ops.csr_by_key(gpu["id_a"], A)
+    out, had = ops.edge_to_atom(m, r, gpu["id_a"], perm, rowptr, 0.9, 2.5)
+    want = go.scatter_sum(m.double().cpu() * r.double().cpu(), cpu["id_a"], A) * 0.9
+    assert relerr(out, want) < 1e-6 and relerr(had, m.double().cpu() * r.double().cpu() * 2.5) < 1e-6
+    # deterministic: bitwise identical on repetition (no atomics)
+    out2, _ = ops.edge_to_atom(m, r, gpu["id_a"], perm, rowptr, 0.9, 2.5)
+    assert torch.equal(out, out2)
+    g1, g2 = torch.randn_like(out), torch.randn_like(had)
+    gm, gr_ = kernel_grads(lambda a, b: ops.edge_to_atom(a, b, gpu["id_a"], perm, rowptr, 0.9, 2.5), [m, r], (g1, g2))
+    gm0, gr0 = oracle_grads(lambda a, b: (go.scatter_sum(a * b, cpu["id_a"], A) * 0.9, a * b * 2.5), [m, r], (g1, g2))
+    assert relerr(gm, gm0) < 1e-6 and relerr(gr_, gr0) < 1e-6
+    # atoms without incoming edges stay zero (atom_update_block.py:131-132 comment)
+    lone = torch.zeros(3, dtype=torch.int32, device=dev)
+    rp, pm = ops.csr_by_key(lone, 4)
+    o = ops.edge_to_atom(m[:3].contiguous(), r[:3].contiguous(), lone, pm, rp, 1.0)
+    assert o[1:].abs().max().item() == 0
+
+
+# ----------------------------------------------------------------------------- H12
+def test_molecule_sum_and_force_readout(ops, dev):
+    torch.manual_seed(6)
+    cpu, gpu = batch(list(range(40, 70)), True, dev)
+    A, E, nMol = len(cpu["Z"]), len(cpu["id_c"]), 30
+    for nT in (1, 3):
+        Ea = torch.randn(A, nT, device=dev)
+        mol_rowptr, _ = ops.csr_from_sorted(gpu["batch_seg"], nMol)
+        for mean in (False, True):
+            out = ops.molecule_sum(Ea, gpu["batch_seg"], mol_rowptr, mean)
+            fn = go.scatter_mean if mean else go.scatter_sum
+            assert relerr(out, fn(Ea.double().cpu(), cpu["batch_seg"], nMol)) < 1e-6
+            g = torch.randn_like(out)
+            (gE,) = kernel_grads(lambda e: ops.molecule_sum(e, gpu["batch_seg"], mol_rowptr, mean), [Ea], g)
+            (gE0,) = oracle_grads(lambda e: fn(e, cpu["batch_seg"], nMol), [Ea], g)
+            assert relerr(gE, gE0) < 1e-6
+        Fca, V = torch.randn(E, nT, device=dev), torch.randn(E, 3, device=dev)
+        rowptr, perm = ops.csr_by_key(gpu["id_a"], A)
+        Fj = ops.force_readout(Fca, V, gpu["id_a"], perm, rowptr)
+        want = go.scatter_sum(Fca.double().cpu()[:, :, None] * V.double().cpu()[:, None, :], cpu["id_a"], A)
+        assert relerr(Fj, want) < 1e-6
+        g = torch.randn_like(Fj)
+        gF, gV = kernel_grads(lambda f, v: ops.force_readout(f, v, gpu["id_a"], perm, rowptr), [Fca, V], g)
+        gF0, gV0 = oracle_grads(lambda f, v: go.scatter_sum(f[:, :, None] * v[:, None, :], cpu["id_a"], A), [Fca, V], g)
+        assert relerr(gF, gF0) < 1e-6 and relerr(gV, gV0) < 1e-6
