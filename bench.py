@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — molecules/sec of the GemNet energy+force hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--model T|Q] [--batch B] [--impl b200|reference]
+
+N=1 workload = BASELINE.json configs[1]: GemNet-T inference (energy + forces by -dE/dR, as the shipped checkpoints),
+COLL-shaped synthetic batch of 64 molecules per GPU, emb_size 128, fp32.  One "step" = one energy+force evaluation
+of one batch.  N>1 (torchrun): whole molecules sharded per rank, weak scaling, no data-path collective
+(inference needs none); time = max over ranks.
+
+JSON line keys follow the driver contract; in addition
+  roofline      the triplet segmented-bilinear kernel (row H7) at the bench batch: algorithmic bytes (SURVEY §8d
+                formula) / CUDA-event time of isolated launches vs MEASURED_PEAKS.json hbm_gbs
+  roofline_large same kernel on a 2048-molecule batch (the batch-64 launch is latency-bound)
+  cpu_baseline  the oracle port (torch CPU restatement of the reference, all host threads) on the same batch
+`--impl reference` times that CPU path on rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+BASE_KW = dict(num_spherical=7, num_radial=6, num_blocks=4, emb_size_atom=128, emb_size_edge=128, emb_size_trip=64,
+               emb_size_quad=32, emb_size_rbf=16, emb_size_cbf=16, emb_size_sbf=32, emb_size_bil_trip=64,
+               emb_size_bil_quad=32, num_before_skip=1, num_after_skip=1, num_concat=1, num_atom=2, num_targets=1,
+               direct_forces=False, cutoff=5.0, int_cutoff=10.0, envelope_exponent=5, extensive=True,
+               forces_coupled=False, output_init="HeOrthogonal", activation="swish", scale_file=None)
+
+
+def synthetic_molecules(n_mol, seed):
+    """COLL-shaped synthetic molecules: resample (with replacement) from the 256 committed COLL test molecules and
+    jitter the coordinates by N(0, 0.05 A) (SURVEY §8d input 2)."""
+    sub = dict(np.load(os.path.join(GOLDEN, "coll_subset.npz")))
+    N = sub["N"].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(N)])
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(0, len(N), size=n_mol)
+    Rl = [sub["R"][off[i]:off[i + 1]] + rng.normal(0.0, 0.05, size=(N[i], 3)) for i in ids]
+    Zl = [sub["Z"][off[i]:off[i + 1]].astype(np.int64) for i in ids]
+    return Rl, Zl
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for j, n in enumerate(names):
+                if any(len(r) > 2 + j and r[2 + j].strip().lower() == "active" for r in rows):
+                    out["reasons"].append(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def bilinear_bytes(E, U, S, C, I, O, b=4):
+    """each operand once, output once, padding excluded, int32 CSR."""
+    return b * (E * C + U * S + E * I * S + C * I * O + E * O) + 4 * (U + E + 1)
+
+
+def bilinear_flops(E, U, S, C, I, O):
+    return 2 * U * S * C + 2 * E * I * S * C + 2 * E * C * I * O
+
+
+def time_bilinear(plan, dev, flush, reps, algo=0):
+    """CUDA-event time of isolated launches of the triplet segmented-bilinear kernel on this plan's graph."""
+    from gemnet_pytorch_b200 import ops
+    E, T = plan.n_edges, plan.n_triplets
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(E, 64, generator=g).to(dev)
+    sph = torch.randn(T, 7, generator=g).to(dev)
+    rw = torch.randn(E, 16, 7, generator=g).to(dev)
+    W = (torch.randn(64, 16, 64, generator=g) / 32).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            ops.segmented_bilinear(x, sph, rw, W, plan.id3_expand, plan.rowptr3, 1.0, algo)
+        times = []
+        for _ in range(reps):
+            flush()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            ops.segmented_bilinear(x, sph, rw, W, plan.id3_expand, plan.rowptr3, 1.0, algo)
+            e.record()
+            e.synchronize()
+            times.append(s.elapsed_time(e) * 1e-3)
+    t = float(np.mean(times))
+    return t, bilinear_bytes(E, T, 7, 64, 16, 64), bilinear_flops(E, T, 7, 64, 16, 64)
+
+
+def pick_cpu_threads(fn):
+    """The reference is a chain of small torch CPU ops: using every hardware thread of a 100+ core host makes it
+    slower, not faster.  Time one call at a few thread counts (bounded) and keep the fastest."""
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    best, best_t = None, None
+    for n in [c for c in (8, 16, 32, 64) if c <= avail] or [avail]:
+        torch.set_num_threads(n)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+        if dt > 30:
+            break
+    torch.set_num_threads(best)
+    return best, avail
+
+
+def run_reference(args, kw, rank, world):
+    """CPU arm: the oracle port of the reference forward (torch CPU, all host threads) on rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import gemnet_oracle as go
+    from oracle import graph_oracle as gr
+    Rl, Zl = synthetic_molecules(args.batch, 1234)
+    t0 = time.perf_counter()
+    inputs = gr.to_torch_inputs(gr.build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]))
+    t_index = time.perf_counter() - t0
+    model = go.OracleGemNet(kw, go.synthetic_state_dict(kw, seed=1234))
+    threads, avail = pick_cpu_threads(lambda: model.predict(inputs))
+    for _ in range(args.warmup):
+        model.predict(inputs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.predict(inputs)
+    dt = time.perf_counter() - t0
+    val = args.batch * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "molecules_per_sec", "value": val, "unit": "molecules/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, kw, "cpu"),
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": threads, "host_cores": avail, "kind": "port",
+                         "sample": f"{args.steps} energy+force evaluations of the same {args.batch}-molecule batch "
+                                   f"(oracle/gemnet_oracle.py, torch CPU fp32; index build {t_index * 1e3:.0f} ms excluded)"},
+        "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, kw, where):
+    name = "GemNet-T" if kw["triplets_only"] else "GemNet-Q"
+    return {"workload": f"{name} energy+force inference (forces = -dE/dR), COLL-shaped synthetic batch={args.batch} "
+                        f"molecules/GPU, emb_size=128, cutoff 5 A",
+            "batch_per_gpu": args.batch, "l2": "flushed (256 MiB write) between timed iterations",
+            "weights": "seeded synthetic (random-init architecture weights)", "device": where}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="T", choices=["T", "Q"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--large-batch", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time the eager step instead of its CUDA-graph replay")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kw = dict(BASE_KW, triplets_only=(args.model == "T"))
+
+    if args.impl == "reference":
+        run_reference(args, kw, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gemnet_pytorch_b200 import GemNet, _lib, build_batch, graph
+    from oracle import gemnet_oracle as go  # weights generator + CPU baseline only
+
+    sd = go.synthetic_state_dict(kw, seed=1234)
+    model = GemNet(**kw)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+
+    Rl, Zl = synthetic_molecules(args.batch, 1234 + rank)
+    t0 = time.perf_counter()
+    host_inputs = build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"], pin_memory=True)
+    t_index = time.perf_counter() - t0
+    inputs = {k: v.to(dev) for k, v in host_inputs.items()}
+    plan = graph.get_plan(inputs, kw["triplets_only"])
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.zero_()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value): the whole energy+force step replayed as one CUDA graph
+    for _ in range(args.warmup):
+        model(inputs)
+    k0 = _lib.KERNEL_LAUNCHES[0]
+    model(inputs)
+    launches_per_step = _lib.KERNEL_LAUNCHES[0] - k0  # our kernels per step (the graph replays exactly these)
+    use_graph = not args.eager
+    step = model.make_graphed(inputs) if use_graph else (lambda: model(inputs))
+    for _ in range(args.warmup):
+        step()
+
+    def timed(fn):
+        evs = []
+        for _ in range(args.steps):
+            flush()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_dev = timed(step)
+    barrier()
+    clocks = sampler.stop()
+    t_eager = timed(lambda: model(inputs)) if use_graph else t_dev
+    launches = launches_per_step * args.steps
+
+    # ---------------- end-to-end timing: pinned host dict -> device -> forward -> E,F back on the host
+    h2d = sum(v.numel() * v.element_size() for v in host_inputs.values())
+    d2h = 0
+    for _ in range(max(2, args.warmup // 2)):
+        model.predict({k: v.to(dev, non_blocking=True) for k, v in host_inputs.items()})
+    barrier()
+    ev2 = []
+    for _ in range(args.steps):
+        flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step_in = {k: v.to(dev, non_blocking=True) for k, v in host_inputs.items()}
+        E_h, F_h = model.predict(step_in)  # includes the per-batch index plan and the D2H of E and F
+        e.record()
+        ev2.append((s, e))
+        d2h = E_h.numel() * 4 + F_h.numel() * 4
+    barrier()
+    t_e2e = sum(s.elapsed_time(e) for s, e in ev2) * 1e-3
+
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = tt.tolist()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tc_peak, peak_kind = peaks()
+    mols = args.batch * world * args.steps
+    line = {
+        "metric": "molecules_per_sec", "value": mols / t_dev, "unit": "molecules/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, kw, torch.cuda.get_device_name(dev)),
+        "clocks": clocks,
+        "e2e": {"value": mols / t_e2e, "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3,
+                "host_index_build_ms": t_index * 1e3},
+        "gpu_launches": int(launches),
+        "gpu_launches_per_step": launches_per_step,
+        "mode": "cuda-graph replay of the eager step" if use_graph else "eager",
+        "eager": {"value": mols / max(t_eager, 1e-12) if world == 1 else None, "ms_per_step": t_eager / args.steps * 1e3},
+        "graph": {"atoms": plan.n_atoms, "edges": plan.n_edges, "triplets": plan.n_triplets,
+                  "quadruplets": getattr(plan, "n_quads", 0)},
+    }
+
+    # ---------------- roofline of the dominant kernel (H7, triplet segmented bilinear)
+    t_k, bts, fl = time_bilinear(plan, dev, flush, 30)
+    line["roofline"] = {"kernel": "segbil_fwd_kernel<7,64,16,64> (H7 triplets, fp32 CUDA cores)", "bound": "hbm",
+                        "achieved": bts / t_k / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bts / t_k / 1e9 / hbm_peak,
+                        "traffic": None, "peak_kind": peak_kind, "bytes_per_launch": bts, "us_per_launch": t_k * 1e6,
+                        "tflops": fl / t_k / 1e12, "bytes_per_triplet": bts / max(plan.n_triplets, 1)}
+    if args.large_batch and world == 1:
+        Rb, Zb = synthetic_molecules(args.large_batch, 4321)
+        big = {k: v.to(dev) for k, v in build_batch(Rb, Zb, kw["cutoff"], kw["int_cutoff"], True).items()}
+        bplan = graph.GraphPlan(big, True)
+        t_k, bts, fl = time_bilinear(bplan, dev, flush, 10)
+        line["roofline_large"] = {"molecules": args.large_batch, "edges": bplan.n_edges, "triplets": bplan.n_triplets,
+                                  "bound": "hbm", "achieved": bts / t_k / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": bts / t_k / 1e9 / hbm_peak, "us_per_launch": t_k * 1e6,
+                                  "tflops": fl / t_k / 1e12}
+        del big, bplan
+
+    # ---------------- CPU baseline beside it (oracle port of the reference path, bounded sample)
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import graph_oracle as gr
+        cpu_inputs = gr.to_torch_inputs(gr.build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]))
+        orc = go.OracleGemNet(kw, sd)
+        threads, avail = pick_cpu_threads(lambda: orc.predict(cpu_inputs))
+        n_rep, t0 = 0, time.perf_counter()
+        while n_rep < 5 or (time.perf_counter() - t0 < 10 and n_rep < 40):
+            E_c, F_c = orc.predict(cpu_inputs)
+            n_rep += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": args.batch * n_rep / dt, "unit": "molecules/s",
+                                "cores": threads, "host_cores": avail, "kind": "port",
+                                "sample": f"{n_rep} energy+force evaluations of the same {args.batch}-molecule batch "
+                                          "with oracle/gemnet_oracle.py (torch CPU fp32 restatement of the reference)"}
+        # parity of the timed GPU result against the CPU result of the same batch
+        E_g, F_g = model.predict(inputs)
+        line["parity_vs_cpu"] = {"rel_dE": float((E_g - E_c).abs().max() / E_c.abs().max()),
+                                 "rel_dF": float((F_g - F_c).abs().max() / F_c.abs().max())}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,13 @@ _SIGNATURES = {
     "gemnet_molecule_sum_bwd": [_P, _P, _P, _I64, _I32, _I32, _P, _P],
     "gemnet_force_readout_fwd": [_P, _P, _P, _P, _I64, _I32, _P, _P],
     "gemnet_force_readout_bwd": [_P, _P, _P, _I64, _I32, _P, _P, _P, _P],
+    "gemnet_scaled_silu_fwd": [_P, _P, _F, _I64, _I32, _P, _P],
+    "gemnet_scaled_silu_bwd": [_P, _P, _F, _I64, _P, _P],
+    "gemnet_add_scale": [_P, _P, _P, _F, _I64, _P, _P],
+    "gemnet_mul_scale_fwd": [_P, _P, _F, _I64, _P, _P],
+    "gemnet_mul_scale_bwd": [_P, _P, _P, _F, _I64, _P, _P, _P],
+    "gemnet_gather_rows": [_P, _P, _I64, _I32, _P, _P],
+    "gemnet_segment_sum_rows": [_P, _P, _P, _I64, _I32, _P, _P],
     "gemnet_graph_build_host": [_P, _P, _I64, _D, _D, _I32, ctypes.POINTER(_P)],
     "gemnet_graph_size": [_P, ctypes.c_char_p],
     "gemnet_graph_copy_host": [_P, ctypes.c_char_p, _P],
@@ -82,7 +89,12 @@ def load():
     return lib
 
 
-def check(rc, what):
+# number of CUDA kernels launched through the C ABI since import (bench.py reports the per-step count)
+KERNEL_LAUNCHES = [0]
+
+
+def check(rc, what, kernels=1):
+    KERNEL_LAUNCHES[0] += kernels
     if rc != 0:
         msg = load().gemnet_last_error()
         raise GemnetB200Error(f"{what} failed: {msg.decode() if msg else 'unknown error'}")

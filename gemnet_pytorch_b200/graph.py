@@ -97,7 +97,9 @@ class GraphPlan:
         flags = []
         self.mol_rowptr, f = ops.csr_from_sorted(self.batch_seg, self.n_mol)
         flags.append(f)
-        self.atom_rowptr, self.atom_perm = ops.csr_by_key(self.id_a, self.n_atoms)
+        self.atom_rowptr, self.atom_perm = ops.csr_by_key(self.id_a, self.n_atoms)   # edges by target atom
+        self.src_rowptr, self.src_perm = ops.csr_by_key(self.id_c, self.n_atoms)     # edges by source atom
+        self.swap_rowptr, self.swap_perm = ops.csr_by_key(self.id_swap, self.n_edges)  # inverse of id_swap
 
         self.id3_reduce, self.id3_expand = i32("id3_reduce_ca"), i32("id3_expand_ba")
         self.n_triplets = int(self.id3_reduce.numel())
@@ -107,7 +109,8 @@ class GraphPlan:
         if not triplets_only:
             self.id4_reduce_ca = i32("id4_reduce_ca")
             self.id4_reduce_cab, self.id4_expand_abd = i32("id4_reduce_cab"), i32("id4_expand_abd")
-            self.id4_expand_intm_db64 = inputs["id4_expand_intm_db"]
+            self.id4_expand_intm_db = i32("id4_expand_intm_db")
+            self.intm_db_rowptr, self.intm_db_perm = ops.csr_by_key(self.id4_expand_intm_db, self.n_edges)
             self.n_quads = int(self.id4_reduce_ca.numel())
             self.rowptr4, f = ops.csr_from_sorted(self.id4_reduce_ca, self.n_edges)
             flags.append(f)

@@ -20,6 +20,12 @@ INV_SQRT_2 = 1 / (2.0 ** 0.5)
 INV_SQRT_3 = 1 / (3.0 ** 0.5)
 
 
+def _w(module, param):
+    """Parameters of the custom kernels: in eval mode they are constants (forces only need dE/dR), so their
+    (expensive, reduction-over-all-edges) gradients are not computed; in training mode they are differentiated."""
+    return param if (module.training and torch.is_grad_enabled()) else param.detach()
+
+
 # ----------------------------------------------------------------------------- init (initializers.py:4-40)
 def _standardize(kernel):
     eps = 1e-6
@@ -44,7 +50,7 @@ class ScaledSiLU(torch.nn.Module):
         self.scale_factor = 1 / 0.6
 
     def forward(self, x):
-        return torch.nn.functional.silu(x) * self.scale_factor
+        return ops.scaled_silu(x)  # silu(x) / 0.6 in one kernel (fwd) / one kernel (bwd)
 
 
 class Dense(torch.nn.Module):
@@ -79,7 +85,14 @@ class ResidualLayer(torch.nn.Module):
             *[Dense(units, units, activation=activation, bias=False) for _ in range(nLayers)])
 
     def forward(self, inputs):
-        return (inputs + self.dense_mlp(inputs)) * INV_SQRT_2
+        x = inputs
+        for layer in self.dense_mlp[:-1]:
+            x = layer(x)
+        last = self.dense_mlp[-1]
+        z = last.linear(x)
+        if isinstance(last._activation, ScaledSiLU):
+            return ops.residual_tail(z, inputs, INV_SQRT_2)  # (inputs + silu(z)/0.6) / sqrt(2), one kernel
+        return ops.add_scale(INV_SQRT_2, inputs, z)
 
 
 class AtomEmbedding(torch.nn.Module):
@@ -98,9 +111,19 @@ class EdgeEmbedding(torch.nn.Module):
         super().__init__()
         self.dense = Dense(2 * atom_features + edge_features, out_features, activation=activation, bias=False)
 
-    def forward(self, h, m_rbf, idnb_a, idnb_c):
-        # embedding_block.py:70-74 (call sites pass (id_c, id_a) for (idnb_a, idnb_c))
-        return self.dense(torch.cat([h[idnb_a], h[idnb_c], m_rbf], dim=-1))
+    def forward(self, h, m_rbf, plan):
+        """dense(cat([h[id_c], h[id_a], m_rbf]))  (embedding_block.py:70-74; the call sites pass (id_c, id_a) for
+        the parameters named (idnb_a, idnb_c)).  Evaluated without the concatenation: the weight is split into its
+        three column blocks, the two atom blocks are applied on the nAtoms rows (10x fewer than nEdges) and gathered:
+            z[e] = (h W_1^T)[id_c[e]] + (h W_2^T)[id_a[e]] + m_rbf[e] W_3^T."""
+        W = self.dense.linear.weight
+        A = h.shape[1]
+        p_c = torch.nn.functional.linear(h, W[:, :A])
+        p_a = torch.nn.functional.linear(h, W[:, A:2 * A])
+        y = torch.nn.functional.linear(m_rbf, W[:, 2 * A:])
+        z = ops.add_scale(1.0, y, ops.gather_rows(p_c, plan.id_c, plan.src_perm, plan.src_rowptr),
+                          ops.gather_rows(p_a, plan.id_a, plan.atom_perm, plan.atom_rowptr))
+        return self.dense._activation(z)
 
 
 # ----------------------------------------------------------------------------- scaling (scaling.py:150-174)
@@ -146,7 +169,7 @@ class BesselBasisLayer(torch.nn.Module):
             data=torch.Tensor(np.pi * np.arange(1, num_radial + 1, dtype=np.float32)), requires_grad=True)
 
     def forward(self, d):
-        return ops.bessel_rbf(d, self.frequencies, self.cutoff, self.p)
+        return ops.bessel_rbf(d, _w(self, self.frequencies), self.cutoff, self.p)
 
 
 class SphericalBasisLayer(torch.nn.Module):
@@ -182,7 +205,7 @@ class EfficientInteractionDownProjection(torch.nn.Module):
 
     def forward(self, rad, l_of_s):
         """rad (E, L, R) -> rbf_W1 (E, I, S)   (efficient.py:41-57)"""
-        return ops.down_projection(rad, self.weight, l_of_s)
+        return ops.down_projection(rad, _w(self, self.weight), l_of_s)
 
 
 class EfficientInteractionBilinear(torch.nn.Module):
@@ -198,7 +221,7 @@ class EfficientInteractionBilinear(torch.nn.Module):
 
     def forward(self, rbf_W1, sph, x, expand, rowptr, scale=1.0, algo=0):
         """x: UN-gathered (n_x, C) table; expand/rowptr: CSR of the units (efficient.py:159-189 + gather + scale)."""
-        return ops.segmented_bilinear(x, sph, rbf_W1, self.weight, expand, rowptr, scale, algo)
+        return ops.segmented_bilinear(x, sph, rbf_W1, _w(self, self.weight), expand, rowptr, scale, algo)
 
 
 # ----------------------------------------------------------------------------- atom_update_block.py
@@ -290,13 +313,13 @@ class TripletInteraction(torch.nn.Module):
 
     def forward(self, m, rbf3, rbf_W1, sph3, plan, algo=0):
         x_ba = self.dense_ba(m)
-        x_ba = self.scale_rbf(x_ba, x_ba * self.mlp_rbf(rbf3))
+        x_ba = ops.mul_scale(x_ba, self.mlp_rbf(rbf3), self.scale_rbf.value())
         x_ba = self.down_projection(x_ba)  # (E, emb_size_trip) — NOT gathered: the kernel gathers
         x = self.mlp_cbf(rbf_W1, sph3, x_ba, plan.id3_expand, plan.rowptr3, scale=self.scale_cbf_sum.value(),
                          algo=algo)
         x_ca = self.up_projection_ca(x)
-        x_ac = self.up_projection_ac(x)[plan.id_swap64]
-        return (x_ca + x_ac) * INV_SQRT_2
+        x_ac = ops.gather_rows(self.up_projection_ac(x), plan.id_swap, plan.swap_perm, plan.swap_rowptr)
+        return ops.add_scale(INV_SQRT_2, x_ca, x_ac)
 
 
 class QuadrupletInteraction(torch.nn.Module):
@@ -317,16 +340,16 @@ class QuadrupletInteraction(torch.nn.Module):
 
     def forward(self, m, rbf4, cbf4, rbf_W1, ylm, plan, algo=0):
         x_db = self.dense_db(m)
-        x_db = self.scale_rbf(x_db, x_db * self.mlp_rbf(rbf4))
+        x_db = ops.mul_scale(x_db, self.mlp_rbf(rbf4), self.scale_rbf.value())
         x_db = self.down_projection(x_db)
-        x_db = x_db[plan.id4_expand_intm_db64]  # (intmTriplets, emb_size_quad)
-        x_db = self.scale_cbf(x_db, x_db * self.mlp_cbf(cbf4))
+        x_db = ops.gather_rows(x_db, plan.id4_expand_intm_db, plan.intm_db_perm, plan.intm_db_rowptr)  # (M, C4)
+        x_db = ops.mul_scale(x_db, self.mlp_cbf(cbf4), self.scale_cbf.value())
         # second gather (id4_expand_abd) happens inside the kernel
         x = self.mlp_sbf(rbf_W1, ylm, x_db, plan.id4_expand_abd, plan.rowptr4, scale=self.scale_sbf_sum.value(),
                          algo=algo)
         x_ca = self.up_projection_ca(x)
-        x_ac = self.up_projection_ac(x)[plan.id_swap64]
-        return (x_ca + x_ac) * INV_SQRT_2
+        x_ac = ops.gather_rows(self.up_projection_ac(x), plan.id_swap, plan.swap_perm, plan.swap_rowptr)
+        return ops.add_scale(INV_SQRT_2, x_ca, x_ac)
 
 
 class InteractionBlock(torch.nn.Module):
@@ -363,22 +386,22 @@ class InteractionBlock(torch.nn.Module):
         x_ca_skip = self.dense_ca(m)
         if self.triplets_only:
             x3 = self.trip_interaction(m, basis["rbf3"], basis["rbf_W1_3"], basis["sph3"], plan, algo)
-            x = (x_ca_skip + x3) * INV_SQRT_2
+            x = ops.add_scale(INV_SQRT_2, x_ca_skip, x3)
         else:
             x4 = self.quad_interaction(m, basis["rbf4"], basis["cbf4"], basis["rbf_W1_4"], basis["ylm"], plan, algo)
             x3 = self.trip_interaction(m, basis["rbf3"], basis["rbf_W1_3"], basis["sph3"], plan, algo)
-            x = (x_ca_skip + x3 + x4) * INV_SQRT_3
+            x = ops.add_scale(INV_SQRT_3, x_ca_skip, x3, x4)
         for layer in self.layers_before_skip:
             x = layer(x)
-        m = (m + x) * INV_SQRT_2
+        m = ops.add_scale(INV_SQRT_2, m, x)
         for layer in self.layers_after_skip:
             m = layer(m)
         h2 = self.atom_update(h, m, basis["rbf_h"], plan)
-        h = (h + h2) * INV_SQRT_2
-        m2 = self.concat_layer(h, m, plan.id_c64, plan.id_a64)
+        h = ops.add_scale(INV_SQRT_2, h, h2)
+        m2 = self.concat_layer(h, m, plan)
         for layer in self.residual_m:
             m2 = layer(m2)
-        m = (m + m2) * INV_SQRT_2
+        m = ops.add_scale(INV_SQRT_2, m, m2)
         return h, m
 
 

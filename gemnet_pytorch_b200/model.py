@@ -133,7 +133,7 @@ class GemNet(torch.nn.Module):
         sph3 = ops.triplet_sph(R, plan.id_c, plan.id_a, plan.id3_reduce, plan.id3_expand, S)  # H2+H4 (T, S)
 
         h = self.atom_emb(Z)
-        m = self.edge_emb(h, rbf, plan.id_c64, plan.id_a64)
+        m = self.edge_emb(h, rbf, plan)
 
         if not self.triplets_only:
             basis["rbf4"] = self.mlp_rbf4(rbf)
@@ -182,8 +182,40 @@ class GemNet(torch.nn.Module):
         E, F = self(inputs)
         return E.detach().cpu(), F.detach().cpu()
 
+    def make_graphed(self, inputs, warmup=3):
+        """Capture the whole energy+force evaluation of ONE batch topology (forward, and the autograd backward that
+        produces the forces) into a CUDA graph.  Batch-64 GemNet is launch-latency bound; replaying
+        ~1000 kernels as one graph removes the per-launch host cost.  Returns a GraphedGemNet whose call replays
+        the graph on the static device buffers of `inputs` (new coordinates of the same topology can be copied into
+        `inputs["R"]` first)."""
+        return GraphedGemNet(self, inputs, warmup)
+
     def load_weights(self, path):
         self.load_state_dict(torch.load(path))
 
     def save_weights(self, path):
         torch.save(self.state_dict(), path)
+
+
+class GraphedGemNet:
+    """CUDA-graph replay of GemNet.forward for a fixed batch topology (inference / force evaluation)."""
+
+    def __init__(self, model, inputs, warmup=3):
+        assert not model.training, "graph capture is for inference (model.eval())"
+        self.model, self.inputs = model, inputs
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                model(inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.E, self.F = model(inputs)
+
+    def __call__(self, R=None):
+        if R is not None:
+            self.inputs["R"].copy_(R)
+        self.graph.replay()
+        return self.E, self.F

@@ -60,7 +60,7 @@ def csr_by_key(ids, n_rows):
     perm = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
     ws = torch.empty(n_rows + 1, dtype=torch.int32, device=ids.device)
     _check(_L().gemnet_csr_by_key(_p(ids), ids.numel(), n_rows, _p(rowptr), _p(perm), _p(ws), _stream()),
-           "gemnet_csr_by_key")
+           "gemnet_csr_by_key", kernels=5)
     return rowptr, perm
 
 
@@ -325,7 +325,8 @@ class _DownProj(Function):
         g_rad = torch.empty_like(rad) if ctx.needs_input_grad[0] else None
         g_Wd = torch.zeros_like(Wd) if ctx.needs_input_grad[1] else None
         _check(_L().gemnet_downproj_bwd(_p(rad), _p(Wd), _p(l_of_s), E, L, nR, S, I, _p(g), _p(g_rad), _p(g_Wd),
-                                        _stream()), "gemnet_downproj_bwd")
+                                        _stream()), "gemnet_downproj_bwd",
+               kernels=int(g_rad is not None) + int(g_Wd is not None))
         return g_rad, g_Wd, None
 
 
@@ -402,7 +403,7 @@ class _EdgeToAtom(Function):
         had = torch.empty_like(m) if had_scale is not None else None
         _check(_L().gemnet_edge_to_atom_fwd(_p(m), _p(r), _p(_i32(perm)), _p(_i32(rowptr)), A, E, F, scale, _p(out),
                                             0.0 if had_scale is None else had_scale, _p(had), _stream()),
-               "gemnet_edge_to_atom_fwd")
+               "gemnet_edge_to_atom_fwd", kernels=1 if had is None else 2)
         ctx.save_for_backward(m, r, id_a)
         ctx.cfg = (scale, had_scale)
         if had is None:
@@ -488,3 +489,143 @@ class _ForceReadout(Function):
 def force_readout(F_ca, V, id_a, perm, rowptr):
     """F_j = scatter_add(F_ca[:, :, None] * V_ca[:, None, :], id_a) (gemnet.py:594-597): (A, T, 3)."""
     return _ForceReadout.apply(F_ca, V, id_a, perm, rowptr)
+
+
+# ----------------------------------------------------------------------------- N1: fused pointwise + gathers
+def _n4(t):
+    assert t.numel() % 4 == 0, "fused pointwise kernels need a multiple of 4 elements"
+    return t.numel()
+
+
+class _ScaledSiLU(Function):
+    @staticmethod
+    def forward(ctx, z):
+        z = _f32(z)
+        out = torch.empty_like(z)
+        _check(_L().gemnet_scaled_silu_fwd(_p(z), None, 1.0, _n4(z), 0, _p(out), _stream()), "gemnet_scaled_silu_fwd")
+        ctx.save_for_backward(z)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (z,) = ctx.saved_tensors
+        g = _f32(g)
+        gz = torch.empty_like(z)
+        _check(_L().gemnet_scaled_silu_bwd(_p(z), _p(g), 1.0, z.numel(), _p(gz), _stream()), "gemnet_scaled_silu_bwd")
+        return gz
+
+
+def scaled_silu(z):
+    """ScaledSiLU (base_layers.py:51-58): silu(z) / 0.6 in one kernel."""
+    return _ScaledSiLU.apply(z)
+
+
+class _ResidualTail(Function):
+    @staticmethod
+    def forward(ctx, z, x, s):
+        z, x = _f32(z), _f32(x)
+        out = torch.empty_like(z)
+        _check(_L().gemnet_scaled_silu_fwd(_p(z), _p(x), s, _n4(z), 1, _p(out), _stream()), "gemnet_scaled_silu_fwd")
+        ctx.save_for_backward(z)
+        ctx.s = s
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (z,) = ctx.saved_tensors
+        g = _f32(g)
+        gz = torch.empty_like(z)
+        _check(_L().gemnet_scaled_silu_bwd(_p(z), _p(g), ctx.s, z.numel(), _p(gz), _stream()), "gemnet_scaled_silu_bwd")
+        gx = None
+        if ctx.needs_input_grad[1]:
+            gx = torch.empty_like(z)
+            _check(_L().gemnet_add_scale(_p(g), None, None, ctx.s, z.numel(), _p(gx), _stream()), "gemnet_add_scale")
+        return gz, gx, None
+
+
+def residual_tail(z, x, s):
+    """(x + silu(z)/0.6) * s — the last activation + skip + 1/sqrt(2) of ResidualLayer (base_layers.py:86-89)."""
+    return _ResidualTail.apply(z, x, float(s))
+
+
+class _AddScale(Function):
+    @staticmethod
+    def forward(ctx, s, a, b, c):
+        a, b, c = _f32(a), _f32(b), _f32(c)
+        out = torch.empty_like(a)
+        _check(_L().gemnet_add_scale(_p(a), _p(b), _p(c), s, _n4(a), _p(out), _stream()), "gemnet_add_scale")
+        ctx.s = s
+        ctx.has = (b is not None, c is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = _f32(g)
+        gs = torch.empty_like(g)
+        _check(_L().gemnet_add_scale(_p(g), None, None, ctx.s, g.numel(), _p(gs), _stream()), "gemnet_add_scale")
+        return None, gs, gs if ctx.has[0] else None, gs if ctx.has[1] else None
+
+
+def add_scale(s, a, b=None, c=None):
+    """(a [+ b [+ c]]) * s — skip connections with their 1/sqrt(2), 1/sqrt(3) (interaction_block.py:202-233)."""
+    return _AddScale.apply(float(s), a, b, c)
+
+
+class _MulScale(Function):
+    @staticmethod
+    def forward(ctx, a, b, s):
+        a, b = _f32(a), _f32(b)
+        out = torch.empty_like(a)
+        _check(_L().gemnet_mul_scale_fwd(_p(a), _p(b), s, _n4(a), _p(out), _stream()), "gemnet_mul_scale_fwd")
+        ctx.save_for_backward(a, b)
+        ctx.s = s
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = _f32(g)
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        if ga is not None or gb is not None:
+            _check(_L().gemnet_mul_scale_bwd(_p(a), _p(b), _p(g), ctx.s, a.numel(), _p(ga), _p(gb), _stream()),
+                   "gemnet_mul_scale_bwd")
+        return ga, gb, None
+
+
+def mul_scale(a, b, s=1.0):
+    """a * b * s — Hadamard product with its ScalingFactor (interaction_block.py:661-664; scaling.py:170-174)."""
+    return _MulScale.apply(a, b, float(s))
+
+
+class _GatherRows(Function):
+    @staticmethod
+    def forward(ctx, x, idx, perm, rowptr):
+        x = _f32(x)
+        n, F = idx.numel(), x.shape[1]
+        out = torch.empty(n, F, dtype=torch.float32, device=x.device)
+        _check(_L().gemnet_gather_rows(_p(x), _p(_i32(idx)), n, F, _p(out), _stream()), "gemnet_gather_rows")
+        ctx.save_for_backward(perm, rowptr)
+        ctx.shape = (x.shape[0], F)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        perm, rowptr = ctx.saved_tensors
+        g = _f32(g)
+        n_rows, F = ctx.shape
+        gx = torch.empty(n_rows, F, dtype=torch.float32, device=g.device)
+        _check(_L().gemnet_segment_sum_rows(_p(g), _p(_i32(perm)), _p(_i32(rowptr)), n_rows, F, _p(gx), _stream()),
+               "gemnet_segment_sum_rows")
+        return gx, None, None, None
+
+
+def gather_rows(x, idx, perm, rowptr):
+    """x[idx] with a CSR (perm, rowptr = csr_by_key(idx, x.shape[0])) so that the backward is a deterministic
+    segment sum instead of ATen's sort + atomics index_put (embedding_block.py:70-71, interaction_block.py:693)."""
+    return _GatherRows.apply(x, idx, perm, rowptr)

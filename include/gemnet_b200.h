@@ -201,6 +201,27 @@ int gemnet_force_readout_bwd(const float* F_ca, const float* V, const int32_t* i
                              int32_t n_targets, const float* g_F_atom, float* g_F_ca, float* g_V, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N1 (first step): fused pointwise kernels around the dense layers and gathers with a deterministic backward.
+ *   scaled_silu  mode 0: out = silu(z)/0.6                       ScaledSiLU (base_layers.py:51-58)
+ *                mode 1: out = (x + silu(z)/0.6) * s             tail of ResidualLayer (base_layers.py:86-89)
+ *   scaled_silu_bwd      gz = g * s * d/dz[silu(z)/0.6]          (the x-branch gradient of mode 1 is g*s: add_scale)
+ *   add_scale            out = (a [+ b [+ c]]) * s               skip connections (interaction_block.py:202-233)
+ *   mul_scale            out = a * b * s                         Hadamard + ScalingFactor (interaction_block.py:661-664)
+ *   gather_rows          out[j,:] = x[idx[j],:]                  h[id_a], h[id_c], x[id_swap] (embedding_block.py:70-71)
+ *   segment_sum_rows     out[r,:] = sum_k src[perm[k],:] over the CSR row r — the gather's backward, no atomics
+ * n = number of floats, must be a multiple of 4; pointers 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_scaled_silu_fwd(const float* z, const float* x, float s, int64_t n, int32_t mode, float* out, void* stream);
+int gemnet_scaled_silu_bwd(const float* z, const float* g, float s, int64_t n, float* gz, void* stream);
+int gemnet_add_scale(const float* a, const float* b, const float* c, float s, int64_t n, float* out, void* stream);
+int gemnet_mul_scale_fwd(const float* a, const float* b, float s, int64_t n, float* out, void* stream);
+int gemnet_mul_scale_bwd(const float* a, const float* b, const float* g, float s, int64_t n, float* ga, float* gb,
+                         void* stream);
+int gemnet_gather_rows(const float* x, const int32_t* idx, int64_t n, int32_t F, float* out, void* stream);
+int gemnet_segment_sum_rows(const float* src, const int32_t* perm, const int32_t* rowptr, int64_t n_rows, int32_t F,
+                            float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * H0  host index builder: DataContainer.__getitem__ / get_triplets / get_quadruplets
  *     (gemnet/training/data_container.py:156-408, 411-489).  HOST function, native C++.
  * Input: molecules concatenated, R_host float64 (n_atoms,3), n_per_mol int32[n_mol].

@@ -363,3 +363,38 @@ def test_molecule_sum_and_force_readout(ops, dev):
         gF, gV = kernel_grads(lambda f, v: ops.force_readout(f, v, gpu["id_a"], perm, rowptr), [Fca, V], g)
         gF0, gV0 = oracle_grads(lambda f, v: go.scatter_sum(f[:, :, None] * v[:, None, :], cpu["id_a"], A), [Fca, V], g)
         assert relerr(gF, gF0) < 1e-6 and relerr(gV, gV0) < 1e-6
+
+
+# ----------------------------------------------------------------------------- N1: fused pointwise + gathers
+def test_fused_pointwise_and_gathers(ops, dev):
+    torch.manual_seed(8)
+    z, x, c = (torch.randn(1000, 128, device=dev) * 3 for _ in range(3))
+    ssilu = lambda t: torch.nn.functional.silu(t) / 0.6  # noqa: E731
+    s = 0.7071
+    cases = [
+        (lambda a: ops.scaled_silu(a), lambda a: ssilu(a), [z]),
+        (lambda a, b: ops.residual_tail(a, b, s), lambda a, b: (b + ssilu(a)) * s, [z, x]),
+        (lambda a, b: ops.add_scale(s, a, b), lambda a, b: (a + b) * s, [z, x]),
+        (lambda a, b, d: ops.add_scale(s, a, b, d), lambda a, b, d: (a + b + d) * s, [z, x, c]),
+        (lambda a, b: ops.mul_scale(a, b, 2.5), lambda a, b: a * b * 2.5, [z, x]),
+    ]
+    for kern, ref, ins in cases:
+        out = kern(*ins)
+        assert relerr(out, ref(*[t.double().cpu() for t in ins])) < 1e-6
+        g = torch.randn_like(out)
+        got = kernel_grads(kern, ins, g)
+        want = oracle_grads(ref, ins, g)
+        for a, b in zip(got, want):
+            assert relerr(a, b) < 1e-6
+    # gather with CSR backward == index_select / index_add, bitwise deterministic
+    idx = torch.randint(0, 300, (5000,), device=dev, dtype=torch.int32)
+    rowptr, perm = ops.csr_by_key(idx, 300)
+    src = torch.randn(300, 64, device=dev)
+    out = ops.gather_rows(src, idx, perm, rowptr)
+    assert torch.equal(out, src[idx.long()])
+    g = torch.randn_like(out)
+    (gs,) = kernel_grads(lambda t: ops.gather_rows(t, idx, perm, rowptr), [src], g)
+    (gs0,) = oracle_grads(lambda t: t[idx.long().cpu()], [src], g)
+    assert relerr(gs, gs0) < 1e-6
+    (gs2,) = kernel_grads(lambda t: ops.gather_rows(t, idx, perm, rowptr), [src], g)
+    assert torch.equal(gs, gs2)
