@@ -310,6 +310,12 @@ static int launch_bwd(const float* x, const int32_t* expand, const int32_t* rowp
   return check_launch("gemnet_segbilinear_bwd");
 }
 
+// tcgen05 path (segbilinear_tc.cu)
+int64_t segbil_tc_workspace_bytes();
+int launch_segbil_fwd_tc(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                         const float* rbf_W1, const float* W, float scale, int64_t n_edges, float* out,
+                         void* workspace, cudaStream_t st);
+
 using TripCfg = SegCfg<7, 64, 16, 64, 16>;
 using QuadCfg = SegCfg<49, 32, 32, 32, 32>;
 
@@ -319,7 +325,8 @@ using namespace gemnet;
 
 GEMNET_API int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O,
                                                       int32_t algo, int32_t backward) {
-  (void)n_edges; (void)S; (void)C; (void)I; (void)O; (void)algo; (void)backward;
+  (void)n_edges;
+  if (algo == 1 && !backward && S == 7 && C == 64 && I == 16 && O == 64) return segbil_tc_workspace_bytes();
   return 0;
 }
 
@@ -333,15 +340,16 @@ GEMNET_API int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, con
                                       const float* rbf_W1, const float* W, float scale, int64_t n_edges,
                                       int64_t n_units, int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo,
                                       float* out, void* workspace, void* stream) {
-  (void)workspace;
   GEMNET_REQUIRE(n_edges >= 0 && n_units >= 0, "negative size");
-  GEMNET_REQUIRE(algo == 0, "algo 1 (tcgen05) is not built into this library version");
+  GEMNET_REQUIRE(algo == 0 || algo == 1, "algo must be 0 (fp32 CUDA cores) or 1 (tcgen05)");
   const int sid = shape_id(S, C, I, O);
   GEMNET_REQUIRE(sid != 0, "unsupported (S,C,I,O): built for (7,64,16,64) and (49,32,32,32)");
+  GEMNET_REQUIRE(algo == 0 || sid == 1, "algo 1 (tcgen05) is built for the triplet shape (7,64,16,64) only");
   if (n_edges == 0) return 0;
   GEMNET_REQUIRE(rowptr && rbf_W1 && W && out && (n_units == 0 || (x && expand && sph)), "null pointer");
   GEMNET_REQUIRE(((uintptr_t)W | (uintptr_t)out) % 16 == 0, "W/out must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
+  if (algo == 1) return launch_segbil_fwd_tc(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, workspace, st);
   if (sid == 1) return launch_fwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, st);
   return launch_fwd<QuadCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, st);
 }
@@ -352,8 +360,8 @@ GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, con
                                       const float* g_out, float* g_x, float* g_sph, float* g_rbf_W1, float* g_W,
                                       void* workspace, void* stream) {
   (void)workspace;
+  (void)algo;  // the backward runs on the fp32 CUDA-core kernel for every algo in this library version
   GEMNET_REQUIRE(n_edges >= 0 && n_units >= 0, "negative size");
-  GEMNET_REQUIRE(algo == 0, "algo 1 (tcgen05) is not built into this library version");
   GEMNET_REQUIRE(g_W == nullptr, "g_W is computed by the host wrapper in this library version; pass NULL");
   const int sid = shape_id(S, C, I, O);
   GEMNET_REQUIRE(sid != 0, "unsupported (S,C,I,O): built for (7,64,16,64) and (49,32,32,32)");

@@ -1,0 +1,367 @@
+// H7 forward on the 5th-generation tensor cores (algo 1): tcgen05.mma with the accumulator in TMEM.
+//
+//   out[e,:] = scale * B_e (1 x K) @ W' (K x O),   K = C*I = 1024, O = 64
+//   B_e[k = c*I + i] = sum_s rbf_W1[e,i,s] * A_e[s,c],   A_e[s,c] = sum_{t in seg(e)} sph[t,s] * x[expand[t], c]
+//
+// Persistent warp-specialised kernel, one CTA per SM, tile = 128 target edges (UMMA M = 128, N = 64):
+//   warps 0-15  (512 threads) PRODUCERS: thread (edge el = tid/4, column cl = tid%4) owns one x-column per K-chunk.
+//               A chunk is 4 columns c = 4*chunk .. 4*chunk+3, i.e. 64 consecutive k.  The thread gathers its column
+//               over the CSR segment (phase 1), contracts with rbf_W1 from shared memory (phase 2) and writes its 16
+//               k-values, split into bf16 hi + bf16 lo, into the K-major SWIZZLE_128B A-operand tile of the stage.
+//   warp 16     lane 0 issues tcgen05.mma: D += Ahi*Whi + Ahi*Wlo + Alo*Whi (bf16x3: the dropped lo*lo term is
+//               2^-16 relative, so the result is fp32-accurate: parity mode, not a reduced-precision mode).
+//   warp 17     lane 0 streams the pre-packed (already swizzled) W chunk image with one cp.async.bulk per stage.
+//   warps 0-3   also run the epilogue: tcgen05.ld of the 128 x 64 fp32 accumulator, scale, vectorised store.
+// Stage ring (kStages): {A_hi 16 KB, A_lo 16 KB, W_hi 8 KB, W_lo 8 KB}; full/empty mbarriers; tcgen05.commit frees
+// a stage and, after the 16th chunk, publishes the accumulator to the epilogue warps.
+//
+// Shapes: only the published triplet shape (S,C,I,O) = (7,64,16,64).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace gemnet {
+namespace tc {
+
+constexpr int S = 7, C = 64, I = 16, O = 64;
+constexpr int K = C * I;                 // 1024
+constexpr int TILE_M = 128;
+constexpr int KC = 64;                   // k per chunk (4 columns of x times I)
+constexpr int NCHUNK = K / KC;           // 16
+constexpr int kStages = 2;
+constexpr int PRODUCER_WARPS = 16;
+constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;  // 512
+constexpr int THREADS = PRODUCER_THREADS + 64;         // + MMA warp + loader warp
+
+constexpr int A_TILE_BYTES = TILE_M * KC * 2;          // 16384 (bf16)
+constexpr int W_TILE_BYTES = O * KC * 2;               // 8192
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;  // 49152
+constexpr int RW_LD = I * 8 + 4;                       // padded row of rbf_W1 in smem (floats): conflict-free float4 reads
+constexpr int RW_BYTES = TILE_M * RW_LD * 4;           // 67584
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + RW_BYTES + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 64;
+
+// packed weight image: [chunk][hi|lo][o][k_local] bf16, rows already XOR-swizzled (SWIZZLE_128B)
+constexpr int WPACK_BYTES = NCHUNK * 2 * W_TILE_BYTES;  // 262144
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 26)) __trap();  // never hang the device on a protocol bug
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 x bf16 -> fp32), single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_128B operand tile (rows of 128 bytes, 8-row groups of 1024 bytes): shared-memory matrix descriptor
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);   // start address
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), 16 B units
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, N = 64, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------- weight packing
+// Wp[chunk][h][o][chunk16 ^ (o & 7)][8 bf16]  with  k_local = cl*16 + i  <->  W[c = 4*chunk + cl][i][o]
+__global__ void pack_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (chunk, o, k_local)
+  if (idx >= NCHUNK * O * KC) return;
+  const int kl = idx % KC, o = (idx / KC) % O, chunk = idx / (KC * O);
+  const int cl = kl / I, i = kl % I;
+  const int c = chunk * (KC / I) + cl;
+  __nv_bfloat16 hi, lo;
+  split_bf16(W[((int64_t)c * I + i) * O + o], hi, lo);
+  const int j = kl / 8;                       // 16-byte chunk within the 128-byte row
+  const int phys = o * KC + ((j ^ (o & 7)) * 8) + (kl % 8);
+  Wp[(int64_t)(chunk * 2 + 0) * (O * KC) + phys] = hi;
+  Wp[(int64_t)(chunk * 2 + 1) * (O * KC) + phys] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(THREADS, 1)
+segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ expand,
+                     const int32_t* __restrict__ rowptr, const float* __restrict__ sph,
+                     const float* __restrict__ rbf_W1, const __nv_bfloat16* __restrict__ Wp, float scale,
+                     int64_t n_edges, int n_tiles, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t stage_base = base;                                    // kStages * STAGE_BYTES
+  float* rw_s = reinterpret_cast<float*>(sm + kStages * STAGE_BYTES);  // [TILE_M][RW_LD]
+  const uint32_t bar_base = base + kStages * STAGE_BYTES + RW_BYTES;
+  // barriers: full[kStages], empty[kStages], acc_full, acc_empty, then the TMEM address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t acc_full = bar_base + 8u * (2 * kStages);
+  const uint32_t acc_empty = bar_base + 8u * (2 * kStages + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kStages * STAGE_BYTES + RW_BYTES +
+                                                                           8 * (2 * kStages + 2));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), PRODUCER_WARPS + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == PRODUCER_WARPS) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < PRODUCER_WARPS) {
+    // ============================================================ producers (+ epilogue on warps 0-3)
+    const int el = tid >> 2, cl = tid & 3;
+    uint32_t g = 0;  // global chunk counter (stage ring position)
+    for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int64_t e0 = (int64_t)tile * TILE_M;
+      // stage rbf_W1 of the tile: rw_s[el][i][s] (s padded to 8)
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");  // previous tile's readers are done
+      for (int idx = tid; idx < TILE_M * I * S; idx += PRODUCER_THREADS) {
+        const int r = idx / (I * S), rem = idx - r * (I * S);
+        const int i = rem / S, s = rem - i * S;
+        const int64_t e = e0 + r;
+        rw_s[r * RW_LD + i * 8 + s] = e < n_edges ? __ldg(rbf_W1 + e * (I * S) + rem) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
+
+      const int64_t e = e0 + el;
+      const bool live = e < n_edges;
+      const int32_t beg = live ? __ldg(rowptr + e) : 0, end = live ? __ldg(rowptr + e + 1) : 0;
+      const float* rw = rw_s + el * RW_LD;
+
+      for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
+        const int stage = g % kStages;
+        const uint32_t parity = (g / kStages) & 1u;
+        // phase 1: A[s] for column c = 4*chunk + cl
+        float A[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) A[s] = 0.f;
+        const int c = chunk * 4 + cl;
+        for (int32_t t = beg; t < end; ++t) {
+          const float xv = __ldg(x + (int64_t)__ldg(expand + t) * C + c);
+          const float* sp = sph + (int64_t)t * S;
+#pragma unroll
+          for (int s = 0; s < S; ++s) A[s] = fmaf(__ldg(sp + s), xv, A[s]);
+        }
+        // phase 2: 16 k-values of this thread, bf16 hi/lo
+        uint32_t hi_w[8], lo_w[8];
+#pragma unroll
+        for (int i2 = 0; i2 < I; i2 += 2) {
+          float b[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 w0 = *reinterpret_cast<const float4*>(rw + (i2 + u) * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(rw + (i2 + u) * 8 + 4);
+            b[u] = w0.x * A[0] + w0.y * A[1] + w0.z * A[2] + w0.w * A[3] + w1.x * A[4] + w1.y * A[5] + w1.z * A[6];
+          }
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(b[0], h0, l0);
+          split_bf16(b[1], h1, l1);
+          hi_w[i2 / 2] = pack2(h0, h1);
+          lo_w[i2 / 2] = pack2(l0, l1);
+        }
+        // wait until the MMA has drained this stage, then write 2 x 16 B (hi) and 2 x 16 B (lo) into row el
+        mbar_wait(empty_bar(stage), parity ^ 1u);
+        uint8_t* a_hi = sm + stage * STAGE_BYTES;
+        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+        const int j0 = cl * 2;
+        const uint32_t off0 = el * 128 + (((j0) ^ (el & 7)) << 4);
+        const uint32_t off1 = el * 128 + (((j0 + 1) ^ (el & 7)) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off0) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+        *reinterpret_cast<uint4*>(a_hi + off1) = make_uint4(hi_w[4], hi_w[5], hi_w[6], hi_w[7]);
+        *reinterpret_cast<uint4*>(a_lo + off0) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+        *reinterpret_cast<uint4*>(a_lo + off1) = make_uint4(lo_w[4], lo_w[5], lo_w[6], lo_w[7]);
+        fence_proxy_async();  // make the generic-proxy writes visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+      }
+
+      if (warp < 4) {
+        // ---------------- epilogue: TMEM lane = edge row of this thread (tid < 128)
+        mbar_wait(acc_full, (uint32_t)it & 1u);
+        tc_fence_after();
+        const int64_t er = e0 + tid;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + half * 32, r);
+          if (er < n_edges) {
+            float4* dst = reinterpret_cast<float4*>(out + er * O + half * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              dst[q] = make_float4(__uint_as_float(r[4 * q]) * scale, __uint_as_float(r[4 * q + 1]) * scale,
+                                   __uint_as_float(r[4 * q + 2]) * scale, __uint_as_float(r[4 * q + 3]) * scale);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+    }
+  } else if (warp == PRODUCER_WARPS) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
+          const int stage = g % kStages;
+          const uint32_t parity = (g / kStages) & 1u;
+          mbar_wait(full_bar(stage), parity);
+          if (chunk == 0) mbar_wait(acc_empty, ((uint32_t)it & 1u) ^ 1u);  // epilogue of the previous tile done
+          tc_fence_after();
+          const uint32_t sa = stage_base + stage * STAGE_BYTES;
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+          const uint64_t w_hi = make_desc(sa + 2 * A_TILE_BYTES), w_lo = make_desc(sa + 2 * A_TILE_BYTES + W_TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle atom
+            umma_bf16(tmem_base, a_hi + adv, w_hi + adv, kIdesc, (chunk | kk) != 0);
+            umma_bf16(tmem_base, a_hi + adv, w_lo + adv, kIdesc, 1u);
+            umma_bf16(tmem_base, a_lo + adv, w_hi + adv, kIdesc, 1u);
+          }
+          umma_commit(empty_bar(stage));                 // stage reusable once these MMAs have read it
+          if (chunk == NCHUNK - 1) umma_commit(acc_full);  // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ============================================================ W loader
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
+          const int stage = g % kStages;
+          const uint32_t parity = (g / kStages) & 1u;
+          mbar_wait(empty_bar(stage), parity ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), 2 * W_TILE_BYTES);
+          bulk_g2s(stage_base + stage * STAGE_BYTES + 2 * A_TILE_BYTES,
+                   reinterpret_cast<const uint8_t*>(Wp) + (size_t)chunk * 2 * W_TILE_BYTES, 2 * W_TILE_BYTES,
+                   full_bar(stage));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+
+int64_t segbil_tc_workspace_bytes() { return tc::WPACK_BYTES; }
+
+int launch_segbil_fwd_tc(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                         const float* rbf_W1, const float* W, float scale, int64_t n_edges, float* out,
+                         void* workspace, cudaStream_t st) {
+  using namespace tc;
+  if (!workspace || ((uintptr_t)workspace % 16) != 0) {
+    set_error("gemnet_segbilinear_fwd(algo=1): workspace of gemnet_segbilinear_workspace_bytes() bytes required");
+    return 1;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(segbil_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("segbilinear tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  __nv_bfloat16* Wp = reinterpret_cast<__nv_bfloat16*>(workspace);
+  pack_weight_kernel<<<(NCHUNK * O * KC + 255) / 256, 256, 0, st>>>(W, Wp);
+  const int n_tiles = (int)ceil_div(n_edges, TILE_M);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  segbil_fwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(x, expand, rowptr, sph, rbf_W1, Wp, scale, n_edges, n_tiles,
+                                                         out);
+  return check_launch("gemnet_segbilinear_fwd(algo=1)");
+}
+
+}  // namespace gemnet

@@ -356,9 +356,11 @@ class _SegBilinear(Function):
         C, _, O = W.shape
         U = expand.numel()
         out = torch.empty(E, O, dtype=torch.float32, device=x.device)
+        nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, algo, 0)
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
         _check(_L().gemnet_segbilinear_fwd(_p(x), _p(_i32(expand)), _p(_i32(rowptr)), _p(sph), _p(rbf_W1), _p(W),
-                                           scale, E, U, S, C, I, O, algo, _p(out), None, _stream()),
-               "gemnet_segbilinear_fwd")
+                                           scale, E, U, S, C, I, O, algo, _p(out), _p(ws), _stream()),
+               "gemnet_segbilinear_fwd", kernels=1 if algo == 0 else 2)
         ctx.save_for_backward(x, sph, rbf_W1, W, expand, rowptr)
         ctx.cfg = (scale, algo)
         return out

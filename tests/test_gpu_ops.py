@@ -398,3 +398,29 @@ def test_fused_pointwise_and_gathers(ops, dev):
     assert relerr(gs, gs0) < 1e-6
     (gs2,) = kernel_grads(lambda t: ops.gather_rows(t, idx, perm, rowptr), [src], g)
     assert torch.equal(gs, gs2)
+
+
+# ----------------------------------------------------------------------------- H7 on tensor cores (tcgen05, algo 1)
+@pytest.mark.parametrize("ids", [[1, 4, 7, 9, 16], list(range(64)), list(range(200))])
+def test_segmented_bilinear_tcgen05_matches_fp32_kernel_and_oracle(ops, dev, ids):
+    torch.manual_seed(4)
+    cpu, gpu = batch(ids, True, dev)
+    nE, U = len(cpu["id_c"]), len(cpu["id3_reduce_ca"])
+    x = torch.randn(nE, 64, device=dev)
+    sph = torch.randn(U, 7, device=dev)
+    rbf_W1 = torch.randn(nE, 16, 7, device=dev) * 0.3
+    W = torch.randn(64, 16, 64, device=dev) / 32
+    expand = gpu["id3_expand_ba"]
+    rowptr, _ = ops.csr_from_sorted(gpu["id3_reduce_ca"], nE)
+    out0 = ops.segmented_bilinear(x, sph, rbf_W1, W, expand, rowptr, 1.3, algo=0)
+    out1 = ops.segmented_bilinear(x, sph, rbf_W1, W, expand, rowptr, 1.3, algo=1)
+    torch.cuda.synchronize()
+    want = _bilinear_oracle(x.double().cpu(), sph.double().cpu(), rbf_W1.double().cpu(), W.double().cpu(),
+                            cpu["id3_expand_ba"], cpu["id3_reduce_ca"], cpu["Kidx3"], 1.3)
+    e0, e1 = relerr(out0, want), relerr(out1, want)
+    print(f"E={nE} T={U}: fp32 kernel rel err {e0:.2e}, tcgen05 bf16x3 rel err {e1:.2e}")
+    assert e0 < 3e-6
+    assert e1 < 2e-5   # bf16x3 split: ~2^-16 per product, fp32 accumulation in TMEM
+    # replays are bitwise identical (no atomics, fixed order)
+    out1b = ops.segmented_bilinear(x, sph, rbf_W1, W, expand, rowptr, 1.3, algo=1)
+    assert torch.equal(out1, out1b)
