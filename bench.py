@@ -331,20 +331,27 @@ def main():
     }
 
     # ---------------- roofline of the dominant kernel (H7, triplet segmented bilinear)
-    t_k, bts, fl = time_bilinear(plan, dev, flush, 30)
-    line["roofline"] = {"kernel": "segbil_fwd_kernel<7,64,16,64> (H7 triplets, fp32 CUDA cores)", "bound": "hbm",
-                        "achieved": bts / t_k / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bts / t_k / 1e9 / hbm_peak,
-                        "traffic": None, "peak_kind": peak_kind, "bytes_per_launch": bts, "us_per_launch": t_k * 1e6,
-                        "tflops": fl / t_k / 1e12, "bytes_per_triplet": bts / max(plan.n_triplets, 1)}
+    t_k, bts, fl = time_bilinear(plan, dev, flush, 30, algo=1)
+    t_k0, _, _ = time_bilinear(plan, dev, flush, 30, algo=0)
+    line["roofline"] = {"kernel": "segbil_fwd_tc_kernel (H7 triplets, tcgen05 bf16x3 + weight pack kernel)",
+                        "bound": "hbm", "achieved": bts / t_k / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bts / t_k / 1e9 / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                        "bytes_per_launch": bts, "us_per_launch": t_k * 1e6, "tflops": fl / t_k / 1e12,
+                        "tensor_frac_of_bf16_peak": 3 * 2 * plan.n_edges * 1024 * 64 / t_k / 1e12 / tc_peak,
+                        "bytes_per_triplet": bts / max(plan.n_triplets, 1),
+                        "fp32_cuda_core_kernel_us": t_k0 * 1e6}
     if args.large_batch and world == 1:
         Rb, Zb = synthetic_molecules(args.large_batch, 4321)
         big = {k: v.to(dev) for k, v in build_batch(Rb, Zb, kw["cutoff"], kw["int_cutoff"], True).items()}
         bplan = graph.GraphPlan(big, True)
-        t_k, bts, fl = time_bilinear(bplan, dev, flush, 10)
+        t_k, bts, fl = time_bilinear(bplan, dev, flush, 10, algo=1)
+        t_k0, _, _ = time_bilinear(bplan, dev, flush, 5, algo=0)
         line["roofline_large"] = {"molecules": args.large_batch, "edges": bplan.n_edges, "triplets": bplan.n_triplets,
                                   "bound": "hbm", "achieved": bts / t_k / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": bts / t_k / 1e9 / hbm_peak, "us_per_launch": t_k * 1e6,
-                                  "tflops": fl / t_k / 1e12}
+                                  "tflops": fl / t_k / 1e12,
+                                  "tensor_frac_of_bf16_peak": 3 * 2 * bplan.n_edges * 1024 * 64 / t_k / 1e12 / tc_peak,
+                                  "fp32_cuda_core_kernel_us": t_k0 * 1e6}
         del big, bplan
 
     # ---------------- CPU baseline beside it (oracle port of the reference path, bounded sample)

@@ -221,6 +221,9 @@ class EfficientInteractionBilinear(torch.nn.Module):
 
     def forward(self, rbf_W1, sph, x, expand, rowptr, scale=1.0, algo=0):
         """x: UN-gathered (n_x, C) table; expand/rowptr: CSR of the units (efficient.py:159-189 + gather + scale)."""
+        S = rbf_W1.shape[2]
+        if algo == 1 and (S, self.emb_size, self.emb_size_interm, self.units_out) != (7, 64, 16, 64):
+            algo = 0  # the tcgen05 kernel is built for the published triplet shape; other shapes use the fp32 kernel
         return ops.segmented_bilinear(x, sph, rbf_W1, _w(self, self.weight), expand, rowptr, scale, algo)
 
 

@@ -60,7 +60,8 @@ class GemNet(torch.nn.Module):
         self.direct_forces = direct_forces
         self.triplets_only = triplets_only
         self.num_spherical, self.num_radial = num_spherical, num_radial
-        self.bilinear_algo = int(kwargs.get("bilinear_algo", 0))
+        # 1 = tcgen05 forward kernel where built (published triplet shape), 0 = fp32 CUDA-core kernels everywhere
+        self.bilinear_algo = int(kwargs.get("bilinear_algo", 1))
 
         # basis layers (no random state)
         self.rbf_basis = BesselBasisLayer(num_radial, cutoff=cutoff, envelope_exponent=envelope_exponent)
