@@ -78,6 +78,25 @@ __global__ void mul_scale_bwd_kernel(const float4* __restrict__ a, const float4*
   }
 }
 
+// scalar tails (n % 4 elements) of the vector kernels above: op 0 silu mode0, 1 silu mode1, 2 silu_bwd, 3 add_scale,
+// 4 mul_scale, 5 mul_scale_bwd
+__global__ void tail_kernel(int op, const float* a, const float* b, const float* c, float s, int64_t begin, int64_t n,
+                            float* o1, float* o2) {
+  const int64_t i = begin + threadIdx.x;
+  if (i >= n) return;
+  switch (op) {
+    case 0: o1[i] = ssilu(a[i]); break;
+    case 1: o1[i] = (b[i] + ssilu(a[i])) * s; break;
+    case 2: o1[i] = b[i] * s * dssilu(a[i]); break;
+    case 3: o1[i] = (a[i] + (b ? b[i] : 0.f) + (c ? c[i] : 0.f)) * s; break;
+    case 4: o1[i] = a[i] * b[i] * s; break;
+    case 5:
+      if (o1) o1[i] = c[i] * b[i] * s;
+      if (o2) o2[i] = c[i] * a[i] * s;
+      break;
+  }
+}
+
 // out[j,:] = x[idx[j],:]  (F % 4 == 0)
 __global__ void gather_rows_kernel(const float4* __restrict__ x, const int32_t* __restrict__ idx, int64_t n, int F4,
                                    float4* __restrict__ out) {
@@ -117,51 +136,61 @@ static inline bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 
 GEMNET_API int gemnet_scaled_silu_fwd(const float* z, const float* x, float s, int64_t n, int32_t mode, float* out,
                                       void* stream) {
-  GEMNET_REQUIRE(n >= 0 && n % 4 == 0, "n must be a non-negative multiple of 4");
+  GEMNET_REQUIRE(n >= 0, "negative size");
   GEMNET_REQUIRE(mode == 0 || (mode == 1 && x), "mode 1 needs x");
   if (n == 0) return 0;
   GEMNET_REQUIRE(z && out && aligned16(z) && aligned16(x) && aligned16(out), "null or misaligned pointer");
-  silu_fwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)z, (const float4*)x, s, n / 4,
-                                                                       mode, (float4*)out);
+  if (n / 4)
+    silu_fwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)z, (const float4*)x, s,
+                                                                         n / 4, mode, (float4*)out);
+  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(mode, z, x, nullptr, s, n - n % 4, n, out, nullptr);
   return check_launch("gemnet_scaled_silu_fwd");
 }
 
 GEMNET_API int gemnet_scaled_silu_bwd(const float* z, const float* g, float s, int64_t n, float* gz, void* stream) {
-  GEMNET_REQUIRE(n >= 0 && n % 4 == 0, "n must be a non-negative multiple of 4");
+  GEMNET_REQUIRE(n >= 0, "negative size");
   if (n == 0) return 0;
   GEMNET_REQUIRE(z && g && gz && aligned16(z) && aligned16(g) && aligned16(gz), "null or misaligned pointer");
-  silu_bwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)z, (const float4*)g, s, n / 4,
-                                                                       (float4*)gz);
+  if (n / 4)
+    silu_bwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)z, (const float4*)g, s,
+                                                                         n / 4, (float4*)gz);
+  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(2, z, g, nullptr, s, n - n % 4, n, gz, nullptr);
   return check_launch("gemnet_scaled_silu_bwd");
 }
 
 GEMNET_API int gemnet_add_scale(const float* a, const float* b, const float* c, float s, int64_t n, float* out,
                                 void* stream) {
-  GEMNET_REQUIRE(n >= 0 && n % 4 == 0, "n must be a non-negative multiple of 4");
+  GEMNET_REQUIRE(n >= 0, "negative size");
   if (n == 0) return 0;
   GEMNET_REQUIRE(a && out && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(out), "null or misaligned pointer");
-  add_scale_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b,
-                                                                        (const float4*)c, s, n / 4, (float4*)out);
+  if (n / 4)
+    add_scale_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b,
+                                                                          (const float4*)c, s, n / 4, (float4*)out);
+  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(3, a, b, c, s, n - n % 4, n, out, nullptr);
   return check_launch("gemnet_add_scale");
 }
 
 GEMNET_API int gemnet_mul_scale_fwd(const float* a, const float* b, float s, int64_t n, float* out, void* stream) {
-  GEMNET_REQUIRE(n >= 0 && n % 4 == 0, "n must be a non-negative multiple of 4");
+  GEMNET_REQUIRE(n >= 0, "negative size");
   if (n == 0) return 0;
   GEMNET_REQUIRE(a && b && out && aligned16(a) && aligned16(b) && aligned16(out), "null or misaligned pointer");
-  mul_scale_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b, s, n / 4,
-                                                                        (float4*)out);
+  if (n / 4)
+    mul_scale_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b, s,
+                                                                          n / 4, (float4*)out);
+  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(4, a, b, nullptr, s, n - n % 4, n, out, nullptr);
   return check_launch("gemnet_mul_scale_fwd");
 }
 
 GEMNET_API int gemnet_mul_scale_bwd(const float* a, const float* b, const float* g, float s, int64_t n, float* ga,
                                     float* gb, void* stream) {
-  GEMNET_REQUIRE(n >= 0 && n % 4 == 0, "n must be a non-negative multiple of 4");
+  GEMNET_REQUIRE(n >= 0, "negative size");
   if (n == 0) return 0;
   GEMNET_REQUIRE(a && b && g && aligned16(a) && aligned16(b) && aligned16(g) && aligned16(ga) && aligned16(gb),
                  "null or misaligned pointer");
-  mul_scale_bwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>(
-      (const float4*)a, (const float4*)b, (const float4*)g, s, n / 4, (float4*)ga, (float4*)gb);
+  if (n / 4)
+    mul_scale_bwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        (const float4*)a, (const float4*)b, (const float4*)g, s, n / 4, (float4*)ga, (float4*)gb);
+  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(5, a, b, g, s, n - n % 4, n, ga, gb);
   return check_launch("gemnet_mul_scale_bwd");
 }
 

@@ -4,9 +4,10 @@
 //   B_e[k = c*I + i] = sum_s rbf_W1[e,i,s] * A_e[s,c],   A_e[s,c] = sum_{t in seg(e)} sph[t,s] * x[expand[t], c]
 //
 // Persistent warp-specialised kernel, one CTA per SM, tile = 128 target edges (UMMA M = 128, N = 64):
-//   warps 0-15  (512 threads) PRODUCERS: thread (edge el = tid/4, column cl = tid%4) owns one x-column per K-chunk.
-//               A chunk is 4 columns c = 4*chunk .. 4*chunk+3, i.e. 64 consecutive k.  The thread gathers its column
-//               over the CSR segment (phase 1), contracts with rbf_W1 from shared memory (phase 2) and writes its 16
+//   warps 0-15  (512 threads) PRODUCERS in 4 groups of 128 threads; group g owns the K-chunks g, g+4, g+8, g+12.
+//               A chunk is 4 columns c = 4*chunk .. 4*chunk+3 of x, i.e. 64 consecutive k = one 128-byte operand
+//               row per edge.  Thread = one edge row: it gathers the 4 columns over the CSR segment with one 128-bit
+//               load per unit (phase 1), contracts with rbf_W1 from shared memory (phase 2) and writes its 64
 //               k-values, split into bf16 hi + bf16 lo, into the K-major SWIZZLE_128B A-operand tile of the stage.
 //   warp 16     lane 0 issues tcgen05.mma: D += Ahi*Whi + Ahi*Wlo + Alo*Whi (bf16x3: the dropped lo*lo term is
 //               2^-16 relative, so the result is fp32-accurate: parity mode, not a reduced-precision mode).
@@ -28,7 +29,7 @@ constexpr int K = C * I;                 // 1024
 constexpr int TILE_M = 128;
 constexpr int KC = 64;                   // k per chunk (4 columns of x times I)
 constexpr int NCHUNK = K / KC;           // 16
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr int PRODUCER_WARPS = 16;
 constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;  // 512
 constexpr int THREADS = PRODUCER_THREADS + 64;         // + MMA warp + loader warp
@@ -38,7 +39,7 @@ constexpr int W_TILE_BYTES = O * KC * 2;               // 8192
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;  // 49152
 constexpr int RW_LD = I * 8 + 4;                       // padded row of rbf_W1 in smem (floats): conflict-free float4 reads
 constexpr int RW_BYTES = TILE_M * RW_LD * 4;           // 67584
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + RW_BYTES + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + RW_BYTES + 512 /*barriers*/;
 constexpr uint32_t TMEM_COLS = 64;
 
 // packed weight image: [chunk][hi|lo][o][k_local] bf16, rows already XOR-swizzled (SWIZZLE_128B)
@@ -164,21 +165,24 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
   const uint32_t stage_base = base;                                    // kStages * STAGE_BYTES
   float* rw_s = reinterpret_cast<float*>(sm + kStages * STAGE_BYTES);  // [TILE_M][RW_LD]
   const uint32_t bar_base = base + kStages * STAGE_BYTES + RW_BYTES;
-  // barriers: full[kStages], empty[kStages], acc_full, acc_empty, then the TMEM address slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t acc_full = bar_base + 8u * (2 * kStages);
-  const uint32_t acc_empty = bar_base + 8u * (2 * kStages + 1);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2);
+  // mbarriers are PER CHUNK (each completes exactly once per tile, phase parity = tile parity): the four producer
+  // groups run out of order, and per-stage barriers would let a fast group get two phases ahead (parity aliasing).
+  //   full[j]     chunk j of this tile is in its stage (4 producer warps + the weight loader's expect_tx)
+  //   consumed[j] the MMAs of chunk j have finished reading its stage (tcgen05.commit)
+  auto full_bar = [&](int j) { return bar_base + 8u * j; };
+  auto cons_bar = [&](int j) { return bar_base + 8u * (NCHUNK + j); };
+  const uint32_t acc_full = bar_base + 8u * (2 * NCHUNK);
+  const uint32_t acc_empty = bar_base + 8u * (2 * NCHUNK + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NCHUNK + 2);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kStages * STAGE_BYTES + RW_BYTES +
-                                                                           8 * (2 * kStages + 2));
+                                                                           8 * (2 * NCHUNK + 2));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), PRODUCER_WARPS + 1);
-      mbar_init(empty_bar(s), 1);
+    for (int j = 0; j < NCHUNK; ++j) {
+      mbar_init(full_bar(j), 4 + 1);  // the 4 warps of one producer group + the weight loader
+      mbar_init(cons_bar(j), 1);
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 4);
@@ -192,8 +196,9 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
 
   if (warp < PRODUCER_WARPS) {
     // ============================================================ producers (+ epilogue on warps 0-3)
-    const int el = tid >> 2, cl = tid & 3;
-    uint32_t g = 0;  // global chunk counter (stage ring position)
+    // thread = (edge row el, warp-group grp); group grp produces chunks grp, grp+4, grp+8, grp+12 of every tile:
+    // one whole 128-byte operand row (4 x-columns x 16 i) per thread and chunk.
+    const int el = tid & (TILE_M - 1), grp = tid >> 7;
     for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t e0 = (int64_t)tile * TILE_M;
       // stage rbf_W1 of the tile: rw_s[el][i][s] (s padded to 8)
@@ -211,51 +216,65 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
       const int32_t beg = live ? __ldg(rowptr + e) : 0, end = live ? __ldg(rowptr + e + 1) : 0;
       const float* rw = rw_s + el * RW_LD;
 
-      for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
-        const int stage = g % kStages;
-        const uint32_t parity = (g / kStages) & 1u;
-        // phase 1: A[s] for column c = 4*chunk + cl
-        float A[S];
+      for (int chunk = grp; chunk < NCHUNK; chunk += PRODUCER_WARPS / 4) {
+        const int stage = chunk % kStages;
+        // phase 1: A[s][cq] for the 4 columns c = 4*chunk + cq (one 128-bit gather per unit of the segment)
+        float A[S][4];
 #pragma unroll
-        for (int s = 0; s < S; ++s) A[s] = 0.f;
-        const int c = chunk * 4 + cl;
+        for (int s = 0; s < S; ++s) A[s][0] = A[s][1] = A[s][2] = A[s][3] = 0.f;
+        const float* xcol = x + chunk * 4;
+        int32_t idx_next = beg < end ? __ldg(expand + beg) : 0;
         for (int32_t t = beg; t < end; ++t) {
-          const float xv = __ldg(x + (int64_t)__ldg(expand + t) * C + c);
+          const int32_t idx = idx_next;
+          if (t + 1 < end) idx_next = __ldg(expand + t + 1);
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(xcol + (int64_t)idx * C));
           const float* sp = sph + (int64_t)t * S;
 #pragma unroll
-          for (int s = 0; s < S; ++s) A[s] = fmaf(__ldg(sp + s), xv, A[s]);
-        }
-        // phase 2: 16 k-values of this thread, bf16 hi/lo
-        uint32_t hi_w[8], lo_w[8];
-#pragma unroll
-        for (int i2 = 0; i2 < I; i2 += 2) {
-          float b[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float4 w0 = *reinterpret_cast<const float4*>(rw + (i2 + u) * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(rw + (i2 + u) * 8 + 4);
-            b[u] = w0.x * A[0] + w0.y * A[1] + w0.z * A[2] + w0.w * A[3] + w1.x * A[4] + w1.y * A[5] + w1.z * A[6];
+          for (int s = 0; s < S; ++s) {
+            const float w = __ldg(sp + s);
+            A[s][0] = fmaf(w, xv.x, A[s][0]);
+            A[s][1] = fmaf(w, xv.y, A[s][1]);
+            A[s][2] = fmaf(w, xv.z, A[s][2]);
+            A[s][3] = fmaf(w, xv.w, A[s][3]);
           }
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(b[0], h0, l0);
-          split_bf16(b[1], h1, l1);
-          hi_w[i2 / 2] = pack2(h0, h1);
-          lo_w[i2 / 2] = pack2(l0, l1);
         }
-        // wait until the MMA has drained this stage, then write 2 x 16 B (hi) and 2 x 16 B (lo) into row el
-        mbar_wait(empty_bar(stage), parity ^ 1u);
-        uint8_t* a_hi = sm + stage * STAGE_BYTES;
+        // wait until the MMA has drained this stage (chunk - kStages of this tile; the previous tile is fully
+        // consumed before any producer passes the tile-start barrier)
+        if (chunk >= kStages) mbar_wait(cons_bar(chunk - kStages), (uint32_t)it & 1u);
+        uint8_t* a_hi = sm + stage * STAGE_BYTES + el * 128;
         uint8_t* a_lo = a_hi + A_TILE_BYTES;
-        const int j0 = cl * 2;
-        const uint32_t off0 = el * 128 + (((j0) ^ (el & 7)) << 4);
-        const uint32_t off1 = el * 128 + (((j0 + 1) ^ (el & 7)) << 4);
-        *reinterpret_cast<uint4*>(a_hi + off0) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
-        *reinterpret_cast<uint4*>(a_hi + off1) = make_uint4(hi_w[4], hi_w[5], hi_w[6], hi_w[7]);
-        *reinterpret_cast<uint4*>(a_lo + off0) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
-        *reinterpret_cast<uint4*>(a_lo + off1) = make_uint4(lo_w[4], lo_w[5], lo_w[6], lo_w[7]);
+        // phase 2: k_local = cq*16 + i, written as 16-byte pieces (8 consecutive i of one column)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float b[4][8];
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const float4 w0 = *reinterpret_cast<const float4*>(rw + (half * 8 + i8) * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(rw + (half * 8 + i8) * 8 + 4);
+#pragma unroll
+            for (int cq = 0; cq < 4; ++cq)
+              b[cq][i8] = w0.x * A[0][cq] + w0.y * A[1][cq] + w0.z * A[2][cq] + w0.w * A[3][cq] + w1.x * A[4][cq] +
+                          w1.y * A[5][cq] + w1.z * A[6][cq];
+          }
+#pragma unroll
+          for (int cq = 0; cq < 4; ++cq) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(b[cq][2 * q], h0, l0);
+              split_bf16(b[cq][2 * q + 1], h1, l1);
+              hw[q] = pack2(h0, h1);
+              lw[q] = pack2(l0, l1);
+            }
+            const uint32_t off = (uint32_t)(((cq * 2 + half) ^ (el & 7)) << 4);
+            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
         fence_proxy_async();  // make the generic-proxy writes visible to the tensor-core (async) proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (lane == 0) mbar_arrive(full_bar(chunk));
       }
 
       if (warp < 4) {
@@ -283,12 +302,10 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
   } else if (warp == PRODUCER_WARPS) {
     // ============================================================ MMA issuer
     if (lane == 0) {
-      uint32_t g = 0;
       for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
-          const int stage = g % kStages;
-          const uint32_t parity = (g / kStages) & 1u;
-          mbar_wait(full_bar(stage), parity);
+        for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+          const int stage = chunk % kStages;
+          mbar_wait(full_bar(chunk), (uint32_t)it & 1u);
           if (chunk == 0) mbar_wait(acc_empty, ((uint32_t)it & 1u) ^ 1u);  // epilogue of the previous tile done
           tc_fence_after();
           const uint32_t sa = stage_base + stage * STAGE_BYTES;
@@ -301,7 +318,7 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
             umma_bf16(tmem_base, a_hi + adv, w_lo + adv, kIdesc, 1u);
             umma_bf16(tmem_base, a_lo + adv, w_hi + adv, kIdesc, 1u);
           }
-          umma_commit(empty_bar(stage));                 // stage reusable once these MMAs have read it
+          umma_commit(cons_bar(chunk));                  // stage reusable once these MMAs have read it
           if (chunk == NCHUNK - 1) umma_commit(acc_full);  // accumulator complete
         }
       }
@@ -309,16 +326,15 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
   } else {
     // ============================================================ W loader
     if (lane == 0) {
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
-          const int stage = g % kStages;
-          const uint32_t parity = (g / kStages) & 1u;
-          mbar_wait(empty_bar(stage), parity ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), 2 * W_TILE_BYTES);
+      for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+          const int stage = chunk % kStages;
+          if (chunk >= kStages) mbar_wait(cons_bar(chunk - kStages), (uint32_t)it & 1u);
+          else if (it > 0) mbar_wait(cons_bar(NCHUNK - kStages + chunk), (uint32_t)(it - 1) & 1u);
+          mbar_arrive_expect_tx(full_bar(chunk), 2 * W_TILE_BYTES);
           bulk_g2s(stage_base + stage * STAGE_BYTES + 2 * A_TILE_BYTES,
                    reinterpret_cast<const uint8_t*>(Wp) + (size_t)chunk * 2 * W_TILE_BYTES, 2 * W_TILE_BYTES,
-                   full_bar(stage));
+                   full_bar(chunk));
         }
       }
     }

@@ -1,0 +1,325 @@
+"""Inference engine: energy + forces of a GemNet batch without torch.autograd.
+
+The shipped checkpoints compute forces as -dE/dR (gemnet/model/gemnet.py:598-613), i.e. every evaluation is a forward
+AND a backward pass.  At batch 64 the step is launch/host bound: ~650 kernels, and torch.autograd spends
+more host time per custom Function (graph node creation, Python trampolines, dispatcher) than the kernels take on the
+GPU.  This module runs the SAME kernels (the forward/backward bodies of the autograd Functions in ops.py are reused
+verbatim through a stand-in ctx object) on a minimal reverse-mode tape: a list of closures, gradients keyed by tensor
+identity, and a "depends on R" flag that prunes everything that does not (weights, atom embeddings).  Weight
+gradients are never formed.  Used by GemNet.forward in eval mode; training keeps using torch.autograd.
+"""
+import torch
+
+from . import graph, layers, ops
+
+
+class _Ctx:
+    """Stand-in for torch.autograd.function.FunctionCtx (what the Function bodies in ops.py touch)."""
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+
+class _Linear:
+    """y = x @ W^T (base_layers.py:45-48, bias-free); backward w.r.t. x only."""
+
+    @staticmethod
+    def forward(ctx, x, W):
+        ctx.W = W
+        return torch.mm(x, W.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.mm(g, ctx.W), None
+
+
+class Tape:
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.closures = []
+        self.grads = {}
+        self.req = set()
+
+    def require(self, t):
+        self.req.add(id(t))
+
+    def needs(self, t):
+        return isinstance(t, torch.Tensor) and id(t) in self.req
+
+    def add_grad(self, t, g):
+        k = id(t)
+        cur = self.grads.get(k)
+        self.grads[k] = g if cur is None else cur + g
+
+    def apply(self, Fn, *args):
+        """Run Fn.forward; if any tensor argument depends on R, record Fn.backward."""
+        ctx = _Ctx()
+        ctx.needs_input_grad = tuple(self.enabled and self.needs(a) for a in args)
+        out = Fn.forward(ctx, *args)
+        if not any(ctx.needs_input_grad):
+            return out
+        outs = out if isinstance(out, tuple) else (out,)
+        for o in outs:
+            self.req.add(id(o))
+
+        def backward():
+            gs = [self.grads.pop(id(o), None) for o in outs]
+            if all(g is None for g in gs):
+                return
+            gs = [torch.zeros_like(o) if g is None else g for g, o in zip(gs, outs)]
+            gin = Fn.backward(ctx, *gs)
+            if not isinstance(gin, tuple):
+                gin = (gin,)
+            for a, need, g in zip(args, ctx.needs_input_grad, gin):
+                if need and g is not None:
+                    self.add_grad(a, g)
+
+        self.closures.append((backward, outs, args))  # keep tensors alive: gradients are keyed by id()
+        return out
+
+    def backward(self):
+        for fn, _, _ in reversed(self.closures):
+            fn()
+        self.closures.clear()
+
+
+# ---------------------------------------------------------------------------------------------- layer evaluation
+class _Run:
+    """One evaluation: thin wrappers that mirror the module tree of layers.py on the tape."""
+
+    def __init__(self, model, tape, plan):
+        self.m, self.t, self.p = model, tape, plan
+
+    # -- primitives
+    def linear(self, dense, x):
+        return self.t.apply(_Linear, x, dense.linear.weight)
+
+    def act(self, dense, z):
+        return self.t.apply(ops._ScaledSiLU, z) if isinstance(dense._activation, layers.ScaledSiLU) else z
+
+    def dense(self, dense, x):
+        return self.act(dense, self.linear(dense, x))
+
+    def residual(self, layer, x):
+        y = x
+        for d in layer.dense_mlp[:-1]:
+            y = self.dense(d, y)
+        last = layer.dense_mlp[-1]
+        z = self.linear(last, y)
+        if isinstance(last._activation, layers.ScaledSiLU):
+            return self.t.apply(ops._ResidualTail, z, x, layers.INV_SQRT_2)
+        return self.add_scale(layers.INV_SQRT_2, x, z)
+
+    def add_scale(self, s, a, b=None, c=None):
+        return self.t.apply(ops._AddScale, float(s), a, b, c)
+
+    def mul_scale(self, a, b, s):
+        return self.t.apply(ops._MulScale, a, b, float(s))
+
+    def gather(self, x, idx, perm, rowptr):
+        return self.t.apply(ops._GatherRows, x, idx, perm, rowptr)
+
+    # -- blocks
+    def edge_embedding(self, emb, h, m_rbf):
+        p = self.p
+        W = emb.dense.linear.weight
+        A = h.shape[1]
+        p_c = self.t.apply(_Linear, h, W[:, :A])
+        p_a = self.t.apply(_Linear, h, W[:, A:2 * A])
+        y = self.t.apply(_Linear, m_rbf, W[:, 2 * A:])
+        z = self.add_scale(1.0, y, self.gather(p_c, p.id_c, p.src_perm, p.src_rowptr),
+                           self.gather(p_a, p.id_a, p.atom_perm, p.atom_rowptr))
+        return self.act(emb.dense, z)
+
+    def atom_update(self, blk, m, rbf, mlp):
+        p = self.p
+        x = self.t.apply(ops._EdgeToAtom, m, self.linear(blk.dense_rbf, rbf), p.id_a, p.atom_perm, p.atom_rowptr,
+                         blk.scale_sum.value(), None)
+        x = self.dense(mlp[0], x)
+        for layer in list(mlp)[1:]:
+            x = self.residual(layer, x)
+        return x
+
+    def output_block(self, blk, m, rbf_out):
+        p = self.p
+        r = self.linear(blk.dense_rbf, rbf_out)
+        if blk.direct_forces:
+            x_E, x_F = self.t.apply(ops._EdgeToAtom, m, r, p.id_a, p.atom_perm, p.atom_rowptr, blk.scale_sum.value(),
+                                    blk.scale_rbf.value())
+        else:
+            x_E = self.t.apply(ops._EdgeToAtom, m, r, p.id_a, p.atom_perm, p.atom_rowptr, blk.scale_sum.value(), None)
+            x_F = None
+        x_E = self.dense(blk.seq_energy[0], x_E)
+        for layer in list(blk.seq_energy)[1:]:
+            x_E = self.residual(layer, x_E)
+        x_E = self.linear(blk.out_energy, x_E)
+        if blk.direct_forces:
+            x_F = self.dense(blk.seq_forces[0], x_F)
+            for layer in list(blk.seq_forces)[1:]:
+                x_F = self.residual(layer, x_F)
+            x_F = self.linear(blk.out_forces, x_F)
+        return x_E, x_F
+
+    def bilinear(self, mod, rbf_W1, sph, x, expand, rowptr, scale, algo):
+        S = rbf_W1.shape[2]
+        if algo == 1 and (S, mod.emb_size, mod.emb_size_interm, mod.units_out) != (7, 64, 16, 64):
+            algo = 0
+        return self.t.apply(ops._SegBilinear, x, sph, rbf_W1, mod.weight.detach(), expand, rowptr, float(scale), int(algo))
+
+    def triplet_interaction(self, ti, m, basis, algo):
+        p = self.p
+        x = self.dense(ti.dense_ba, m)
+        x = self.mul_scale(x, self.linear(ti.mlp_rbf, basis["rbf3"]), ti.scale_rbf.value())
+        x = self.dense(ti.down_projection, x)
+        x = self.bilinear(ti.mlp_cbf, basis["rbf_W1_3"], basis["sph3"], x, p.id3_expand, p.rowptr3,
+                          ti.scale_cbf_sum.value(), algo)
+        x_ca = self.dense(ti.up_projection_ca, x)
+        x_ac = self.gather(self.dense(ti.up_projection_ac, x), p.id_swap, p.swap_perm, p.swap_rowptr)
+        return self.add_scale(layers.INV_SQRT_2, x_ca, x_ac)
+
+    def quadruplet_interaction(self, qi, m, basis, algo):
+        p = self.p
+        x = self.dense(qi.dense_db, m)
+        x = self.mul_scale(x, self.linear(qi.mlp_rbf, basis["rbf4"]), qi.scale_rbf.value())
+        x = self.dense(qi.down_projection, x)
+        x = self.gather(x, p.id4_expand_intm_db, p.intm_db_perm, p.intm_db_rowptr)
+        x = self.mul_scale(x, self.linear(qi.mlp_cbf, basis["cbf4"]), qi.scale_cbf.value())
+        x = self.bilinear(qi.mlp_sbf, basis["rbf_W1_4"], basis["ylm"], x, p.id4_expand_abd, p.rowptr4,
+                          qi.scale_sbf_sum.value(), algo)
+        x_ca = self.dense(qi.up_projection_ca, x)
+        x_ac = self.gather(self.dense(qi.up_projection_ac, x), p.id_swap, p.swap_perm, p.swap_rowptr)
+        return self.add_scale(layers.INV_SQRT_2, x_ca, x_ac)
+
+    def interaction_block(self, blk, h, m, basis, algo):
+        x_skip = self.dense(blk.dense_ca, m)
+        if blk.triplets_only:
+            x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)
+            x = self.add_scale(layers.INV_SQRT_2, x_skip, x3)
+        else:
+            x4 = self.quadruplet_interaction(blk.quad_interaction, m, basis, algo)
+            x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)
+            x = self.add_scale(layers.INV_SQRT_3, x_skip, x3, x4)
+        for layer in blk.layers_before_skip:
+            x = self.residual(layer, x)
+        m = self.add_scale(layers.INV_SQRT_2, m, x)
+        for layer in blk.layers_after_skip:
+            m = self.residual(layer, m)
+        h2 = self.atom_update(blk.atom_update, m, basis["rbf_h"], blk.atom_update.layers)
+        h = self.add_scale(layers.INV_SQRT_2, h, h2)
+        m2 = self.edge_embedding(blk.concat_layer, h, m)
+        for layer in blk.residual_m:
+            m2 = self.residual(layer, m2)
+        m = self.add_scale(layers.INV_SQRT_2, m, m2)
+        return h, m
+
+
+@torch.no_grad()
+def energy_and_forces(model, inputs):
+    """GemNet.forward (gemnet.py:453-615) for inference: returns (E (nMol, T), F (nAtoms, 3) | (nAtoms, T, 3))."""
+    plan = graph.get_plan(inputs, model.triplets_only)
+    Z, R = inputs["Z"], inputs["R"]
+    dev = R.device
+    S, nR = model.num_spherical, model.num_radial
+    need_forces = not model.direct_forces
+    n_passes = model.num_targets if (need_forces and model.num_targets > 1) else 1
+    forces = []
+    E_mol = None
+    for target in range(n_passes):
+        tape = Tape(enabled=need_forces)
+        if need_forces:
+            tape.require(R)
+        run = _Run(model, tape, plan)
+        A = tape.apply
+
+        D_ca, V_ca = A(ops._EdgeGeometry, R, plan.id_c, plan.id_a)
+        basis = {}
+        if not model.triplets_only:
+            D_ab, _ = A(ops._EdgeGeometry, R, plan.id4_int_b, plan.id4_int_a)
+            sph_abd, bd_proj = A(ops._QuadIntm, R, plan.abd_center, plan.abd_first, plan.abd_second, S, True)
+            cs_cab, ac_proj = A(ops._QuadIntm, R, plan.cab_center, plan.cab_first, plan.cab_second, S, False)
+            basis["ylm"] = A(ops._QuadYlm, cs_cab, ac_proj, bd_proj, plan.id4_reduce_cab, plan.id4_expand_abd, S)
+            cb = model.cbf_basis
+            rad_int = A(ops._SphBesselRadial, D_ab, S, nR, cb.cutoff, cb.p)                 # (nInt, S, R)
+            rad_g = A(_Gather42, rad_int, plan.abd_int_edge, plan)                           # (M, S*R)
+            cbf4 = A(_MulBroadcastSph, rad_g, sph_abd, nR)                                   # (M, S*R)
+        rb = model.rbf_basis
+        rbf = A(ops._BesselRbf, D_ca, rb.frequencies.detach(), rb.cutoff, rb.p)
+        c3 = model.cbf_basis3
+        rad = A(ops._SphBesselRadial, D_ca, S, nR, c3.cutoff, c3.p)
+        basis["sph3"] = A(ops._TripletSph, R, plan.id_c, plan.id_a, plan.id3_reduce, plan.id3_expand, S)
+
+        h = model.atom_emb(Z)
+        m = run.edge_embedding(model.edge_emb, h, rbf)
+        if not model.triplets_only:
+            basis["rbf4"] = run.linear(model.mlp_rbf4, rbf)
+            basis["cbf4"] = run.linear(model.mlp_cbf4, cbf4)
+            basis["rbf_W1_4"] = A(ops._DownProj, rad, model.mlp_sbf4.weight.detach(), layers.l_of_s_tensor(S, True, dev))
+        basis["rbf3"] = run.linear(model.mlp_rbf3, rbf)
+        basis["rbf_W1_3"] = A(ops._DownProj, rad, model.mlp_cbf3.weight.detach(), layers.l_of_s_tensor(S, False, dev))
+        basis["rbf_h"] = run.linear(model.mlp_rbf_h, rbf)
+        rbf_out = run.linear(model.mlp_rbf_out, rbf)
+
+        E_a, F_ca = run.output_block(model.out_blocks[0], m, rbf_out)
+        for i in range(model.num_blocks):
+            h, m = run.interaction_block(model.int_blocks[i], h, m, basis, model.bilinear_algo)
+            E, F = run.output_block(model.out_blocks[i + 1], m, rbf_out)
+            E_a = run.add_scale(1.0, E_a, E)
+            if model.direct_forces:
+                F_ca = F_ca + F
+        E_mol = A(ops._MoleculeSum, E_a, plan.batch_seg, plan.mol_rowptr, not model.extensive)
+
+        if model.direct_forces:
+            if model.forces_coupled:
+                nE = plan.n_edges
+                id_undir = inputs["id_undir"]
+                summed = torch.zeros(int(nE / 2), F_ca.shape[1], dtype=F_ca.dtype, device=dev).index_add(0, id_undir, F_ca)
+                cnt = torch.zeros(int(nE / 2), dtype=F_ca.dtype, device=dev).index_add(
+                    0, id_undir, torch.ones(nE, dtype=F_ca.dtype, device=dev)).clamp(min=1)
+                F_ca = (summed / cnt[:, None])[id_undir]
+            F_j = A(ops._ForceReadout, F_ca, V_ca, plan.id_a, plan.atom_perm, plan.atom_rowptr)
+            return E_mol, F_j
+
+        seed = torch.zeros_like(E_mol)
+        if model.num_targets > 1:
+            seed[:, target] = 1.0
+        else:
+            seed.fill_(1.0)
+        tape.add_grad(E_mol, seed)
+        tape.backward()
+        gR = tape.grads.pop(id(R), None)
+        forces.append(-gR if gR is not None else torch.zeros_like(R))
+    F_j = torch.stack(forces, dim=1) if model.num_targets > 1 else forces[0]
+    return E_mol, F_j
+
+
+# ---------------------------------------------------------------------------------------------- small extra ops (cbf4)
+class _Gather42(torch.autograd.Function):
+    """rows of the (nInt, S*R) radial table per intermediate triplet (basis_layers.py:134); S*R = 42 is not a
+    multiple of 4, so this one gather stays an ATen index op (once per evaluation)."""
+
+    @staticmethod
+    def forward(ctx, table, idx, plan):
+        # NB: the tape tracks tensors by identity, so views must be taken INSIDE ops, never between them
+        ctx.idx, ctx.shape = idx.long(), table.shape
+        return table.reshape(table.shape[0], -1)[ctx.idx]
+
+    @staticmethod
+    def backward(ctx, g):
+        out = torch.zeros(ctx.shape[0], g.shape[1], dtype=g.dtype, device=g.device)
+        return out.index_add_(0, ctx.idx, g).view(ctx.shape), None, None
+
+
+class _MulBroadcastSph(torch.autograd.Function):
+    """out[m, l*R + n] = rad[m, l*R + n] * sph[m, l]  (basis_layers.py:135-144)."""
+
+    @staticmethod
+    def forward(ctx, rad, sph, nR):
+        ctx.save_for_backward(rad, sph)
+        ctx.nR = nR
+        return (rad.view(rad.shape[0], -1, nR) * sph[:, :, None]).reshape(rad.shape[0], -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        rad, sph = ctx.saved_tensors
+        g3 = g.view(g.shape[0], -1, ctx.nR)
+        return (g3 * sph[:, :, None]).reshape(g.shape[0], -1), (g3 * rad.view(rad.shape[0], -1, ctx.nR)).sum(-1), None

@@ -12,7 +12,7 @@ fp64, scatters are CSR segment sums without atomics, and scale factors are folde
 """
 import torch
 
-from . import graph, layers, ops
+from . import engine, graph, layers, ops
 from .layers import (AtomEmbedding, BesselBasisLayer, Dense, EdgeEmbedding, EfficientInteractionDownProjection,
                      InteractionBlock, InteractionBlockTripletsOnly, OutputBlock, SphericalBasisLayer,
                      TensorBasisLayer)
@@ -62,6 +62,8 @@ class GemNet(torch.nn.Module):
         self.num_spherical, self.num_radial = num_spherical, num_radial
         # 1 = tcgen05 forward kernel where built (published triplet shape), 0 = fp32 CUDA-core kernels everywhere
         self.bilinear_algo = int(kwargs.get("bilinear_algo", 1))
+        # eval(): evaluate energy+forces on the tape engine (engine.py) instead of torch.autograd (same kernels)
+        self.use_engine = bool(kwargs.get("use_engine", True))
 
         # basis layers (no random state)
         self.rbf_basis = BesselBasisLayer(num_radial, cutoff=cutoff, envelope_exponent=envelope_exponent)
@@ -107,6 +109,15 @@ class GemNet(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs):
+        if self.use_engine and not self.training:
+            E_mol, F_j = engine.energy_and_forces(self, inputs)
+            if not self.direct_forces:
+                inputs["R"].requires_grad = False  # net effect of gemnet.py:493-494,613
+            return E_mol, F_j
+        return self.forward_autograd(inputs)
+
+    def forward_autograd(self, inputs):
+        """The same computation through torch.autograd (training, or use_engine=False)."""
         Z, R = inputs["Z"], inputs["R"]
         plan = graph.get_plan(inputs, self.triplets_only)
         S, nR = self.num_spherical, self.num_radial

@@ -209,7 +209,7 @@ int gemnet_force_readout_bwd(const float* F_ca, const float* V, const int32_t* i
  *   mul_scale            out = a * b * s                         Hadamard + ScalingFactor (interaction_block.py:661-664)
  *   gather_rows          out[j,:] = x[idx[j],:]                  h[id_a], h[id_c], x[id_swap] (embedding_block.py:70-71)
  *   segment_sum_rows     out[r,:] = sum_k src[perm[k],:] over the CSR row r — the gather's backward, no atomics
- * n = number of floats, must be a multiple of 4; pointers 16-byte aligned.
+ * n = number of floats (any; the first n - n%4 are processed as 128-bit vectors); pointers 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */
 int gemnet_scaled_silu_fwd(const float* z, const float* x, float s, int64_t n, int32_t mode, float* out, void* stream);
 int gemnet_scaled_silu_bwd(const float* z, const float* g, float s, int64_t n, float* gz, void* stream);

@@ -189,3 +189,30 @@ def test_training_step_direct_forces(dev):
         assert err < 2e-4, f"{name}: {err:.2e}"
         checked += 1
     assert checked > 100
+
+
+@pytest.mark.parametrize("name", ["T", "Q", "dT", "dQ"])
+def test_engine_matches_autograd_path(name, dev):
+    """eval() runs on the tape engine (engine.py); it must agree with the torch.autograd evaluation of the same
+    kernels to float32 round-off (summation order of gradient accumulation differs)."""
+    fx = H.load_npz(f"model_{name}.npz")
+    kw = H.model_kwargs(fx)
+    sd = go.synthetic_state_dict(kw, seed=21)
+    model = make_model(kw, sd, dev)
+    ids = fx["mol_ids"].tolist()[:8]
+    from gemnet_pytorch_b200 import build_batch
+    inputs = to_dev(build_batch(*H.molecules(ids), kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]), dev)
+    assert model.use_engine
+    E1, F1 = model(inputs)
+    E2, F2 = model.forward_autograd(inputs)
+    assert inputs["R"].requires_grad is False
+    assert (E1 - E2).abs().max() <= 1e-6 * E2.abs().max()
+    assert (F1 - F2).abs().max() <= 2e-6 * F2.abs().max()
+    # multi-target through the engine
+    if name == "T":
+        kw2 = dict(kw, num_targets=2)
+        m2 = make_model(kw2, go.synthetic_state_dict(kw2, seed=21), dev)
+        Ea, Fa = m2(inputs)
+        Eb, Fb = m2.forward_autograd(inputs)
+        assert Fa.shape == Fb.shape == (inputs["R"].shape[0], 2, 3)
+        assert (Fa - Fb).abs().max() <= 2e-6 * Fb.abs().max() and (Ea - Eb).abs().max() <= 1e-6 * Eb.abs().max()
