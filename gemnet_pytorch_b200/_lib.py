@@ -49,6 +49,9 @@ _SIGNATURES = {
     "gemnet_mul_scale_bwd": [_P, _P, _P, _F, _I64, _P, _P, _P],
     "gemnet_gather_rows": [_P, _P, _I64, _I32, _P, _P],
     "gemnet_segment_sum_rows": [_P, _P, _P, _I64, _I32, _P, _P],
+    "gemnet_dense_pack_floats": [_I32, _I32],
+    "gemnet_dense_pack_weight": [_P, _I64, _I64, _I32, _I32, _P, _P],
+    "gemnet_dense_tc": [_P, _P, _I64, _I32, _I32, _P, _I32, _I32, _F, _P, _F, _P, _P, _P],
     "gemnet_graph_build_host": [_P, _P, _I64, _D, _D, _I32, ctypes.POINTER(_P)],
     "gemnet_graph_size": [_P, ctypes.c_char_p],
     "gemnet_graph_copy_host": [_P, ctypes.c_char_p, _P],
@@ -57,6 +60,7 @@ _SIGNATURES = {
 _RESTYPES = {
     "gemnet_last_error": ctypes.c_char_p,
     "gemnet_segbilinear_workspace_bytes": _I64,
+    "gemnet_dense_pack_floats": _I64,
     "gemnet_graph_size": _I64,
     "gemnet_graph_free": None,
 }

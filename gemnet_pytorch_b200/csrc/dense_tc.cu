@@ -1,0 +1,380 @@
+// N1: fused dense layer on the 5th-generation tensor cores — fp32 in / fp32 out GEMM with error-compensated TF32
+// ("3xTF32": hi*hi + hi*lo + lo*hi + lo*lo, fp32 accumulation in TMEM; ~2^-21 relative, i.e. fp32-grade, because the
+// parity gate does not allow a plain TF32 / BF16 dense stack) with the surrounding pointwise work fused in:
+//
+//     A      = x              (M x K)      or   x .* xmul          (prologue Hadamard: the activation backward)
+//     acc    = A @ B^T,   B = (N x K) weight operand  (pre-packed: tf32 hi/lo, K-major SWIZZLE_128B, resident in smem)
+//     y      = s_acc * f(acc) + s_res * res            f = identity | ScaledSiLU  (silu(z)/0.6, base_layers.py:51-58)
+//     dact   = s_acc * f'(acc)                         (optional; what the backward multiplies the gradient with)
+//
+// which covers Dense (base_layers.py:45-48), the tail of ResidualLayer ((x + act(z))/sqrt(2), :86-89) and their
+// input-gradients ((g .* dact) @ W [+ s*g]).  The reference runs these as cuBLAS SIMT-fp32 GEMMs + 2-4 pointwise kernels.
+//
+// Persistent warp-specialised kernel, one CTA per SM, 128-row tiles:
+//   warps 0-7   producers: coalesced 128-bit loads of the fp32 rows, hi = rna_tf32(x), lo = rna_tf32(x - hi), both written into the
+//               K-major SWIZZLE_128B stage (32 k per chunk = one 128-byte row per operand row)
+//   warp 8      one thread issues tcgen05.mma.kind::tf32 (M128, N, K8) into one of two TMEM accumulator slots
+//   warp 9      one thread loads the whole packed weight image once per CTA with cp.async.bulk
+//   warps 10-13 epilogue: tcgen05.ld, activation / scale / residual, 128-byte row-segment stores
+#include "common.cuh"
+
+namespace gemnet {
+namespace dtc {
+
+constexpr int TILE_M = 128;
+constexpr int KB = 32;                          // k per chunk (tf32: 32 x 4 B = one 128-byte swizzle row)
+constexpr int A_HALF_BYTES = TILE_M * KB * 4;   // 16384: one of hi / lo
+constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;   // 32768
+constexpr int kStages = 3;
+constexpr int PRODUCER_WARPS = 8, PRODUCER_THREADS = PRODUCER_WARPS * 32;
+constexpr int EPI_WARP0 = PRODUCER_WARPS + 2;
+constexpr int THREADS = (PRODUCER_WARPS + 2 + 4) * 32;  // 448
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major SWIZZLE_128B, 8-row groups of 1024 B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+constexpr float kSiluScale = 1.0f / 0.6f;
+
+// ---------------------------------------------------------------------------------------------- weight packing
+// image: [kb][h][n][32 elements, 16-byte chunks XOR-swizzled by (n & 7)];  element (n, k) = src[n*sn + k*sk]
+__global__ void pack_weight_kernel(const float* __restrict__ src, int64_t sn, int64_t sk, int N_src, int K_src, int N,
+                                   int K, float* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  const int k = idx % K, n = idx / K;
+  const float w = (n < N_src && k < K_src) ? src[(int64_t)n * sn + (int64_t)k * sk] : 0.f;
+  const float hi = tf32_round(w), lo = tf32_round(w - hi);
+  const int kb = k / KB, kl = k % KB;
+  const int phys = n * KB + (((kl >> 2) ^ (n & 7)) << 2) + (kl & 3);
+  dst[(int64_t)(kb * 2 + 0) * N * KB + phys] = hi;
+  dst[(int64_t)(kb * 2 + 1) * N * KB + phys] = lo;
+}
+
+struct Params {
+  const float* x;      // (M, ldx) rows, K_src valid columns
+  const float* xmul;   // optional (M, ldx) prologue multiplier
+  const float* Wp;     // packed image, NKB * 2 * N * 32 floats
+  const float* res;    // optional (M, N_out) residual
+  float* y;            // (M, N_out)
+  float* dact;         // optional (M, N_out)
+  int64_t M;
+  int ldx, K_src, N_out;
+  int act;             // 0 identity, 1 ScaledSiLU
+  float s_acc, s_res;
+};
+
+template <int NKB, int N>
+__global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, int n_tiles) {
+  constexpr int W_BYTES = NKB * 2 * N * KB * 4;
+  constexpr uint32_t TMEM_COLS = 2 * N;  // two accumulator slots
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_base = base;                       // resident weight image
+  const uint32_t stage_base = base + W_BYTES;         // kStages * STAGE_BYTES
+  const uint32_t bar_base = stage_base + kStages * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 5);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(sm + W_BYTES + kStages * STAGE_BYTES + 8 * (2 * kStages + 5));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), PRODUCER_WARPS);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 4);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == PRODUCER_WARPS) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < PRODUCER_WARPS) {
+    // ============================================================ producers
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t r0 = (int64_t)tile * TILE_M;
+      for (int kb = 0; kb < NKB; ++kb, ++g) {
+        const int stage = g % kStages;
+        const uint32_t parity = (g / kStages) & 1u;
+        // 128 rows x 8 float4 per chunk = 1024 pieces, 4 per thread; consecutive threads -> consecutive 16 B
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int piece = tid + q * PRODUCER_THREADS;
+          const int row = piece >> 3, j = piece & 7;
+          const int64_t r = r0 + row;
+          const int k = kb * KB + j * 4;
+          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < p.M && k < p.K_src) {
+            v[q] = __ldg(reinterpret_cast<const float4*>(p.x + r * p.ldx + k));
+            if (p.xmul) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(p.xmul + r * p.ldx + k));
+              v[q] = make_float4(v[q].x * m.x, v[q].y * m.y, v[q].z * m.z, v[q].w * m.w);
+            }
+          }
+        }
+        mbar_wait(empty_bar(stage), parity ^ 1u);
+        uint8_t* a_hi = sm + W_BYTES + stage * STAGE_BYTES;
+        uint8_t* a_lo = a_hi + A_HALF_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int piece = tid + q * PRODUCER_THREADS;
+          const int row = piece >> 3, j = piece & 7;
+          const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+          const float4 h = make_float4(tf32_round(v[q].x), tf32_round(v[q].y), tf32_round(v[q].z), tf32_round(v[q].w));
+          *reinterpret_cast<float4*>(a_hi + off) = h;
+          *reinterpret_cast<float4*>(a_lo + off) = make_float4(tf32_round(v[q].x - h.x), tf32_round(v[q].y - h.y),
+                                                               tf32_round(v[q].z - h.z), tf32_round(v[q].w - h.w));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+      }
+    }
+  } else if (warp == PRODUCER_WARPS) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      mbar_wait(w_bar, 0);  // weight image resident
+      uint32_t g = 0;
+      for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int slot = it & 1;
+        mbar_wait(acc_empty(slot), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const uint32_t d_tmem = tmem_base + slot * N;
+        for (int kb = 0; kb < NKB; ++kb, ++g) {
+          const int stage = g % kStages;
+          mbar_wait(full_bar(stage), (g / kStages) & 1u);
+          tc_fence_after();
+          const uint32_t sa = stage_base + stage * STAGE_BYTES;
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_HALF_BYTES);
+          const uint64_t w_hi = make_desc(w_base + (kb * 2 + 0) * N * KB * 4);
+          const uint64_t w_lo = make_desc(w_base + (kb * 2 + 1) * N * KB * 4);
+#pragma unroll
+          for (int kk = 0; kk < KB / 8; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 8 tf32 = 32 bytes along K
+            umma_tf32(d_tmem, a_hi + adv, w_hi + adv, kIdesc, (kb | kk) != 0);
+            umma_tf32(d_tmem, a_hi + adv, w_lo + adv, kIdesc, 1u);
+            umma_tf32(d_tmem, a_lo + adv, w_hi + adv, kIdesc, 1u);
+            umma_tf32(d_tmem, a_lo + adv, w_lo + adv, kIdesc, 1u);
+          }
+          umma_commit(empty_bar(stage));
+        }
+        umma_commit(acc_full(slot));
+      }
+    }
+  } else if (warp == PRODUCER_WARPS + 1) {
+    // ============================================================ weight loader (once per CTA)
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, W_BYTES);
+      constexpr int PIECE = 32768;
+      for (int off = 0; off < W_BYTES; off += PIECE)
+        bulk_g2s(w_base + off, reinterpret_cast<const uint8_t*>(p.Wp) + off, (W_BYTES - off) < PIECE ? (W_BYTES - off) : PIECE,
+                 w_bar);
+    }
+  } else {
+    // ============================================================ epilogue (4 warps = 128 TMEM lanes = 128 rows)
+    const int ew = warp & 3;  // a warp can only touch TMEM lanes [32*(warp%4), +32): the quadrant fixes the rows it owns
+    for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int slot = it & 1;
+      mbar_wait(acc_full(slot), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const int64_t r = (int64_t)tile * TILE_M + ew * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + slot * N + c0, acc);
+        if (r < p.M && c0 < p.N_out) {
+          float* yrow = p.y + r * p.N_out + c0;
+          const float* rrow = p.res ? p.res + r * p.N_out + c0 : nullptr;
+          float* drow = p.dact ? p.dact + r * p.N_out + c0 : nullptr;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (c0 + 4 * q >= p.N_out) break;
+            float o[4], d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float z = __uint_as_float(acc[4 * q + u]);
+              if (p.act) {
+                const float sg = 1.0f / (1.0f + expf(-z));
+                o[u] = z * sg * kSiluScale * p.s_acc;
+                d[u] = sg * (1.0f + z * (1.0f - sg)) * kSiluScale * p.s_acc;
+              } else {
+                o[u] = z * p.s_acc;
+                d[u] = p.s_acc;
+              }
+            }
+            if (rrow) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + 4 * q));
+              o[0] += p.s_res * rv.x; o[1] += p.s_res * rv.y; o[2] += p.s_res * rv.z; o[3] += p.s_res * rv.w;
+            }
+            *reinterpret_cast<float4*>(yrow + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            if (drow) *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(slot));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int NKB, int N>
+static int launch(const Params& p, cudaStream_t st) {
+  constexpr int W_BYTES = NKB * 2 * N * KB * 4;
+  constexpr int SMEM = 1024 + W_BYTES + kStages * STAGE_BYTES + 512;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<NKB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  const int n_tiles = (int)ceil_div(p.M, TILE_M);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  dense_tc_kernel<NKB, N><<<n_tiles < sms ? n_tiles : sms, THREADS, SMEM, st>>>(p, n_tiles);
+  return check_launch("gemnet_dense_tc");
+}
+
+}  // namespace dtc
+}  // namespace gemnet
+
+using namespace gemnet;
+
+static inline int round_k(int K) { return K <= 32 ? 32 : (K <= 64 ? 64 : 128); }
+static inline int round_n(int N) { return N <= 64 ? 64 : 128; }
+
+GEMNET_API int64_t gemnet_dense_pack_floats(int32_t N, int32_t K) {
+  if (N < 1 || N > 128 || K < 1 || K > 128) return -1;
+  return (int64_t)(round_k(K) / dtc::KB) * 2 * round_n(N) * dtc::KB;
+}
+
+GEMNET_API int gemnet_dense_pack_weight(const float* W, int64_t stride_n, int64_t stride_k, int32_t N, int32_t K,
+                                        float* packed, void* stream) {
+  GEMNET_REQUIRE(W && packed, "null pointer");
+  GEMNET_REQUIRE(N >= 1 && N <= 128 && K >= 1 && K <= 128, "dense_tc supports N, K in [1, 128]");
+  const int Np = round_n(N), Kp = round_k(K);
+  dtc::pack_weight_kernel<<<(Np * Kp + 255) / 256, 256, 0, as_stream(stream)>>>(W, stride_n, stride_k, N, K, Np, Kp,
+                                                                                packed);
+  return check_launch("gemnet_dense_pack_weight");
+}
+
+GEMNET_API int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int32_t ldx,
+                               const float* packed, int32_t N, int32_t act, float s_acc, const float* res, float s_res,
+                               float* y, float* dact, void* stream) {
+  GEMNET_REQUIRE(M >= 0, "negative size");
+  GEMNET_REQUIRE(N >= 4 && N <= 128 && N % 4 == 0 && K >= 4 && K <= 128 && K % 4 == 0 && ldx % 4 == 0 && ldx >= K,
+                 "dense_tc needs N, K multiples of 4 in [4, 128] and a row stride that keeps 16-byte alignment");
+  if (M == 0) return 0;
+  GEMNET_REQUIRE(x && packed && y, "null pointer");
+  GEMNET_REQUIRE((((uintptr_t)x | (uintptr_t)xmul | (uintptr_t)packed | (uintptr_t)res | (uintptr_t)y | (uintptr_t)dact) % 16) == 0,
+                 "pointers must be 16-byte aligned");
+  dtc::Params p{x, xmul, packed, res, y, dact, M, ldx, K, N, act, s_acc, s_res};
+  cudaStream_t st = as_stream(stream);
+  const int Kp = round_k(K), Np = round_n(N);
+  if (Kp == 32 && Np == 64) return dtc::launch<1, 64>(p, st);
+  if (Kp == 32 && Np == 128) return dtc::launch<1, 128>(p, st);
+  if (Kp == 64 && Np == 64) return dtc::launch<2, 64>(p, st);
+  if (Kp == 64 && Np == 128) return dtc::launch<2, 128>(p, st);
+  if (Kp == 128 && Np == 64) return dtc::launch<4, 64>(p, st);
+  return dtc::launch<4, 128>(p, st);
+}

@@ -1,0 +1,91 @@
+"""Fused dense layers on tcgen05 (include/gemnet_b200.h gemnet_dense_tc): forward/backward pairs in the protocol the
+tape engine (engine.py) consumes — `forward(ctx, ...)` / `backward(ctx, *grads)` — for
+  * Dense        y = f(x W^T)                      (base_layers.py:45-48)      backward  gx = (g .* dact) W
+  * ResidualTC   y = (x + f(f(x W1^T) W2^T)) * s   (base_layers.py:61-89)      backward  gx = ((g .* d2) W2 .* d1) W1 + s g
+Weights are packed once per (storage, version, orientation) into the kernel's resident shared-memory image.
+"""
+import torch
+
+from . import _lib
+from .ops import _L, _check, _f32, _p, _stream
+
+_packs = {}
+
+
+def supported(N, K):
+    return 4 <= N <= 128 and 4 <= K <= 128 and N % 4 == 0 and K % 4 == 0
+
+
+def packed_weight(W, transpose):
+    """B operand of acc = A @ B^T.  transpose=False: B = W (N x K) -> y = x W^T;  True: B = W^T -> gx = g W."""
+    key = (W.data_ptr(), W._version, tuple(W.shape), tuple(W.stride()), transpose)
+    hit = _packs.get(key)
+    if hit is not None:
+        return hit
+    N, K = (W.shape[1], W.shape[0]) if transpose else (W.shape[0], W.shape[1])
+    sn, sk = (W.stride(1), W.stride(0)) if transpose else (W.stride(0), W.stride(1))
+    n = _L().gemnet_dense_pack_floats(N, K)
+    buf = torch.empty(n, dtype=torch.float32, device=W.device)
+    _check(_L().gemnet_dense_pack_weight(_p(W), sn, sk, N, K, _p(buf), _stream()), "gemnet_dense_pack_weight")
+    if len(_packs) > 4096:
+        _packs.clear()
+    _packs[key] = (buf, N, K)
+    return _packs[key]
+
+
+def dense_tc(x, pack, act=0, s_acc=1.0, res=None, s_res=0.0, xmul=None, want_dact=False):
+    """y (M,N) [, dact] = gemnet_dense_tc(...).  x may be a row-strided view (inner stride 1)."""
+    buf, N, K = pack
+    assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == K and x.dtype == torch.float32 and x.is_cuda
+    M, ldx = x.shape[0], x.stride(0)
+    if xmul is not None:
+        assert xmul.shape == x.shape and xmul.stride() == x.stride()
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    dact = torch.empty_like(y) if want_dact else None
+    _check(_L().gemnet_dense_tc(_p(x), _p(xmul), M, K, ldx, _p(buf), N, act, s_acc, _p(res), s_res, _p(y), _p(dact),
+                                _stream()), "gemnet_dense_tc")
+    return (y, dact) if want_dact else y
+
+
+class DenseTC:
+    """forward(ctx, x, W, act) -> y ; backward(ctx, g) -> (gx, None, None)"""
+
+    @staticmethod
+    def forward(ctx, x, W, act):
+        x = _f32(x) if x.stride(-1) != 1 else x
+        need = ctx.needs_input_grad[0]
+        ctx.W, ctx.act = W, act
+        if act and need:
+            y, ctx.dact = dense_tc(x, packed_weight(W, False), act=1, want_dact=True)
+        else:
+            y, ctx.dact = dense_tc(x, packed_weight(W, False), act=act), None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32(g)
+        return dense_tc(g, packed_weight(ctx.W, True), xmul=ctx.dact), None, None
+
+
+class ResidualTC:
+    """forward(ctx, x, W1, W2, s) -> (x + ssilu(ssilu(x W1^T) W2^T)) * s ; backward(ctx, g) -> (gx, None, None, None)"""
+
+    @staticmethod
+    def forward(ctx, x, W1, W2, s):
+        x = _f32(x)
+        need = ctx.needs_input_grad[0]
+        ctx.W1, ctx.W2, ctx.s = W1, W2, s
+        if need:
+            y1, ctx.d1 = dense_tc(x, packed_weight(W1, False), act=1, want_dact=True)
+            out, ctx.d2 = dense_tc(y1, packed_weight(W2, False), act=1, s_acc=s, res=x, s_res=s, want_dact=True)
+        else:
+            y1 = dense_tc(x, packed_weight(W1, False), act=1)
+            out = dense_tc(y1, packed_weight(W2, False), act=1, s_acc=s, res=x, s_res=s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32(g)
+        t = dense_tc(g, packed_weight(ctx.W2, True), xmul=ctx.d2)                 # (g .* s f'(z2)) W2
+        gx = dense_tc(t, packed_weight(ctx.W1, True), xmul=ctx.d1, res=g, s_res=ctx.s)  # (t .* f'(z1)) W1 + s g
+        return gx, None, None, None

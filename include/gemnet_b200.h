@@ -222,6 +222,22 @@ int gemnet_segment_sum_rows(const float* src, const int32_t* perm, const int32_t
                             float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N1: fused dense layer on tcgen05 (Dense / ResidualLayer, gemnet/model/layers/base_layers.py:5-89):
+ *     y    = s_acc * f(A @ B^T) + s_res * res,   A = x or x .* xmul,   f = identity (act=0) | silu(.)/0.6 (act=1)
+ *     dact = s_acc * f'(A @ B^T)                 (optional output: the factor the backward multiplies the gradient by)
+ * fp32 in / fp32 out; the product is an error-compensated TF32 GEMM (hi*hi + hi*lo + lo*hi + lo*lo, fp32 accumulate
+ * in TMEM) so the result is fp32-grade.  B is given pre-packed: gemnet_dense_pack_weight converts an (N x K) operand
+ * with arbitrary element strides (so W, W^T and column slices of W all pack without copies) into the resident
+ * shared-memory image (gemnet_dense_pack_floats(N, K) floats).  N, K multiples of 4 in [4, 128]; x rows have stride ldx.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t gemnet_dense_pack_floats(int32_t N, int32_t K);
+int gemnet_dense_pack_weight(const float* W, int64_t stride_n, int64_t stride_k, int32_t N, int32_t K, float* packed,
+                             void* stream);
+int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int32_t ldx, const float* packed,
+                    int32_t N, int32_t act, float s_acc, const float* res, float s_res, float* y, float* dact,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * H0  host index builder: DataContainer.__getitem__ / get_triplets / get_quadruplets
  *     (gemnet/training/data_container.py:156-408, 411-489).  HOST function, native C++.
  * Input: molecules concatenated, R_host float64 (n_atoms,3), n_per_mol int32[n_mol].

@@ -424,3 +424,61 @@ def test_segmented_bilinear_tcgen05_matches_fp32_kernel_and_oracle(ops, dev, ids
     # replays are bitwise identical (no atomics, fixed order)
     out1b = ops.segmented_bilinear(x, sph, rbf_W1, W, expand, rowptr, 1.3, algo=1)
     assert torch.equal(out1, out1b)
+
+
+# ----------------------------------------------------------------------------- N1: fused dense on tcgen05 (3xTF32)
+@pytest.mark.parametrize("M,K,N", [(1, 128, 128), (300, 16, 128), (8186, 128, 128), (5000, 128, 64), (777, 64, 128),
+                                   (20000, 128, 128), (130, 128, 16)])
+def test_dense_tc_matches_fp64(dev, M, K, N):
+    from gemnet_pytorch_b200 import dense_ops as D
+    torch.manual_seed(M + K + N)
+    x = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    ssilu = lambda t: torch.nn.functional.silu(t) / 0.6  # noqa: E731
+    xd, Wd = x.double().cpu(), W.double().cpu()
+    y = D.dense_tc(x, D.packed_weight(W, False))
+    e_plain = relerr(y, xd @ Wd.t())
+    e_cublas = relerr(torch.mm(x, W.t()), xd @ Wd.t())
+    print(f"M={M} K={K} N={N}: 3xTF32 rel err {e_plain:.2e} (cuBLAS fp32 {e_cublas:.2e})")
+    assert e_plain < 2e-6
+    res = torch.randn(M, N, device=dev)
+    y2, d2 = D.dense_tc(x, D.packed_weight(W, False), act=1, s_acc=0.7, res=res, s_res=0.3, want_dact=True)
+    z = (xd @ Wd.t()).requires_grad_(True)
+    want = 0.7 * ssilu(z) + 0.3 * res.double().cpu()
+    assert relerr(y2, want) < 2e-6
+    (dwant,) = torch.autograd.grad((0.7 * ssilu(z)).sum(), z)
+    assert relerr(d2, dwant) < 2e-6
+    # transposed operand + prologue multiply (the backward form): (g .* d) @ W
+    g = torch.randn(M, N, device=dev)
+    gx = D.dense_tc(g, D.packed_weight(W, True), xmul=d2)
+    assert relerr(gx, (g.double().cpu() * dwant) @ Wd) < 2e-6
+    # column-slice views of a wider weight (edge embedding) pack without copies
+    if K == 128 and N == 128:
+        Wwide = torch.randn(N, 3 * K, device=dev) / K ** 0.5
+        ys = D.dense_tc(x, D.packed_weight(Wwide[:, K:2 * K], False))
+        assert relerr(ys, xd @ Wwide[:, K:2 * K].double().cpu().t()) < 2e-6
+
+
+def test_residual_tc_forward_backward(dev):
+    from gemnet_pytorch_b200 import dense_ops as D
+    from gemnet_pytorch_b200.engine import Tape
+    torch.manual_seed(0)
+    M = 3000
+    x = torch.randn(M, 128, device=dev)
+    W1, W2 = (torch.randn(128, 128, device=dev) / 128 ** 0.5 for _ in range(2))
+    s = 0.7071067811865475
+    tape = Tape()
+    tape.require(x)
+    y = tape.apply(D.ResidualTC, x, W1, W2, s)
+    g = torch.randn_like(y)
+    tape.add_grad(y, g)
+    tape.backward()
+    gx = tape.grads[id(x)]
+    ssilu = lambda t: torch.nn.functional.silu(t) / 0.6  # noqa: E731
+
+    def ref(a):
+        return (a + ssilu(ssilu(a @ W1.double().cpu().t()) @ W2.double().cpu().t())) * s
+
+    assert relerr(y, ref(x.double().cpu())) < 2e-6
+    (gx0,) = oracle_grads(ref, [x], g)
+    assert relerr(gx, gx0) < 3e-6
