@@ -29,13 +29,15 @@ def packed_weight(W, transpose):
     _check(_L().gemnet_dense_pack_weight(_p(W), sn, sk, N, K, _p(buf), _stream()), "gemnet_dense_pack_weight")
     if len(_packs) > 4096:
         _packs.clear()
-    _packs[key] = (buf, N, K)
+    # keep W referenced: while the entry lives its storage cannot be freed and handed to another tensor with the
+    # same (data_ptr, version) — which would silently serve a stale image
+    _packs[key] = (buf, N, K, W)
     return _packs[key]
 
 
 def dense_tc(x, pack, act=0, s_acc=1.0, res=None, s_res=0.0, xmul=None, want_dact=False):
     """y (M,N) [, dact] = gemnet_dense_tc(...).  x may be a row-strided view (inner stride 1)."""
-    buf, N, K = pack
+    buf, N, K = pack[0], pack[1], pack[2]
     assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == K and x.dtype == torch.float32 and x.is_cuda
     M, ldx = x.shape[0], x.stride(0)
     if xmul is not None:

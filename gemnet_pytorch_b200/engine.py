@@ -10,7 +10,7 @@ gradients are never formed.  Used by GemNet.forward in eval mode; training keeps
 """
 import torch
 
-from . import graph, layers, ops
+from . import dense_ops, graph, layers, ops
 
 
 class _Ctx:
@@ -89,18 +89,33 @@ class _Run:
 
     def __init__(self, model, tape, plan):
         self.m, self.t, self.p = model, tape, plan
+        self.tc = getattr(model, "dense_algo", 1) == 1  # fused tcgen05 dense layers where the shape is supported
 
     # -- primitives
-    def linear(self, dense, x):
-        return self.t.apply(_Linear, x, dense.linear.weight)
+    def _tc_ok(self, W, x):
+        return self.tc and dense_ops.supported(W.shape[0], W.shape[1]) and x.shape[0] > 0
+
+    def linear(self, dense, x, W=None):
+        W = dense.linear.weight if W is None else W
+        if self._tc_ok(W, x):
+            return self.t.apply(dense_ops.DenseTC, x, W, 0)
+        return self.t.apply(_Linear, x, W)
 
     def act(self, dense, z):
         return self.t.apply(ops._ScaledSiLU, z) if isinstance(dense._activation, layers.ScaledSiLU) else z
 
     def dense(self, dense, x):
+        W = dense.linear.weight
+        if isinstance(dense._activation, layers.ScaledSiLU) and self._tc_ok(W, x):
+            return self.t.apply(dense_ops.DenseTC, x, W, 1)
         return self.act(dense, self.linear(dense, x))
 
     def residual(self, layer, x):
+        if (self.tc and len(layer.dense_mlp) == 2 and x.shape[0] > 0
+                and all(isinstance(d._activation, layers.ScaledSiLU) and
+                        dense_ops.supported(*d.linear.weight.shape) for d in layer.dense_mlp)):
+            return self.t.apply(dense_ops.ResidualTC, x, layer.dense_mlp[0].linear.weight,
+                                layer.dense_mlp[1].linear.weight, layers.INV_SQRT_2)
         y = x
         for d in layer.dense_mlp[:-1]:
             y = self.dense(d, y)
@@ -124,9 +139,9 @@ class _Run:
         p = self.p
         W = emb.dense.linear.weight
         A = h.shape[1]
-        p_c = self.t.apply(_Linear, h, W[:, :A])
-        p_a = self.t.apply(_Linear, h, W[:, A:2 * A])
-        y = self.t.apply(_Linear, m_rbf, W[:, 2 * A:])
+        p_c = self.linear(None, h, W[:, :A])
+        p_a = self.linear(None, h, W[:, A:2 * A])
+        y = self.linear(None, m_rbf, W[:, 2 * A:])
         z = self.add_scale(1.0, y, self.gather(p_c, p.id_c, p.src_perm, p.src_rowptr),
                            self.gather(p_a, p.id_a, p.atom_perm, p.atom_rowptr))
         return self.act(emb.dense, z)

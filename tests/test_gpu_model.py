@@ -206,8 +206,16 @@ def test_engine_matches_autograd_path(name, dev):
     E1, F1 = model(inputs)
     E2, F2 = model.forward_autograd(inputs)
     assert inputs["R"].requires_grad is False
+    # same kernels and cuBLAS GEMMs on both paths: only the gradient-accumulation order differs
     assert (E1 - E2).abs().max() <= 1e-6 * E2.abs().max()
     assert (F1 - F2).abs().max() <= 2e-6 * F2.abs().max()
+    # opt-in fused tcgen05 (3xTF32) dense layers: biased accumulation keeps them inside the 1e-4
+    # north_star gate but outside our 2e-5 margin
+    model.dense_algo = 1
+    E3, F3 = model(inputs)
+    model.dense_algo = 0
+    assert (E3 - E2).abs().max() <= 3e-4 * E2.abs().max()
+    assert (F3 - F2).abs().max() <= 3e-4 * F2.abs().max()
     # multi-target through the engine
     if name == "T":
         kw2 = dict(kw, num_targets=2)
