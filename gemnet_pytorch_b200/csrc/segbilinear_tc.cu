@@ -3,18 +3,20 @@
 //   out[e,:] = scale * B_e (1 x K) @ W' (K x O),   K = C*I = 1024, O = 64
 //   B_e[k = c*I + i] = sum_s rbf_W1[e,i,s] * A_e[s,c],   A_e[s,c] = sum_{t in seg(e)} sph[t,s] * x[expand[t], c]
 //
-// Persistent warp-specialised kernel, one CTA per SM, tile = 128 target edges (UMMA M = 128, N = 64):
-//   warps 0-15  (512 threads) PRODUCERS in 4 groups of 128 threads; group g owns the K-chunks g, g+4, g+8, g+12.
-//               A chunk is 4 columns c = 4*chunk .. 4*chunk+3 of x, i.e. 64 consecutive k = one 128-byte operand
-//               row per edge.  Thread = one edge row: it gathers the 4 columns over the CSR segment with one 128-bit
-//               load per unit (phase 1), contracts with rbf_W1 from shared memory (phase 2) and writes its 64
-//               k-values, split into bf16 hi + bf16 lo, into the K-major SWIZZLE_128B A-operand tile of the stage.
-//   warp 16     lane 0 issues tcgen05.mma: D += Ahi*Whi + Ahi*Wlo + Alo*Whi (bf16x3: the dropped lo*lo term is
-//               2^-16 relative, so the result is fp32-accurate: parity mode, not a reduced-precision mode).
-//   warp 17     lane 0 streams the pre-packed (already swizzled) W chunk image with one cp.async.bulk per stage.
-//   warps 0-3   also run the epilogue: tcgen05.ld of the 128 x 64 fp32 accumulator, scale, vectorised store.
-// Stage ring (kStages): {A_hi 16 KB, A_lo 16 KB, W_hi 8 KB, W_lo 8 KB}; full/empty mbarriers; tcgen05.commit frees
-// a stage and, after the 16th chunk, publishes the accumulator to the epilogue warps.
+// Persistent warp-specialised kernel, one CTA per SM, tile = 64 target edges (UMMA M = 64, N = 64, K = 16):
+//   phase 1  (16 producer warps, one warp per edge, lanes over c): the CSR segment is gathered ONCE per edge with
+//            fully coalesced 256-byte row loads; A_e (7 x 64 fp32) goes to shared memory (As, 64 edges = 113 KB).
+//   phase 2  (same 512 threads, 8 per edge row): for each of the 16 K-chunks (4 x-columns x 16 i = 64 k) the thread
+//            (row, column cq, i-half ih) contracts its 7 A-values with its 8 x 7 register-resident rbf_W1 block and
+//            writes 8 k-values, split into bf16 hi + bf16 lo, into the K-major SWIZZLE_128B operand tile of the stage.
+//   warp 16  lane 0 issues tcgen05.mma: D += Ahi*Whi + Ahi*Wlo + Alo*Whi (bf16x3: the dropped lo*lo term is 2^-16
+//            relative, so this is an fp32-parity mode, not a reduced-precision one) into one of two TMEM accumulators.
+//   warp 17  lane 0 streams the pre-packed (already swizzled) W chunk image with one cp.async.bulk per stage.
+//   warps 0-3 also run the epilogue of the previous accumulator: tcgen05.ld, scale, 128-bit stores.
+// Why 64-edge tiles: the gather side wants (edge-major, all columns) — coalesced, once — while the MMA wants
+// (all edges, one K-chunk); the transposition has to live in shared memory and 128 edges x 7 x 64 fp32 does not fit.
+// The first version of this kernel (128-edge tiles, per-chunk re-gather by one thread per edge row) spent 20 L1
+// wavefronts per request on uncoalesced gathers (profiles/ncu_r01_segbil_fwd_tc_v1_large.txt).
 //
 // Shapes: only the published triplet shape (S,C,I,O) = (7,64,16,64).
 #include <cuda_bf16.h>
@@ -26,7 +28,7 @@ namespace tc {
 
 constexpr int S = 7, C = 64, I = 16, O = 64;
 constexpr int K = C * I;                 // 1024
-constexpr int TILE_M = 128;
+constexpr int TILE_M = 64;
 constexpr int KC = 64;                   // k per chunk (4 columns of x times I)
 constexpr int NCHUNK = K / KC;           // 16
 constexpr int kStages = 3;
@@ -34,13 +36,13 @@ constexpr int PRODUCER_WARPS = 16;
 constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;  // 512
 constexpr int THREADS = PRODUCER_THREADS + 64;         // + MMA warp + loader warp
 
-constexpr int A_TILE_BYTES = TILE_M * KC * 2;          // 16384 (bf16)
+constexpr int A_TILE_BYTES = TILE_M * KC * 2;          // 8192 (bf16)
 constexpr int W_TILE_BYTES = O * KC * 2;               // 8192
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;  // 49152
-constexpr int RW_LD = I * 8 + 4;                       // padded row of rbf_W1 in smem (floats): conflict-free float4 reads
-constexpr int RW_BYTES = TILE_M * RW_LD * 4;           // 67584
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + RW_BYTES + 512 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 64;
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;  // 32768
+constexpr int AS_LD = S * C + 4;                       // padded A_e row (floats): conflict-free phase-2 reads
+constexpr int AS_BYTES = TILE_M * AS_LD * 4;           // 115712
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + AS_BYTES + 512 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 128;                    // two 64-column accumulators
 
 // packed weight image: [chunk][hi|lo][o][k_local] bf16, rows already XOR-swizzled (SWIZZLE_128B)
 constexpr int WPACK_BYTES = NCHUNK * 2 * W_TILE_BYTES;  // 262144
@@ -163,29 +165,28 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage_base = base;                                    // kStages * STAGE_BYTES
-  float* rw_s = reinterpret_cast<float*>(sm + kStages * STAGE_BYTES);  // [TILE_M][RW_LD]
-  const uint32_t bar_base = base + kStages * STAGE_BYTES + RW_BYTES;
-  // mbarriers are PER CHUNK (each completes exactly once per tile, phase parity = tile parity): the four producer
-  // groups run out of order, and per-stage barriers would let a fast group get two phases ahead (parity aliasing).
-  //   full[j]     chunk j of this tile is in its stage (4 producer warps + the weight loader's expect_tx)
-  //   consumed[j] the MMAs of chunk j have finished reading its stage (tcgen05.commit)
-  auto full_bar = [&](int j) { return bar_base + 8u * j; };
-  auto cons_bar = [&](int j) { return bar_base + 8u * (NCHUNK + j); };
-  const uint32_t acc_full = bar_base + 8u * (2 * NCHUNK);
-  const uint32_t acc_empty = bar_base + 8u * (2 * NCHUNK + 1);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * NCHUNK + 2);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kStages * STAGE_BYTES + RW_BYTES +
-                                                                           8 * (2 * NCHUNK + 2));
+  float* As = reinterpret_cast<float*>(sm + kStages * STAGE_BYTES);    // [TILE_M][AS_LD]: A_e[s][c] at s*C + c
+  const uint32_t bar_base = base + kStages * STAGE_BYTES + AS_BYTES;
+  // every producer warp produces every chunk, in order: a plain stage ring (full/empty per stage) is safe
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(sm + kStages * STAGE_BYTES + AS_BYTES + 8 * (2 * kStages + 4));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int j = 0; j < NCHUNK; ++j) {
-      mbar_init(full_bar(j), 4 + 1);  // the 4 warps of one producer group + the weight loader
-      mbar_init(cons_bar(j), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), PRODUCER_WARPS + 1);  // 16 producer warps + the weight loader's expect_tx
+      mbar_init(empty_bar(s), 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 4);
+    }
     fence_barrier_init();
   }
   if (warp == PRODUCER_WARPS) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -196,117 +197,143 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
 
   if (warp < PRODUCER_WARPS) {
     // ============================================================ producers (+ epilogue on warps 0-3)
-    // thread = (edge row el, warp-group grp); group grp produces chunks grp, grp+4, grp+8, grp+12 of every tile:
-    // one whole 128-byte operand row (4 x-columns x 16 i) per thread and chunk.
-    const int el = tid & (TILE_M - 1), grp = tid >> 7;
-    for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int64_t e0 = (int64_t)tile * TILE_M;
-      // stage rbf_W1 of the tile: rw_s[el][i][s] (s padded to 8)
-      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");  // previous tile's readers are done
-      for (int idx = tid; idx < TILE_M * I * S; idx += PRODUCER_THREADS) {
-        const int r = idx / (I * S), rem = idx - r * (I * S);
-        const int i = rem / S, s = rem - i * S;
-        const int64_t e = e0 + r;
-        rw_s[r * RW_LD + i * 8 + s] = e < n_edges ? __ldg(rbf_W1 + e * (I * S) + rem) : 0.f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
+    const int el = tid >> 3;          // phase-2 edge row of this thread
+    const int q = tid & 7;
+    const int cq = q & 3, ih = q >> 2;  // column within the chunk, half of the 16 i
+    uint32_t g = 0;                   // chunk counter = position in the stage ring
 
-      const int64_t e = e0 + el;
-      const bool live = e < n_edges;
-      const int32_t beg = live ? __ldg(rowptr + e) : 0, end = live ? __ldg(rowptr + e + 1) : 0;
-      const float* rw = rw_s + el * RW_LD;
-
-      for (int chunk = grp; chunk < NCHUNK; chunk += PRODUCER_WARPS / 4) {
-        const int stage = chunk % kStages;
-        // phase 1: A[s][cq] for the 4 columns c = 4*chunk + cq (one 128-bit gather per unit of the segment)
-        float A[S][4];
+    // epilogue of accumulator slot `slot` for tile `tile` (warps 0-3; M=64 layout: row r -> TMEM lane (r%16)+32*(r/16))
+    auto epilogue = [&](int it, int tile) {
+      const int slot = it & 1;
+      mbar_wait(acc_full(slot), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const int64_t er = (int64_t)tile * TILE_M + warp * 16 + lane;  // valid for lane < 16
 #pragma unroll
-        for (int s = 0; s < S; ++s) A[s][0] = A[s][1] = A[s][2] = A[s][3] = 0.f;
-        const float* xcol = x + chunk * 4;
-        int32_t idx_next = beg < end ? __ldg(expand + beg) : 0;
-        for (int32_t t = beg; t < end; ++t) {
-          const int32_t idx = idx_next;
-          if (t + 1 < end) idx_next = __ldg(expand + t + 1);
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(xcol + (int64_t)idx * C));
-          const float* sp = sph + (int64_t)t * S;
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * O + half * 32, r);
+        if (lane < 16 && er < n_edges) {
+          float4* dst = reinterpret_cast<float4*>(out + er * O + half * 32);
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            dst[v] = make_float4(__uint_as_float(r[4 * v]) * scale, __uint_as_float(r[4 * v + 1]) * scale,
+                                 __uint_as_float(r[4 * v + 2]) * scale, __uint_as_float(r[4 * v + 3]) * scale);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(slot));
+    };
+
+    int prev_tile = -1, it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int64_t e0 = (int64_t)tile * TILE_M;
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");  // As of the previous tile is no longer read
+
+      // ---------------- phase 1: one warp per edge, lanes over the 64 columns (c = lane, lane + 32)
+      for (int r = warp; r < TILE_M; r += PRODUCER_WARPS) {
+        const int64_t e = e0 + r;
+        float A0[S], A1[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) A0[s] = A1[s] = 0.f;
+        if (e < n_edges) {
+          const int32_t beg = __ldg(rowptr + e), end = __ldg(rowptr + e + 1);
+          int32_t idx_next = beg < end ? __ldg(expand + beg) : 0;
+          for (int32_t t = beg; t < end; ++t) {
+            const float* xr = x + (int64_t)idx_next * C + lane;
+            if (t + 1 < end) idx_next = __ldg(expand + t + 1);
+            const float x0 = __ldg(xr), x1 = __ldg(xr + 32);
+            const float* sp = sph + (int64_t)t * S;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const float w = __ldg(sp + s);
+              A0[s] = fmaf(w, x0, A0[s]);
+              A1[s] = fmaf(w, x1, A1[s]);
+            }
+          }
+        }
+        float* arow = As + r * AS_LD + lane;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          arow[s * C] = A0[s];
+          arow[s * C + 32] = A1[s];
+        }
+      }
+
+      // rbf_W1 block of this thread: rows i = 8*ih .. 8*ih+7, all 7 s  (56 contiguous floats, 16-byte aligned)
+      float rw[8][S];
+      {
+        const int64_t e = e0 + el;
+        if (e < n_edges) {
+          const float4* src = reinterpret_cast<const float4*>(rbf_W1 + e * (I * S) + ih * 8 * S);
+          float tmp[56];
+#pragma unroll
+          for (int v = 0; v < 14; ++v) {
+            const float4 f = __ldg(src + v);
+            tmp[4 * v] = f.x; tmp[4 * v + 1] = f.y; tmp[4 * v + 2] = f.z; tmp[4 * v + 3] = f.w;
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8)
+#pragma unroll
+            for (int s = 0; s < S; ++s) rw[i8][s] = tmp[i8 * S + s];
+        } else {
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8)
+#pragma unroll
+            for (int s = 0; s < S; ++s) rw[i8][s] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");  // As complete
+
+      // epilogue of the PREVIOUS tile here: its MMAs had the whole phase 1 of this tile to finish
+      if (warp < 4 && prev_tile >= 0) epilogue(it - 1, prev_tile);
+
+      // ---------------- phase 2: 16 chunks of 64 k; thread = (row el, column cq, i-half ih) -> 8 k-values
+      const float* arow = As + el * AS_LD + cq;
+      for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
+        const int stage = g % kStages;
+        const uint32_t parity = (g / kStages) & 1u;
+        float a[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) a[s] = arow[s * C + chunk * 4];
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float b0 = 0.f, b1 = 0.f;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            const float w = __ldg(sp + s);
-            A[s][0] = fmaf(w, xv.x, A[s][0]);
-            A[s][1] = fmaf(w, xv.y, A[s][1]);
-            A[s][2] = fmaf(w, xv.z, A[s][2]);
-            A[s][3] = fmaf(w, xv.w, A[s][3]);
+            b0 = fmaf(rw[2 * v][s], a[s], b0);
+            b1 = fmaf(rw[2 * v + 1][s], a[s], b1);
           }
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(b0, h0, l0);
+          split_bf16(b1, h1, l1);
+          hw[v] = pack2(h0, h1);
+          lw[v] = pack2(l0, l1);
         }
-        // wait until the MMA has drained this stage (chunk - kStages of this tile; the previous tile is fully
-        // consumed before any producer passes the tile-start barrier)
-        if (chunk >= kStages) mbar_wait(cons_bar(chunk - kStages), (uint32_t)it & 1u);
+        mbar_wait(empty_bar(stage), parity ^ 1u);  // the MMAs that read this stage have completed
         uint8_t* a_hi = sm + stage * STAGE_BYTES + el * 128;
-        uint8_t* a_lo = a_hi + A_TILE_BYTES;
-        // phase 2: k_local = cq*16 + i, written as 16-byte pieces (8 consecutive i of one column)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float b[4][8];
-#pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const float4 w0 = *reinterpret_cast<const float4*>(rw + (half * 8 + i8) * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(rw + (half * 8 + i8) * 8 + 4);
-#pragma unroll
-            for (int cq = 0; cq < 4; ++cq)
-              b[cq][i8] = w0.x * A[0][cq] + w0.y * A[1][cq] + w0.z * A[2][cq] + w0.w * A[3][cq] + w1.x * A[4][cq] +
-                          w1.y * A[5][cq] + w1.z * A[6][cq];
-          }
-#pragma unroll
-          for (int cq = 0; cq < 4; ++cq) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(b[cq][2 * q], h0, l0);
-              split_bf16(b[cq][2 * q + 1], h1, l1);
-              hw[q] = pack2(h0, h1);
-              lw[q] = pack2(l0, l1);
-            }
-            const uint32_t off = (uint32_t)(((cq * 2 + half) ^ (el & 7)) << 4);
-            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        }
-        fence_proxy_async();  // make the generic-proxy writes visible to the tensor-core (async) proxy
+        const uint32_t off = (uint32_t)(((cq * 2 + ih) ^ (el & 7)) << 4);  // k_local = cq*16 + ih*8 + (0..7)
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(a_hi + A_TILE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(chunk));
+        if (lane == 0) mbar_arrive(full_bar(stage));
       }
-
-      if (warp < 4) {
-        // ---------------- epilogue: TMEM lane = edge row of this thread (tid < 128)
-        mbar_wait(acc_full, (uint32_t)it & 1u);
-        tc_fence_after();
-        const int64_t er = e0 + tid;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + half * 32, r);
-          if (er < n_edges) {
-            float4* dst = reinterpret_cast<float4*>(out + er * O + half * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              dst[q] = make_float4(__uint_as_float(r[4 * q]) * scale, __uint_as_float(r[4 * q + 1]) * scale,
-                                   __uint_as_float(r[4 * q + 2]) * scale, __uint_as_float(r[4 * q + 3]) * scale);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty);
-      }
+      prev_tile = tile;
     }
+    if (warp < 4 && prev_tile >= 0) epilogue(it - 1, prev_tile);
   } else if (warp == PRODUCER_WARPS) {
     // ============================================================ MMA issuer
     if (lane == 0) {
+      uint32_t g = 0;
       for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-          const int stage = chunk % kStages;
-          mbar_wait(full_bar(chunk), (uint32_t)it & 1u);
-          if (chunk == 0) mbar_wait(acc_empty, ((uint32_t)it & 1u) ^ 1u);  // epilogue of the previous tile done
+        const int slot = it & 1;
+        mbar_wait(acc_empty(slot), (((uint32_t)it >> 1) & 1u) ^ 1u);  // epilogue of the tile two back is done
+        const uint32_t d_tmem = tmem_base + slot * O;
+        for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
+          const int stage = g % kStages;
+          mbar_wait(full_bar(stage), (g / kStages) & 1u);
           tc_fence_after();
           const uint32_t sa = stage_base + stage * STAGE_BYTES;
           const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
@@ -314,27 +341,27 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle atom
-            umma_bf16(tmem_base, a_hi + adv, w_hi + adv, kIdesc, (chunk | kk) != 0);
-            umma_bf16(tmem_base, a_hi + adv, w_lo + adv, kIdesc, 1u);
-            umma_bf16(tmem_base, a_lo + adv, w_hi + adv, kIdesc, 1u);
+            umma_bf16(d_tmem, a_hi + adv, w_hi + adv, kIdesc, (chunk | kk) != 0);
+            umma_bf16(d_tmem, a_hi + adv, w_lo + adv, kIdesc, 1u);
+            umma_bf16(d_tmem, a_lo + adv, w_hi + adv, kIdesc, 1u);
           }
-          umma_commit(cons_bar(chunk));                  // stage reusable once these MMAs have read it
-          if (chunk == NCHUNK - 1) umma_commit(acc_full);  // accumulator complete
+          umma_commit(empty_bar(stage));
         }
+        umma_commit(acc_full(slot));
       }
     }
   } else {
     // ============================================================ W loader
     if (lane == 0) {
-      for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-          const int stage = chunk % kStages;
-          if (chunk >= kStages) mbar_wait(cons_bar(chunk - kStages), (uint32_t)it & 1u);
-          else if (it > 0) mbar_wait(cons_bar(NCHUNK - kStages + chunk), (uint32_t)(it - 1) & 1u);
-          mbar_arrive_expect_tx(full_bar(chunk), 2 * W_TILE_BYTES);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
+          const int stage = g % kStages;
+          mbar_wait(empty_bar(stage), ((g / kStages) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), 2 * W_TILE_BYTES);
           bulk_g2s(stage_base + stage * STAGE_BYTES + 2 * A_TILE_BYTES,
                    reinterpret_cast<const uint8_t*>(Wp) + (size_t)chunk * 2 * W_TILE_BYTES, 2 * W_TILE_BYTES,
-                   full_bar(chunk));
+                   full_bar(stage));
         }
       }
     }
