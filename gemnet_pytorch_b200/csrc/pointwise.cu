@@ -10,8 +10,11 @@ constexpr float kSiluScale = 1.0f / 0.6f;
 
 __device__ __forceinline__ float ssilu(float x) { return x / (1.0f + expf(-x)) * kSiluScale; }
 __device__ __forceinline__ float dssilu(float x) {
-  const float s = 1.0f / (1.0f + expf(-x));
-  return s * (1.0f + x * (1.0f - s)) * kSiluScale;
+  // sigmoid s and 1 - s from t = exp(-|x|) in (0, 1]: no overflow, no cancellation
+  const float t = expf(-fabsf(x));
+  const float r = 1.0f / (1.0f + t);
+  const float s = x >= 0.f ? r : t * r, oms = x >= 0.f ? t * r : r;
+  return s * fmaf(x, oms, 1.0f) * kSiluScale;
 }
 
 // mode 0: out = ssilu(z)

@@ -10,7 +10,9 @@
 //            (row, column cq, i-half ih) contracts its 7 A-values with its 8 x 7 register-resident rbf_W1 block and
 //            writes 8 k-values, split into bf16 hi + bf16 lo, into the K-major SWIZZLE_128B operand tile of the stage.
 //   warp 16  lane 0 issues tcgen05.mma: D += Ahi*Whi + Ahi*Wlo + Alo*Whi (bf16x3: the dropped lo*lo term is 2^-16
-//            relative, so this is an fp32-parity mode, not a reduced-precision one) into one of two TMEM accumulators.
+//            relative, so this is an fp32-parity mode, not a reduced-precision one).  Main products and correction
+//            products go to separate TMEM accumulators (two slots of each); the epilogue undoes the mean
+//            toward-zero rounding loss of the 64-step main chain.
 //   warp 17  lane 0 streams the pre-packed (already swizzled) W chunk image with one cp.async.bulk per stage.
 //   warps 0-3 also run the epilogue of the previous accumulator: tcgen05.ld, scale, 128-bit stores.
 // Why 64-edge tiles: the gather side wants (edge-major, all columns) — coalesced, once — while the MMA wants
@@ -42,7 +44,8 @@ constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;  // 32768
 constexpr int AS_LD = S * C + 4;                       // padded A_e row (floats): conflict-free phase-2 reads
 constexpr int AS_BYTES = TILE_M * AS_LD * 4;           // 115712
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + AS_BYTES + 512 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 128;                    // two 64-column accumulators
+constexpr uint32_t TMEM_COLS = 256;                    // two slots x (main + correction) 64-column accumulators
+constexpr float kShrinkPerStep = 1.25e-8f;             // mean toward-zero rounding loss of one tcgen05 accumulate
 
 // packed weight image: [chunk][hi|lo][o][k_local] bf16, rows already XOR-swizzled (SWIZZLE_128B)
 constexpr int WPACK_BYTES = NCHUNK * 2 * W_TILE_BYTES;  // 262144
@@ -208,16 +211,27 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
       mbar_wait(acc_full(slot), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       const int64_t er = (int64_t)tile * TILE_M + warp * 16 + lane;  // valid for lane < 16
+      // The 64 hi*hi accumulates of the main accumulator each round toward zero (mean loss 1.25e-8 per step, see
+      // dense_tc.cu / profiles/diag_shrink.py): add the mean loss back through the small correction accumulator.
+      constexpr float kComp = kShrinkPerStep * (float)(NCHUNK * (KC / 16));
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * O + half * 32, r);
+        uint32_t r[32], c[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * 2 * O + half * 32;
+        tmem_ld32(ta, r);
+        tmem_ld32(ta + O, c);
         if (lane < 16 && er < n_edges) {
           float4* dst = reinterpret_cast<float4*>(out + er * O + half * 32);
 #pragma unroll
-          for (int v = 0; v < 8; ++v)
-            dst[v] = make_float4(__uint_as_float(r[4 * v]) * scale, __uint_as_float(r[4 * v + 1]) * scale,
-                                 __uint_as_float(r[4 * v + 2]) * scale, __uint_as_float(r[4 * v + 3]) * scale);
+          for (int v = 0; v < 8; ++v) {
+            float o4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float mainv = __uint_as_float(r[4 * v + u]);
+              o4[u] = (mainv + fmaf(mainv, kComp, __uint_as_float(c[4 * v + u]))) * scale;
+            }
+            dst[v] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+          }
         }
       }
       tc_fence_before();
@@ -330,7 +344,7 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
       for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int slot = it & 1;
         mbar_wait(acc_empty(slot), (((uint32_t)it >> 1) & 1u) ^ 1u);  // epilogue of the tile two back is done
-        const uint32_t d_tmem = tmem_base + slot * O;
+        const uint32_t d_main = tmem_base + slot * 2 * O, d_corr = d_main + O;
         for (int chunk = 0; chunk < NCHUNK; ++chunk, ++g) {
           const int stage = g % kStages;
           mbar_wait(full_bar(stage), (g / kStages) & 1u);
@@ -341,9 +355,9 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle atom
-            umma_bf16(d_tmem, a_hi + adv, w_hi + adv, kIdesc, (chunk | kk) != 0);
-            umma_bf16(d_tmem, a_hi + adv, w_lo + adv, kIdesc, 1u);
-            umma_bf16(d_tmem, a_lo + adv, w_hi + adv, kIdesc, 1u);
+            umma_bf16(d_main, a_hi + adv, w_hi + adv, kIdesc, (chunk | kk) != 0);
+            umma_bf16(d_corr, a_hi + adv, w_lo + adv, kIdesc, (chunk | kk) != 0);
+            umma_bf16(d_corr, a_lo + adv, w_hi + adv, kIdesc, 1u);
           }
           umma_commit(empty_bar(stage));
         }

@@ -62,12 +62,10 @@ class GemNet(torch.nn.Module):
         self.num_spherical, self.num_radial = num_spherical, num_radial
         # 1 = tcgen05 forward kernel where built (published triplet shape), 0 = fp32 CUDA-core kernels everywhere
         self.bilinear_algo = int(kwargs.get("bilinear_algo", 1))
-        # 0 = cuBLAS fp32 GEMMs + fused pointwise kernels (default: unbiased fp32 accumulation);
-        # 1 = fused tcgen05 (3xTF32) dense layers in the engine.  Measured on B200: the tensor core TRUNCATES when it
-        # adds into the fp32 TMEM accumulator (mean signed error -1.6e-8 per accumulate, -1.05e-6 for K=128), and that
-        # systematic shrink compounds over the ~40 dense layers to ~1e-4 on E/F — at the parity gate, so it is opt-in
-        # (DESIGN.md §4); the fix (short accumulation chains in separate TMEM accumulators) is follow-up work.
-        self.dense_algo = int(kwargs.get("dense_algo", 0))
+        # 1 = fused tcgen05 dense layers in the engine (dense_tc.cu: exact 3-way bf16 split, short accumulation
+        # chains in separate TMEM accumulators -> unbiased, rms error 3e-8 vs cuBLAS fp32 1.5e-7); 0 = cuBLAS fp32 GEMMs
+        # + fused pointwise kernels
+        self.dense_algo = int(kwargs.get("dense_algo", 1))
         # eval(): evaluate energy+forces on the tape engine (engine.py) instead of torch.autograd (same kernels)
         self.use_engine = bool(kwargs.get("use_engine", True))
 

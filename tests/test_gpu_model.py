@@ -206,16 +206,14 @@ def test_engine_matches_autograd_path(name, dev):
     E1, F1 = model(inputs)
     E2, F2 = model.forward_autograd(inputs)
     assert inputs["R"].requires_grad is False
-    # same kernels and cuBLAS GEMMs on both paths: only the gradient-accumulation order differs
-    assert (E1 - E2).abs().max() <= 1e-6 * E2.abs().max()
-    assert (F1 - F2).abs().max() <= 2e-6 * F2.abs().max()
-    # opt-in fused tcgen05 (3xTF32) dense layers: biased accumulation keeps them inside the 1e-4
-    # north_star gate but outside our 2e-5 margin
-    model.dense_algo = 1
+    # engine = fused tcgen05 dense layers (unbiased, fp32-grade), autograd path = cuBLAS fp32 GEMMs
+    assert (E1 - E2).abs().max() <= 3e-6 * E2.abs().max()
+    assert (F1 - F2).abs().max() <= 5e-6 * F2.abs().max()
+    model.dense_algo = 0  # same engine on the cuBLAS GEMMs: only the gradient-accumulation order differs
     E3, F3 = model(inputs)
-    model.dense_algo = 0
-    assert (E3 - E2).abs().max() <= 3e-4 * E2.abs().max()
-    assert (F3 - F2).abs().max() <= 3e-4 * F2.abs().max()
+    model.dense_algo = 1
+    assert (E3 - E2).abs().max() <= 1e-6 * E2.abs().max()
+    assert (F3 - F2).abs().max() <= 2e-6 * F2.abs().max()
     # multi-target through the engine
     if name == "T":
         kw2 = dict(kw, num_targets=2)
@@ -223,4 +221,4 @@ def test_engine_matches_autograd_path(name, dev):
         Ea, Fa = m2(inputs)
         Eb, Fb = m2.forward_autograd(inputs)
         assert Fa.shape == Fb.shape == (inputs["R"].shape[0], 2, 3)
-        assert (Fa - Fb).abs().max() <= 2e-6 * Fb.abs().max() and (Ea - Eb).abs().max() <= 1e-6 * Eb.abs().max()
+        assert (Fa - Fb).abs().max() <= 5e-6 * Fb.abs().max() and (Ea - Eb).abs().max() <= 3e-6 * Eb.abs().max()

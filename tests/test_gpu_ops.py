@@ -426,7 +426,7 @@ def test_segmented_bilinear_tcgen05_matches_fp32_kernel_and_oracle(ops, dev, ids
     assert torch.equal(out1, out1b)
 
 
-# ----------------------------------------------------------------------------- N1: fused dense on tcgen05 (3xTF32)
+# ----------------------------------------------------------------------------- N1: fused dense on tcgen05 (bf16x3 split)
 @pytest.mark.parametrize("M,K,N", [(1, 128, 128), (300, 16, 128), (8186, 128, 128), (5000, 128, 64), (777, 64, 128),
                                    (20000, 128, 128), (130, 128, 16)])
 def test_dense_tc_matches_fp64(dev, M, K, N):
@@ -439,15 +439,21 @@ def test_dense_tc_matches_fp64(dev, M, K, N):
     y = D.dense_tc(x, D.packed_weight(W, False))
     e_plain = relerr(y, xd @ Wd.t())
     e_cublas = relerr(torch.mm(x, W.t()), xd @ Wd.t())
-    print(f"M={M} K={K} N={N}: 3xTF32 rel err {e_plain:.2e} (cuBLAS fp32 {e_cublas:.2e})")
-    assert e_plain < 2e-6
+    print(f"M={M} K={K} N={N}: dense_tc rel err {e_plain:.2e} (cuBLAS fp32 {e_cublas:.2e})")
+    assert e_plain < 5e-7
+    # unbiased: the mean signed error is far below the rms error (a chained accumulator gives -1e-6 at K=128)
+    if M >= 300:
+        xp, Wp_ = x.abs() + 0.5, W.abs() + 0.5
+        ref = xp.double().cpu() @ Wp_.double().cpu().t()
+        rel = (D.dense_tc(xp, D.packed_weight(Wp_, False)).double().cpu() - ref) / ref
+        assert abs(rel.mean().item()) < 3e-8 and rel.pow(2).mean().sqrt().item() < 1e-7
     res = torch.randn(M, N, device=dev)
     y2, d2 = D.dense_tc(x, D.packed_weight(W, False), act=1, s_acc=0.7, res=res, s_res=0.3, want_dact=True)
     z = (xd @ Wd.t()).requires_grad_(True)
     want = 0.7 * ssilu(z) + 0.3 * res.double().cpu()
-    assert relerr(y2, want) < 2e-6
+    assert relerr(y2, want) < 1e-6
     (dwant,) = torch.autograd.grad((0.7 * ssilu(z)).sum(), z)
-    assert relerr(d2, dwant) < 2e-6
+    assert relerr(d2, dwant) < 1e-6
     # transposed operand + prologue multiply (the backward form): (g .* d) @ W
     g = torch.randn(M, N, device=dev)
     gx = D.dense_tc(g, D.packed_weight(W, True), xmul=d2)
