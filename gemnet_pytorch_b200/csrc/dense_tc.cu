@@ -147,6 +147,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int64_t sn, in
   dst[(int64_t)(kb * 3 + 2) * N * KB + phys] = l;
 }
 
+static inline int64_t ceil_div_i(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
 struct Params {
   const float* x;      // (M, ldx) rows, K_src valid columns
   const float* xmul;   // optional (M, ldx) prologue multiplier
@@ -158,6 +160,7 @@ struct Params {
   int ldx, K_src, N_out;
   int act;             // 0 identity, 1 ScaledSiLU
   float s_acc, s_res;
+  int N_img;           // rows per (kb, split) block of the packed image (64 or 128)
 };
 
 template <int NKB, int N>
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
       reinterpret_cast<volatile uint32_t*>(sm + W_BYTES + kStages * STAGE_BYTES + 8 * (2 * kStages + 3));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_off = blockIdx.y * N;  // column slab of this CTA (small-M launches split N = 128 over two CTAs)
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), PRODUCER_WARPS);
@@ -283,10 +287,10 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
     // ============================================================ weight loader (once per CTA)
     if (lane == 0) {
       mbar_arrive_expect_tx(w_bar, W_BYTES);
-      constexpr int PIECE = 32768;
-      for (int off = 0; off < W_BYTES; off += PIECE)
-        bulk_g2s(w_base + off, reinterpret_cast<const uint8_t*>(p.Wp) + off, (W_BYTES - off) < PIECE ? (W_BYTES - off) : PIECE,
-                 w_bar);
+      constexpr int BLK = N * KB * 2;  // one (kb, split) block of this CTA's slab: N rows x 128 B
+      for (int b = 0; b < NKB * 3; ++b)
+        bulk_g2s(w_base + b * BLK,
+                 reinterpret_cast<const uint8_t*>(p.Wp) + ((size_t)b * p.N_img + n_off) * (KB * 2), BLK, w_bar);
     }
   } else {
     // ============================================================ epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves
@@ -322,13 +326,14 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
         }
 #pragma unroll
         for (int v = 0; v < 32; ++v) acc[v] = __float_as_uint(__uint_as_float(acc[v]) + __uint_as_float(t2[v]));
-        if (r < p.M && c0 < p.N_out) {
-          float* yrow = p.y + r * p.N_out + c0;
-          const float* rrow = p.res ? p.res + r * p.N_out + c0 : nullptr;
-          float* drow = p.dact ? p.dact + r * p.N_out + c0 : nullptr;
+        const int col0 = n_off + c0;
+        if (r < p.M && col0 < p.N_out) {
+          float* yrow = p.y + r * p.N_out + col0;
+          const float* rrow = p.res ? p.res + r * p.N_out + col0 : nullptr;
+          float* drow = p.dact ? p.dact + r * p.N_out + col0 : nullptr;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            if (c0 + 4 * q >= p.N_out) break;
+            if (col0 + 4 * q >= p.N_out) break;
             float o[4], d[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
 }
 
 template <int NKB, int N>
-static int launch(const Params& p, cudaStream_t st) {
+static int launch(const Params& p, cudaStream_t st, int n_slabs = 1) {
   constexpr int W_BYTES = NKB * 3 * N * KB * 2;
   constexpr int SMEM = 1024 + W_BYTES + kStages * STAGE_BYTES + 512;
   static bool configured = false;
@@ -384,7 +389,7 @@ static int launch(const Params& p, cudaStream_t st) {
   const int n_tiles = (int)ceil_div(p.M, TILE_M);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  dense_tc_kernel<NKB, N><<<n_tiles < sms ? n_tiles : sms, THREADS, SMEM, st>>>(p, n_tiles);
+  dense_tc_kernel<NKB, N><<<dim3(n_tiles < sms ? n_tiles : sms, n_slabs), THREADS, SMEM, st>>>(p, n_tiles);
   return check_launch("gemnet_dense_tc");
 }
 
@@ -421,11 +426,14 @@ GEMNET_API int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int
   GEMNET_REQUIRE(x && packed && y, "null pointer");
   GEMNET_REQUIRE((((uintptr_t)x | (uintptr_t)xmul | (uintptr_t)packed | (uintptr_t)res | (uintptr_t)y | (uintptr_t)dact) % 16) == 0,
                  "pointers must be 16-byte aligned");
-  dtc::Params p{x, xmul, packed, res, y, dact, M, ldx, K, N, act, s_acc, s_res};
-  cudaStream_t st = as_stream(stream);
   const int Kp = round_k(K), Np = round_n(N);
+  dtc::Params p{x, xmul, packed, res, y, dact, M, ldx, K, N, act, s_acc, s_res, Np};
+  cudaStream_t st = as_stream(stream);
   if (Kp == 64 && Np == 64) return dtc::launch<1, 64>(p, st);
-  if (Kp == 64 && Np == 128) return dtc::launch<1, 128>(p, st);
   if (Kp == 128 && Np == 64) return dtc::launch<2, 64>(p, st);
-  return dtc::launch<2, 128>(p, st);
+  // N = 128: with few row tiles (launch-bound sizes) two CTAs share a tile, 64 output columns each, so that twice as
+  // many SMs work and each loads half of the weight image; large M keeps one CTA per tile (A is read only once)
+  const bool split = dtc::ceil_div_i(M, dtc::TILE_M) <= 74 && N > 64;
+  if (Kp == 64) return split ? dtc::launch<1, 64>(p, st, 2) : dtc::launch<1, 128>(p, st);
+  return split ? dtc::launch<2, 64>(p, st, 2) : dtc::launch<2, 128>(p, st);
 }

@@ -441,12 +441,13 @@ def test_dense_tc_matches_fp64(dev, M, K, N):
     e_cublas = relerr(torch.mm(x, W.t()), xd @ Wd.t())
     print(f"M={M} K={K} N={N}: dense_tc rel err {e_plain:.2e} (cuBLAS fp32 {e_cublas:.2e})")
     assert e_plain < 5e-7
-    # unbiased: the mean signed error is far below the rms error (a chained accumulator gives -1e-6 at K=128)
-    if M >= 300:
-        xp, Wp_ = x.abs() + 0.5, W.abs() + 0.5
-        ref = xp.double().cpu() @ Wp_.double().cpu().t()
-        rel = (D.dense_tc(xp, D.packed_weight(Wp_, False)).double().cpu() - ref) / ref
-        assert abs(rel.mean().item()) < 3e-8 and rel.pow(2).mean().sqrt().item() < 1e-7
+    # no systematic shrink on zero-mean data: regression slope of the error on the exact value ~ 0 (an uncompensated
+    # 4-step accumulation chain gives -5e-8, a 64-step chain -1e-6; profiles/diag_shrink.py)
+    if M >= 5000:
+        ref = xd @ Wd.t()
+        err = y.double().cpu() - ref
+        slope = ((err * ref).sum() / (ref * ref).sum()).item()
+        assert abs(slope) < 1.5e-8 and (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() < 1e-7
     res = torch.randn(M, N, device=dev)
     y2, d2 = D.dense_tc(x, D.packed_weight(W, False), act=1, s_acc=0.7, res=res, s_res=0.3, want_dact=True)
     z = (xd @ Wd.t()).requires_grad_(True)
