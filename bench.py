@@ -187,6 +187,69 @@ def run_reference(args, kw, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, kw, rank, local_rank, world):
+    """BASELINE configs[3]: direct-force GemNet-dT training step on COLL-shaped synthetic molecules, fp32 (the kernels
+    are fp32; bf16 storage is follow-up work), whole molecules per rank, ONE flat NCCL all-reduce of the gradients per
+    optimiser step (gemnet_pytorch_b200.dist), loss normalised by global molecule / atom counts."""
+    import torch.distributed as dist
+    from gemnet_pytorch_b200 import GemNet, build_batch
+    from gemnet_pytorch_b200 import dist as gdist
+    from oracle import gemnet_oracle as go
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kw = dict(kw, triplets_only=True, direct_forces=True)
+    model = GemNet(**kw)
+    model.load_state_dict(go.synthetic_state_dict(kw, seed=1234), strict=True)
+    model = model.to(dev).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, amsgrad=True)
+    Rl, Zl = synthetic_molecules(args.batch, 1234 + rank)
+    inputs = {k: v.to(dev) for k, v in build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], True).items()}
+    g = torch.Generator().manual_seed(7 + rank)
+    E_t = torch.randn(args.batch, 1, generator=g).to(dev)
+    F_t = torch.randn(inputs["R"].shape[0], 3, generator=g).to(dev)
+    n_mol, n_atom = gdist.global_counts(args.batch, inputs["R"].shape[0], device=dev)
+
+    def step():
+        E, F = model(inputs)
+        loss = (E - E_t).abs().sum() / n_mol + (F - F_t).norm(dim=-1).sum() / n_atom  # MAE(E) + MAE(|F|) (trainer.py:338-343)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        gdist.allreduce_gradients_(params)
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    if rank == 0:
+        t = float(t)
+        print(json.dumps({
+            "metric": "molecules_per_sec", "value": args.batch * world * args.steps / t, "unit": "molecules/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"GemNet-dT direct-force TRAINING step (fwd+bwd+flat NCCL all-reduce+AdamW), "
+                                   f"COLL-shaped synthetic batch={args.batch} molecules/GPU, fp32",
+                       "grad_floats_allreduced": int(sum(p.numel() for p in params))},
+            "loss": float(loss)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def workload_config(args, kw, where):
     name = "GemNet-T" if kw["triplets_only"] else "GemNet-Q"
     return {"workload": f"{name} energy+force inference (forces = -dE/dR), COLL-shaped synthetic batch={args.batch} "
@@ -206,6 +269,9 @@ def main():
     ap.add_argument("--large-batch", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager step instead of its CUDA-graph replay")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train = BASELINE configs[3]: GemNet-dT direct-force training step (fp32), molecule-sharded, "
+                         "one flat NCCL gradient all-reduce per step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -215,6 +281,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, kw, rank, world)
+        return
+    if args.mode == "train":
+        run_train(args, kw, rank, local_rank, world)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"

@@ -35,17 +35,32 @@ def packed_weight(W, transpose):
     return _packs[key]
 
 
+_fn = []
+
+
 def dense_tc(x, pack, act=0, s_acc=1.0, res=None, s_res=0.0, xmul=None, want_dact=False):
-    """y (M,N) [, dact] = gemnet_dense_tc(...).  x may be a row-strided view (inner stride 1)."""
+    """y (M,N) [, dact] = gemnet_dense_tc(...).  x may be a row-strided view (inner stride 1).
+    (Hot host path: ~230 calls per GemNet-T evaluation — kept free of helper calls.)"""
     buf, N, K = pack[0], pack[1], pack[2]
-    assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == K and x.dtype == torch.float32 and x.is_cuda
     M, ldx = x.shape[0], x.stride(0)
-    if xmul is not None:
-        assert xmul.shape == x.shape and xmul.stride() == x.stride()
-    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
-    dact = torch.empty_like(y) if want_dact else None
-    _check(_L().gemnet_dense_tc(_p(x), _p(xmul), M, K, ldx, _p(buf), N, act, s_acc, _p(res), s_res, _p(y), _p(dact),
-                                _stream()), "gemnet_dense_tc")
+    if x.stride(1) != 1 or x.shape[1] != K or x.dtype is not torch.float32 or not x.is_cuda:
+        raise _lib.GemnetB200Error("dense_tc: x must be a CUDA float32 (M, K) tensor with unit inner stride")
+    if xmul is not None and (xmul.shape != x.shape or xmul.stride() != x.stride()):
+        raise _lib.GemnetB200Error("dense_tc: xmul must match x in shape and strides")
+    if want_dact:
+        both = torch.empty((2, M, N), dtype=torch.float32, device=x.device)  # one allocation for y and dact
+        y, dact = both[0], both[1]
+        pd = dact.data_ptr()
+    else:
+        y, dact, pd = torch.empty((M, N), dtype=torch.float32, device=x.device), None, None
+    if not _fn:
+        _fn.append(_L().gemnet_dense_tc)
+    rc = _fn[0](x.data_ptr(), None if xmul is None else xmul.data_ptr(), M, K, ldx, buf.data_ptr(), N, act, s_acc,
+                None if res is None else res.data_ptr(), s_res, y.data_ptr(), pd,
+                torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    _lib.KERNEL_LAUNCHES[0] += 1
+    if rc != 0:
+        _check(rc, "gemnet_dense_tc")
     return (y, dact) if want_dact else y
 
 
