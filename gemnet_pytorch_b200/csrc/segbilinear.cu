@@ -21,31 +21,62 @@ struct SegCfg {
   static constexpr int TX = O / 4;       // threads across o (float4 each) in phase 3
   static constexpr int THREADS = 256;
   static constexpr int WARPS = THREADS / 32;
+  static constexpr int SP = (S + 3) / 4 * 4;    // basis row padded to a multiple of 4 floats in shared memory
+  static constexpr int SB = 8;                  // units staged per batch and warp
+  static constexpr int STAGE_FLOATS = WARPS * SB * (SP + 1);  // + the row index of the unit
   static_assert(C % 32 == 0, "C must be a multiple of 32");
   static_assert(O % 4 == 0 && (THREADS / TX) == EB, "EB must equal 256 / (O/4)");
   static_assert((C & (C - 1)) == 0, "C must be a power of two");
 };
 
+// Stage the basis rows (and gather indices) of up to SB units of this warp's segment in shared memory: the rows of
+// consecutive units are contiguous in global memory, so the stage is one coalesced copy, and the per-unit broadcast
+// reads become 128-bit shared loads (4 values / instruction) instead of one global load (+ descriptor moves) per
+// value.  stage layout per warp: [SB][SP] basis values, then [SB] row indices (as float bit patterns).
+template <typename Cfg>
+__device__ __forceinline__ int stage_units(const int32_t* __restrict__ expand, const float* __restrict__ sph,
+                                           int32_t t0, int32_t end, int lane, float* __restrict__ st) {
+  const int nb = min(Cfg::SB, end - t0);
+  __syncwarp();  // the previous batch has been consumed
+  const float* src = sph + (int64_t)t0 * Cfg::S;
+  for (int i = lane; i < nb * Cfg::S; i += 32) {
+    const int u = i / Cfg::S, s = i - u * Cfg::S;
+    st[u * Cfg::SP + s] = __ldg(src + i);
+  }
+  if (lane < nb) st[Cfg::SB * Cfg::SP + lane] = __int_as_float(__ldg(expand + t0 + lane));
+  __syncwarp();
+  return nb;
+}
+
 // phase 1: A[s][cc] for edge segment [beg, end)
 template <typename Cfg>
 __device__ __forceinline__ void segment_sum(const float* __restrict__ x, const int32_t* __restrict__ expand,
                                             const float* __restrict__ sph, int32_t beg, int32_t end, int lane,
-                                            float (&A)[Cfg::S][Cfg::CC]) {
+                                            float* __restrict__ st, float (&A)[Cfg::S][Cfg::CC]) {
 #pragma unroll
   for (int s = 0; s < Cfg::S; ++s)
 #pragma unroll
     for (int cc = 0; cc < Cfg::CC; ++cc) A[s][cc] = 0.f;
-  for (int32_t t = beg; t < end; ++t) {
-    const float* xr = x + (int64_t)__ldg(expand + t) * Cfg::C + lane;
-    float xv[Cfg::CC];
+  for (int32_t t0 = beg; t0 < end; t0 += Cfg::SB) {
+    const int nb = stage_units<Cfg>(expand, sph, t0, end, lane, st);
+    for (int u = 0; u < nb; ++u) {
+      const float* xr = x + (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
+      float xv[Cfg::CC];
 #pragma unroll
-    for (int cc = 0; cc < Cfg::CC; ++cc) xv[cc] = __ldg(xr + 32 * cc);
-    const float* sp = sph + (int64_t)t * Cfg::S;
+      for (int cc = 0; cc < Cfg::CC; ++cc) xv[cc] = __ldg(xr + 32 * cc);
+      const float4* sp4 = reinterpret_cast<const float4*>(st + u * Cfg::SP);
 #pragma unroll
-    for (int s = 0; s < Cfg::S; ++s) {
-      const float w = __ldg(sp + s);
+      for (int s4 = 0; s4 < Cfg::SP / 4; ++s4) {
+        const float4 w = sp4[s4];
+        const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int cc = 0; cc < Cfg::CC; ++cc) A[s][cc] = fmaf(w, xv[cc], A[s][cc]);
+        for (int j = 0; j < 4; ++j) {
+          if (4 * s4 + j < Cfg::S) {
+#pragma unroll
+            for (int cc = 0; cc < Cfg::CC; ++cc) A[4 * s4 + j][cc] = fmaf(wv[j], xv[cc], A[4 * s4 + j][cc]);
+          }
+        }
+      }
     }
   }
 }
@@ -61,6 +92,7 @@ __global__ void __launch_bounds__(256) segbil_fwd_kernel(const float* __restrict
   extern __shared__ __align__(16) float smem[];
   float* Bs = smem;  // [EB][LD]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* st = smem + Cfg::EB * Cfg::LD + warp * (Cfg::SB * (Cfg::SP + 1));  // per-warp unit stage
   const int64_t e0 = (int64_t)blockIdx.x * Cfg::EB;
 
   for (int el = warp; el < Cfg::EB; el += Cfg::WARPS) {
@@ -71,7 +103,7 @@ __global__ void __launch_bounds__(256) segbil_fwd_kernel(const float* __restrict
       continue;
     }
     float A[Cfg::S][Cfg::CC];
-    segment_sum<Cfg>(x, expand, sph, rowptr[e], rowptr[e + 1], lane, A);
+    segment_sum<Cfg>(x, expand, sph, rowptr[e], rowptr[e + 1], lane, st, A);
     const float* rw = rbf_W1 + e * (Cfg::I * Cfg::S);
 #pragma unroll 4
     for (int i = 0; i < Cfg::I; ++i) {
@@ -148,6 +180,7 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
   float* dBs = smem;                        // [EB][LD]
   float* gs = smem + Cfg::EB * Cfg::LD;     // [EB][O]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* st = gs + Cfg::EB * Cfg::O + warp * (Cfg::SB * (Cfg::SP + 1));  // per-warp unit stage
   const int64_t e0 = (int64_t)blockIdx.x * Cfg::EB;
 
   for (int idx = threadIdx.x; idx < Cfg::EB * Cfg::O; idx += Cfg::THREADS) {
@@ -191,7 +224,7 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
     const float* drow = dBs + el * Cfg::LD;
     const float* rw = rbf_W1 + e * IS;
     float A[Cfg::S][Cfg::CC];
-    segment_sum<Cfg>(x, expand, sph, beg, end, lane, A);
+    segment_sum<Cfg>(x, expand, sph, beg, end, lane, st, A);
 
     // dA[s,c] = sum_i rbf_W1[e,i,s] dB[i,c];   g_rbf_W1[e,i,s] = sum_c dB[i,c] A[s,c]
     float dA[Cfg::S][Cfg::CC];
@@ -232,15 +265,18 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
     }
 
     // per unit t of the segment: g_sph[t,s] = sum_c dA[s,c] x[exp,c];  g_x[exp,c] += sum_s sph[t,s] dA[s,c]
-    for (int32_t t = beg; t < end; ++t) {
-      const int64_t row = (int64_t)__ldg(expand + t) * Cfg::C + lane;
+    for (int32_t t0 = beg; t0 < end; t0 += Cfg::SB) {
+     const int nb = stage_units<Cfg>(expand, sph, t0, end, lane, st);
+     for (int u = 0; u < nb; ++u) {
+      const int32_t t = t0 + u;
+      const int64_t row = (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
       float xv[Cfg::CC], gx[Cfg::CC];
 #pragma unroll
       for (int cc = 0; cc < Cfg::CC; ++cc) {
         xv[cc] = __ldg(x + row + 32 * cc);
         gx[cc] = 0.f;
       }
-      const float* sp = sph + (int64_t)t * Cfg::S;
+      const float* sp = st + u * Cfg::SP;
 #pragma unroll
       for (int s0 = 0; s0 < Cfg::S; s0 += SP) {
         float v[SP];
@@ -248,7 +284,7 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
         for (int k = 0; k < SP; ++k) {
           float p = 0.f;
           if (s0 + k < Cfg::S) {
-            const float w = __ldg(sp + s0 + k);
+            const float w = sp[s0 + k];
 #pragma unroll
             for (int cc = 0; cc < Cfg::CC; ++cc) {
               p = fmaf(dA[(s0 + k) < Cfg::S ? (s0 + k) : 0][cc], xv[cc], p);
@@ -267,6 +303,7 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
 #pragma unroll
         for (int cc = 0; cc < Cfg::CC; ++cc) atomicAdd(g_x + row + 32 * cc, gx[cc]);
       }
+     }
     }
   }
 }
@@ -275,7 +312,7 @@ template <typename Cfg>
 static int launch_fwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
                       const float* rbf_W1, const float* W, float scale, int64_t n_edges, float* out,
                       cudaStream_t st) {
-  const size_t smem = sizeof(float) * Cfg::EB * Cfg::LD;
+  const size_t smem = sizeof(float) * (Cfg::EB * Cfg::LD + Cfg::STAGE_FLOATS);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(segbil_fwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -294,7 +331,7 @@ template <typename Cfg>
 static int launch_bwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
                       const float* rbf_W1, const float* W, float scale, int64_t n_edges, const float* g_out,
                       float* g_x, float* g_sph, float* g_rbf_W1, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (Cfg::EB * Cfg::LD + Cfg::EB * Cfg::O);
+  const size_t smem = sizeof(float) * (Cfg::EB * Cfg::LD + Cfg::EB * Cfg::O + Cfg::STAGE_FLOATS);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(segbil_bwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -134,6 +134,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -214,16 +224,16 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
       // The 64 hi*hi accumulates of the main accumulator each round toward zero (mean loss 1.25e-8 per step, see
       // dense_tc.cu / profiles/diag_shrink.py): add the mean loss back through the small correction accumulator.
       constexpr float kComp = kShrinkPerStep * (float)(NCHUNK * (KC / 16));
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32], c[32];
-        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * 2 * O + half * 32;
-        tmem_ld32(ta, r);
-        tmem_ld32(ta + O, c);
+#pragma unroll 1
+      for (int part = 0; part < 4; ++part) {  // 16 columns at a time keeps the epilogue out of the producers' registers
+        uint32_t r[16], c[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * 2 * O + part * 16;
+        tmem_ld16(ta, r);
+        tmem_ld16(ta + O, c);
         if (lane < 16 && er < n_edges) {
-          float4* dst = reinterpret_cast<float4*>(out + er * O + half * 32);
+          float4* dst = reinterpret_cast<float4*>(out + er * O + part * 16);
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
+          for (int v = 0; v < 4; ++v) {
             float o4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
