@@ -27,26 +27,47 @@ struct SegCfg {
   static_assert(C % 32 == 0, "C must be a multiple of 32");
   static_assert(O % 4 == 0 && (THREADS / TX) == EB, "EB must equal 256 / (O/4)");
   static_assert((C & (C - 1)) == 0, "C must be a power of two");
+  static_assert(I % SB == 0, "I must be a multiple of the stage depth");
 };
 
 // Stage the basis rows (and gather indices) of up to SB units of this warp's segment in shared memory: the rows of
 // consecutive units are contiguous in global memory, so the stage is one coalesced copy, and the per-unit broadcast
 // reads become 128-bit shared loads (4 values / instruction) instead of one global load (+ descriptor moves) per
-// value.  stage layout per warp: [SB][SP] basis values, then [SB] row indices (as float bit patterns).
+// value.  The copy is software-pipelined through registers: fetch() issues all loads of the NEXT batch (independent,
+// so they overlap each other and the FMAs of the current batch), commit() parks them in shared memory.
+// stage layout per warp: [SB][SP] basis values, then [SB] row indices (as float bit patterns).
 template <typename Cfg>
-__device__ __forceinline__ int stage_units(const int32_t* __restrict__ expand, const float* __restrict__ sph,
-                                           int32_t t0, int32_t end, int lane, float* __restrict__ st) {
-  const int nb = min(Cfg::SB, end - t0);
-  __syncwarp();  // the previous batch has been consumed
-  const float* src = sph + (int64_t)t0 * Cfg::S;
-  for (int i = lane; i < nb * Cfg::S; i += 32) {
-    const int u = i / Cfg::S, s = i - u * Cfg::S;
-    st[u * Cfg::SP + s] = __ldg(src + i);
+struct UnitStager {
+  static constexpr int NL = (Cfg::SB * Cfg::S + 31) / 32;
+  float v[NL];
+  int32_t idx;
+
+  __device__ __forceinline__ void fetch(const int32_t* __restrict__ expand, const float* __restrict__ sph, int32_t t0,
+                                        int32_t end, int lane) {
+    const int n = min(Cfg::SB, end - t0) * Cfg::S;
+    const float* src = sph + (int64_t)t0 * Cfg::S;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = lane + 32 * j;
+      v[j] = i < n ? __ldg(src + i) : 0.f;
+    }
+    idx = (expand != nullptr && lane < Cfg::SB && t0 + lane < end) ? __ldg(expand + t0 + lane) : 0;
   }
-  if (lane < nb) st[Cfg::SB * Cfg::SP + lane] = __int_as_float(__ldg(expand + t0 + lane));
-  __syncwarp();
-  return nb;
-}
+
+  __device__ __forceinline__ void commit(float* __restrict__ st, int lane) const {
+    __syncwarp();  // the previous batch has been consumed
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = lane + 32 * j;
+      if (i < Cfg::SB * Cfg::S) {
+        const int u = i / Cfg::S, s = i - u * Cfg::S;
+        st[u * Cfg::SP + s] = v[j];
+      }
+    }
+    if (lane < Cfg::SB) st[Cfg::SB * Cfg::SP + lane] = __int_as_float(idx);
+    __syncwarp();
+  }
+};
 
 // phase 1: A[s][cc] for edge segment [beg, end)
 template <typename Cfg>
@@ -57,23 +78,37 @@ __device__ __forceinline__ void segment_sum(const float* __restrict__ x, const i
   for (int s = 0; s < Cfg::S; ++s)
 #pragma unroll
     for (int cc = 0; cc < Cfg::CC; ++cc) A[s][cc] = 0.f;
+  UnitStager<Cfg> stg;
+  if (beg < end) stg.fetch(expand, sph, beg, end, lane);
   for (int32_t t0 = beg; t0 < end; t0 += Cfg::SB) {
-    const int nb = stage_units<Cfg>(expand, sph, t0, end, lane, st);
-    for (int u = 0; u < nb; ++u) {
-      const float* xr = x + (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
-      float xv[Cfg::CC];
+    const int nb = min(Cfg::SB, end - t0);
+    stg.commit(st, lane);
+    if (t0 + Cfg::SB < end) stg.fetch(expand, sph, t0 + Cfg::SB, end, lane);
+    // issue the gathers of the whole batch first (SB independent L2 requests in flight per lane), then the FMAs
+    float xb[Cfg::SB][Cfg::CC];
 #pragma unroll
-      for (int cc = 0; cc < Cfg::CC; ++cc) xv[cc] = __ldg(xr + 32 * cc);
-      const float4* sp4 = reinterpret_cast<const float4*>(st + u * Cfg::SP);
+    for (int u = 0; u < Cfg::SB; ++u) {
+      if (u < nb) {
+        const float* xr = x + (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
 #pragma unroll
-      for (int s4 = 0; s4 < Cfg::SP / 4; ++s4) {
-        const float4 w = sp4[s4];
-        const float wv[4] = {w.x, w.y, w.z, w.w};
+        for (int cc = 0; cc < Cfg::CC; ++cc) xb[u][cc] = __ldg(xr + 32 * cc);
+      }
+    }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (4 * s4 + j < Cfg::S) {
+    for (int u = 0; u < Cfg::SB; ++u) {
+      if (u < nb) {
+        const float4* sp4 = reinterpret_cast<const float4*>(st + u * Cfg::SP);
 #pragma unroll
-            for (int cc = 0; cc < Cfg::CC; ++cc) A[4 * s4 + j][cc] = fmaf(wv[j], xv[cc], A[4 * s4 + j][cc]);
+        for (int s4 = 0; s4 < Cfg::SP / 4; ++s4) {
+          const float4 w = sp4[s4];
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * s4 + j < Cfg::S) {
+#pragma unroll
+              for (int cc = 0; cc < Cfg::CC; ++cc)
+                A[4 * s4 + j][cc] = fmaf(wv[j], xb[u][cc], A[4 * s4 + j][cc]);
+            }
           }
         }
       }
@@ -104,20 +139,35 @@ __global__ void __launch_bounds__(256) segbil_fwd_kernel(const float* __restrict
     }
     float A[Cfg::S][Cfg::CC];
     segment_sum<Cfg>(x, expand, sph, rowptr[e], rowptr[e + 1], lane, st, A);
+    // phase 2 with the (I,S) slab of rbf_W1 streamed through the same per-warp stage, SB rows of i at a time
     const float* rw = rbf_W1 + e * (Cfg::I * Cfg::S);
-#pragma unroll 4
-    for (int i = 0; i < Cfg::I; ++i) {
-      float b[Cfg::CC];
+    UnitStager<Cfg> rs;
+    rs.fetch(nullptr, rw, 0, Cfg::I, lane);
+#pragma unroll 1
+    for (int i0 = 0; i0 < Cfg::I; i0 += Cfg::SB) {
+      rs.commit(st, lane);
+      if (i0 + Cfg::SB < Cfg::I) rs.fetch(nullptr, rw, i0 + Cfg::SB, Cfg::I, lane);
 #pragma unroll
-      for (int cc = 0; cc < Cfg::CC; ++cc) b[cc] = 0.f;
+      for (int u = 0; u < Cfg::SB; ++u) {
+        float b[Cfg::CC];
 #pragma unroll
-      for (int s = 0; s < Cfg::S; ++s) {
-        const float w = __ldg(rw + i * Cfg::S + s);
+        for (int cc = 0; cc < Cfg::CC; ++cc) b[cc] = 0.f;
+        const float4* w4 = reinterpret_cast<const float4*>(st + u * Cfg::SP);
 #pragma unroll
-        for (int cc = 0; cc < Cfg::CC; ++cc) b[cc] = fmaf(w, A[s][cc], b[cc]);
+        for (int s4 = 0; s4 < Cfg::SP / 4; ++s4) {
+          const float4 w = w4[s4];
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * s4 + j < Cfg::S) {
+#pragma unroll
+              for (int cc = 0; cc < Cfg::CC; ++cc) b[cc] = fmaf(wv[j], A[4 * s4 + j][cc], b[cc]);
+            }
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CC; ++cc) brow[(i0 + u) * Cfg::C + lane + 32 * cc] = b[cc];
       }
-#pragma unroll
-      for (int cc = 0; cc < Cfg::CC; ++cc) brow[i * Cfg::C + lane + 32 * cc] = b[cc];
     }
   }
   __syncthreads();
@@ -233,14 +283,22 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
 #pragma unroll
       for (int cc = 0; cc < Cfg::CC; ++cc) dA[s][cc] = 0.f;
     constexpr int SHIFT = SP == 8 ? 2 : (SP == 16 ? 1 : 0);
+    UnitStager<Cfg> rs;
+    rs.fetch(nullptr, rw, 0, Cfg::I, lane);
 #pragma unroll 1
-    for (int i = 0; i < Cfg::I; ++i) {
+    for (int i0 = 0; i0 < Cfg::I; i0 += Cfg::SB) {
+     rs.commit(st, lane);
+     if (i0 + Cfg::SB < Cfg::I) rs.fetch(nullptr, rw, i0 + Cfg::SB, Cfg::I, lane);
+#pragma unroll 1
+     for (int u = 0; u < Cfg::SB; ++u) {
+      const int i = i0 + u;
+      const float* wrow = st + u * Cfg::SP;
       float d[Cfg::CC];
 #pragma unroll
       for (int cc = 0; cc < Cfg::CC; ++cc) d[cc] = drow[i * Cfg::C + lane + 32 * cc];
 #pragma unroll
       for (int s = 0; s < Cfg::S; ++s) {
-        const float w = __ldg(rw + i * Cfg::S + s);
+        const float w = wrow[s];
 #pragma unroll
         for (int cc = 0; cc < Cfg::CC; ++cc) dA[s][cc] = fmaf(w, d[cc], dA[s][cc]);
       }
@@ -262,18 +320,34 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
           if ((lane & ((1 << SHIFT) - 1)) == 0 && s0 + k < Cfg::S) g_rbf_W1[e * IS + i * Cfg::S + s0 + k] = tot;
         }
       }
+     }
     }
 
     // per unit t of the segment: g_sph[t,s] = sum_c dA[s,c] x[exp,c];  g_x[exp,c] += sum_s sph[t,s] dA[s,c]
+    UnitStager<Cfg> stg;
+    if (beg < end) stg.fetch(expand, sph, beg, end, lane);
     for (int32_t t0 = beg; t0 < end; t0 += Cfg::SB) {
-     const int nb = stage_units<Cfg>(expand, sph, t0, end, lane, st);
-     for (int u = 0; u < nb; ++u) {
+     const int nb = min(Cfg::SB, end - t0);
+     stg.commit(st, lane);
+     if (t0 + Cfg::SB < end) stg.fetch(expand, sph, t0 + Cfg::SB, end, lane);
+     float xb[Cfg::SB][Cfg::CC];
+#pragma unroll
+     for (int u = 0; u < Cfg::SB; ++u) {
+       if (u < nb) {
+         const float* xr = x + (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
+#pragma unroll
+         for (int cc = 0; cc < Cfg::CC; ++cc) xb[u][cc] = __ldg(xr + 32 * cc);
+       }
+     }
+#pragma unroll
+     for (int u = 0; u < Cfg::SB; ++u) {
+      if (u >= nb) break;
       const int32_t t = t0 + u;
       const int64_t row = (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
       float xv[Cfg::CC], gx[Cfg::CC];
 #pragma unroll
       for (int cc = 0; cc < Cfg::CC; ++cc) {
-        xv[cc] = __ldg(x + row + 32 * cc);
+        xv[cc] = xb[u][cc];
         gx[cc] = 0.f;
       }
       const float* sp = st + u * Cfg::SP;
