@@ -91,19 +91,25 @@ __global__ void place_kernel(const int32_t* __restrict__ ids, int64_t n, const i
   }
 }
 
-// make the placement deterministic / stable: ascending positions inside each row (rows are short)
-__global__ void sort_rows_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t* __restrict__ perm) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
-    const int32_t b = rowptr[r], e = rowptr[r + 1];
-    for (int32_t i = b + 1; i < e; ++i) {
-      int32_t v = perm[i];
-      int32_t j = i - 1;
-      while (j >= b && perm[j] > v) {
-        perm[j + 1] = perm[j];
-        --j;
-      }
-      perm[j + 1] = v;
+// make the placement deterministic / stable: ascending positions inside each row.  One warp per row ranks the
+// row's (distinct) positions by counting the smaller ones — O(n^2 / 32) with independent loads, so a long row (a hub
+// atom, or the pad atoms of a static-shape batch) costs microseconds where a per-thread insertion sort cost
+// milliseconds.  `unordered` is the atomics-ordered placement, `perm` the final one.
+__global__ void rank_rows_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
+                                 const int32_t* __restrict__ unordered, int32_t* __restrict__ perm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+    const int32_t b = rowptr[r], n = rowptr[r + 1] - b;
+    if (n == 1) {
+      if (lane == 0) perm[b] = unordered[b];
+      continue;
+    }
+    for (int32_t i = lane; i < n; i += 32) {
+      const int32_t v = unordered[b + i];
+      int32_t rank = 0;
+      for (int32_t j = 0; j < n; ++j) rank += unordered[b + j] < v;
+      perm[b + rank] = v;
     }
   }
 }
@@ -135,8 +141,9 @@ GEMNET_API int gemnet_csr_by_key(const int32_t* ids, int64_t n, int64_t n_rows, 
   if (n > 0) histogram_kernel<<<flat_grid(n, 256), 256, 0, st>>>(ids, n, workspace);
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(workspace, n_rows, rowptr);
   if (n > 0) {
-    place_kernel<<<flat_grid(n, 256), 256, 0, st>>>(ids, n, rowptr, workspace, perm);
-    sort_rows_kernel<<<flat_grid(n_rows, 128), 128, 0, st>>>(rowptr, n_rows, perm);
+    int32_t* unordered = workspace + n_rows + 1;
+    place_kernel<<<flat_grid(n, 256), 256, 0, st>>>(ids, n, rowptr, workspace, unordered);
+    rank_rows_kernel<<<flat_grid(n_rows * 32, 256), 256, 0, st>>>(rowptr, n_rows, unordered, perm);
   }
   return check_launch("gemnet_csr_by_key");
 }

@@ -329,11 +329,12 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
             b0 = fmaf(rw[2 * v][s], a[s], b0);
             b1 = fmaf(rw[2 * v + 1][s], a[s], b1);
           }
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(b0, h0, l0);
-          split_bf16(b1, h1, l1);
-          hw[v] = pack2(h0, h1);
-          lw[v] = pack2(l0, l1);
+          // packed round-to-nearest conversions (one F2FP per pair instead of two scalar F2F + a PRMT)
+          const __nv_bfloat162 h = __floats2bfloat162_rn(b0, b1);  // .x (low half) = b0 -> k, .y = b1 -> k + 1
+          const float2 hf = __bfloat1622float2(h);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(b0 - hf.x, b1 - hf.y);
+          hw[v] = *reinterpret_cast<const uint32_t*>(&h);
+          lw[v] = *reinterpret_cast<const uint32_t*>(&l);
         }
         mbar_wait(empty_bar(stage), parity ^ 1u);  // the MMAs that read this stage have completed
         uint8_t* a_hi = sm + stage * STAGE_BYTES + el * 128;

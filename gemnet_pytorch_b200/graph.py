@@ -18,6 +18,7 @@ import torch
 from . import _lib, ops
 
 _PLAN_KEY = "_gemnet_b200_plan"
+_VALIDATED_KEY = "_gemnet_b200_indices_validated"  # set by pad_batch: the host already checked the index order
 _CHECK_SORTED = os.environ.get("GEMNET_B200_CHECK_INDICES", "1") != "0"
 
 TRIPLET_KEYS = ("id_undir", "id_swap", "id_c", "id_a", "id3_expand_ba", "id3_reduce_ca", "Kidx3")
@@ -141,6 +142,128 @@ def get_plan(inputs, triplets_only):
     key = (inputs["id_c"].data_ptr(), inputs["id3_reduce_ca"].data_ptr(), int(inputs["id_c"].numel()),
            int(inputs["id3_reduce_ca"].numel()), triplets_only)
     if plan is None or plan[0] != key:
-        plan = (key, GraphPlan(inputs, triplets_only))
+        check = _CHECK_SORTED and not inputs.get(_VALIDATED_KEY, False)  # the device check ends in a host sync
+        plan = (key, GraphPlan(inputs, triplets_only, check=check))
         inputs[_PLAN_KEY] = plan
     return plan[1]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Static-shape batches for CUDA-graph serving.
+#
+# A captured graph has every array size baked in, so a batch is padded up to a fixed capacity with INERT entries:
+# a "pad molecule" (id n_molecules) of >= 3 atoms far away from everything, pad edges that only connect pad atoms
+# and pad triplets that only connect pad edges.  Real entries keep their positions (pads are appended), messages
+# never cross between real and pad entries (every scatter/gather follows the index lists), and the model has no
+# batch-global reduction, so energies of the real molecules and forces on the real atoms are unchanged; the pad
+# rows of the outputs are cut off by the caller.  Pad geometry is a non-degenerate triangle so that every pad value
+# is finite as well.
+class BatchCapacity:
+    """Fixed sizes of a serving bucket: atoms, (directed) edges, triplets and molecules per batch."""
+
+    PAD_ATOMS = 3
+    PAD_EDGES = 6
+
+    def __init__(self, atoms, edges, triplets, molecules):
+        self.atoms, self.edges, self.triplets, self.molecules = int(atoms), int(edges), int(triplets), int(molecules)
+        if self.edges % 2:
+            raise ValueError("edge capacity must be even (edges come in directed pairs)")
+
+    @classmethod
+    def for_batches(cls, batches, margin=1.05):
+        """Capacity that holds every batch of `batches` (reference-format dicts) with `margin` head-room."""
+        a = max(int(b["Z"].shape[0]) for b in batches)
+        e = max(int(b["id_c"].shape[0]) for b in batches)
+        t = max(int(b["id3_reduce_ca"].shape[0]) for b in batches)
+        m = max(int(b["N"].shape[0]) for b in batches)
+        up = lambda n, q: -(-int(n * margin + 1) // q) * q  # noqa: E731
+        return cls(up(a + cls.PAD_ATOMS, 8), up(e + cls.PAD_EDGES, 8), up(t, 8), m)
+
+    def fits(self, n_atoms, n_edges, n_triplets, n_molecules):
+        return (n_atoms + self.PAD_ATOMS <= self.atoms and n_edges + self.PAD_EDGES <= self.edges
+                and n_triplets <= self.triplets and n_molecules <= self.molecules)
+
+    def __repr__(self):
+        return (f"BatchCapacity(atoms={self.atoms}, edges={self.edges}, triplets={self.triplets}, "
+                f"molecules={self.molecules})")
+
+
+_PAD_C = np.array([0, 1, 0, 2, 1, 2])        # source pad atom of pad-edge type j % 6
+_PAD_A = np.array([1, 0, 2, 0, 2, 1])        # target pad atom; types (2k, 2k+1) are each other's reverse
+_PAD_PARTNER = np.array([5, 3, 4, 1, 2, 0])  # an edge type with the same target and another source (a valid triplet)
+_PAD_XYZ = np.array([[0.0, 0.0, 0.0], [1.2, 0.0, 0.0], [0.5, 1.1, 0.0]], dtype=np.float32)
+SERVING_KEYS = ("Z", "R", "batch_seg", "N", "id_c", "id_a", "id_swap", "id_undir", "id3_expand_ba", "id3_reduce_ca")
+
+
+def serving_buffers(cap, pin_memory=False):
+    """Capacity-sized host arrays for `pad_batch` (torch tensors; pinned when they feed captured H2D copies)."""
+    shapes = {"Z": (cap.atoms,), "R": (cap.atoms, 3), "batch_seg": (cap.atoms,), "N": (cap.molecules + 1,),
+              "id_c": (cap.edges,), "id_a": (cap.edges,), "id_swap": (cap.edges,), "id_undir": (cap.edges,),
+              "id3_expand_ba": (cap.triplets,), "id3_reduce_ca": (cap.triplets,)}
+    out = {}
+    for k, shp in shapes.items():
+        t = torch.zeros(shp, dtype=torch.float32 if k == "R" else torch.int64)
+        out[k] = t.pin_memory() if pin_memory else t
+    return out
+
+
+def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
+    """Write the triplet-model batch `inputs` (reference format, host) into capacity-sized buffers (see above).
+
+    Returns (buffers, (n_atoms, n_edges, n_triplets, n_molecules)) — the real sizes, for cutting the outputs.
+    `check`: validate on the host what GraphPlan otherwise validates on the device (grouping / index ranges)."""
+    def arr(k):
+        v = inputs[k]
+        return v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+
+    A, E, T, M = arr("Z").shape[0], arr("id_c").shape[0], arr("id3_reduce_ca").shape[0], arr("N").shape[0]
+    if not cap.fits(A, E, T, M):
+        raise _lib.GemnetB200Error(f"batch (atoms={A}, edges={E}, triplets={T}, molecules={M}) exceeds {cap}")
+    if check and A:
+        seg, red = arr("batch_seg"), arr("id3_reduce_ca")
+        ok = (np.all(np.diff(seg) >= 0) and seg[0] >= 0 and seg[-1] < M and np.all(np.diff(red) >= 0)
+              and (T == 0 or (red[0] >= 0 and red[-1] < E)))
+        if not ok:
+            raise _lib.GemnetB200Error(
+                "index tensors are not grouped/sorted as the reference DataContainer produces them "
+                "(batch_seg, id3_reduce_ca must be non-decreasing and in range)")
+    if out is None:
+        out = serving_buffers(cap)
+    o = {k: v.numpy() for k, v in out.items()}
+    for k in ("Z", "R", "batch_seg"):
+        o[k][:A] = arr(k)
+    for k in ("id_c", "id_a", "id_swap", "id_undir"):
+        o[k][:E] = arr(k)
+    for k in ("id3_expand_ba", "id3_reduce_ca"):
+        o[k][:T] = arr(k)
+    # pad molecule: index cap.molecules (molecules M..cap-1 of a short batch stay empty)
+    o["N"][:M] = arr("N")
+    o["N"][M:cap.molecules] = 0
+    o["N"][cap.molecules] = cap.atoms - A
+    o["Z"][A:] = 1
+    o["batch_seg"][A:] = cap.molecules
+    # pad atoms form triangles (3 atoms each, 10 A apart, far from the real atoms); left-over atoms stay isolated
+    n_pad = cap.atoms - A
+    n_tri = max(1, n_pad // 3)
+    far = (float(np.abs(arr("R")).max()) if A else 0.0) + 100.0
+    k = np.arange(n_pad)
+    tri_of_atom = np.minimum(k // 3, n_tri - 1)
+    pos = _PAD_XYZ[np.where(k < 3 * n_tri, k % 3, 0)] + far
+    pos[:, 0] += 10.0 * tri_of_atom
+    o["R"][A:] = pos
+    # pad edges: groups of 6 = the directed edges of one triangle (so the per-atom degree stays molecule-like)
+    n_pe = cap.edges - E
+    j = np.arange(n_pe)
+    base = A + 3 * ((j // 6) % n_tri)
+    o["id_c"][E:] = base + _PAD_C[j % 6]
+    o["id_a"][E:] = base + _PAD_A[j % 6]
+    o["id_swap"][E:] = E + (j ^ 1)
+    o["id_undir"][E:] = E // 2 + j // 2
+    # pad triplets spread evenly over the complete groups of pad edges, CSR order kept (reduce ids non-decreasing);
+    # the expand edge is the edge of the same group with the same target atom and the other source atom
+    nt = cap.triplets - T
+    if nt:
+        r_local = (np.arange(nt) * ((n_pe // 6) * 6)) // nt
+        o["id3_reduce_ca"][T:] = E + r_local
+        o["id3_expand_ba"][T:] = E + (r_local // 6) * 6 + _PAD_PARTNER[r_local % 6]
+    return out, (A, E, T, M)

@@ -206,6 +206,12 @@ class GemNet(torch.nn.Module):
         `inputs["R"]` first)."""
         return GraphedGemNet(self, inputs, warmup)
 
+    def make_serving(self, capacity, warmup=3):
+        """Static-shape serving: ONE CUDA graph (H2D of the batch, index plan, energy+force evaluation, D2H of E and
+        F) that serves every batch fitting `capacity` (graph.BatchCapacity).  Returns a ServingGemNet; its call
+        takes the reference-format HOST batch and returns (E, F) on the host."""
+        return ServingGemNet(self, capacity, warmup)
+
     def load_weights(self, path):
         self.load_state_dict(torch.load(path))
 
@@ -235,3 +241,59 @@ class GraphedGemNet:
             self.inputs["R"].copy_(R)
         self.graph.replay()
         return self.E, self.F
+
+
+
+class ServingGemNet:
+    """CUDA-graph serving of GemNet-T/dT for batches of varying topology.
+
+    Batch-64 GemNet is launch-latency bound, and an eager step spends more time in the host's ~480 launches than on
+    the GPU.  A captured graph has all sizes baked in, so the batch is padded to a fixed capacity with inert
+    entries (graph.pad_batch: a pad molecule whose atoms/edges/triplets only reference each other) directly in
+    pinned staging buffers; the captured graph copies them to the device, builds the index plan (CSR row pointers,
+    edge->atom orderings) with the plan kernels, evaluates energies and forces and copies E and F to pinned host
+    buffers.  One cudaGraphLaunch per batch; the pad rows are cut off on return."""
+
+    def __init__(self, model, capacity, warmup=3):
+        assert not model.training, "serving capture is for inference (model.eval())"
+        if not model.triplets_only:
+            raise NotImplementedError("static-shape serving is built for triplets_only models (GemNet-T / dT)")
+        self.model, self.cap = model, capacity
+        dev = next(model.parameters()).device
+        self.host = graph.serving_buffers(capacity, pin_memory=True)
+        self.dev = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
+        empty = {k: v[:0] for k, v in self.host.items()}
+        graph.pad_batch(empty, capacity, out=self.host)  # an all-pad batch for warm-up and capture
+        self.E_host = self.F_host = None
+
+        def step():
+            for k, h in self.host.items():
+                self.dev[k].copy_(h, non_blocking=True)
+            inputs = dict(self.dev)  # a fresh dict: the index plan is rebuilt (inside the graph) for every batch
+            inputs[graph._VALIDATED_KEY] = True
+            E, F = model(inputs)
+            if self.E_host is None:
+                self.E_host = torch.empty(E.shape, dtype=E.dtype).pin_memory()
+                self.F_host = torch.empty(F.shape, dtype=F.dtype).pin_memory()
+            self.E_host.copy_(E, non_blocking=True)
+            self.F_host.copy_(F, non_blocking=True)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            step()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.d2h_bytes = self.E_host.numel() * 4 + self.F_host.numel() * 4
+
+    def __call__(self, inputs):
+        """inputs: reference-format batch on the HOST (torch CPU tensors or numpy arrays) -> (E, F) host tensors."""
+        _, (A, _, _, M) = graph.pad_batch(inputs, self.cap, out=self.host)
+        self.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        return self.E_host[:M].clone(), self.F_host[:A].clone()

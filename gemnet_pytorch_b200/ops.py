@@ -61,7 +61,7 @@ def csr_by_key(ids, n_rows):
     ids = _i32(ids)
     rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=ids.device)
     perm = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
-    ws = torch.empty(n_rows + 1, dtype=torch.int32, device=ids.device)
+    ws = torch.empty(n_rows + 1 + ids.numel(), dtype=torch.int32, device=ids.device)
     _check(_L().gemnet_csr_by_key(_p(ids), ids.numel(), n_rows, _p(rowptr), _p(perm), _p(ws), _stream()),
            "gemnet_csr_by_key", kernels=5)
     return rowptr, perm

@@ -42,7 +42,7 @@ int gemnet_csr_from_sorted(const int32_t* sorted_ids, int64_t n, int64_t n_rows,
                            int32_t* flag, void* stream);
 
 /* Stable counting sort of `ids` (values in [0, n_rows)): perm = positions ordered by (id, position),
- * rowptr as above.  workspace: int32[n_rows + 1] (cursor).  Used for the edge->atom CSR (id_a) and the
+ * rowptr as above.  workspace: int32[n_rows + 1 + n] (cursor + unordered placement).  Used for the edge->atom CSR (id_a) and the
  * transposed triplet CSR (id3_expand_ba). */
 int gemnet_csr_by_key(const int32_t* ids, int64_t n, int64_t n_rows, int32_t* rowptr, int32_t* perm,
                       int32_t* workspace, void* stream);

@@ -222,3 +222,28 @@ def test_engine_matches_autograd_path(name, dev):
         Eb, Fb = m2.forward_autograd(inputs)
         assert Fa.shape == Fb.shape == (inputs["R"].shape[0], 2, 3)
         assert (Fa - Fb).abs().max() <= 5e-6 * Fb.abs().max() and (Ea - Eb).abs().max() <= 3e-6 * Eb.abs().max()
+
+
+@pytest.mark.parametrize("name", ["T", "dT"])
+def test_static_shape_serving_matches_fixture_and_eager(name, dev):
+    """ServingGemNet: one captured graph (H2D, index plan, E+F, D2H) serves batches of different topology padded
+    to one capacity; results = the reference fixture (first batch) and the eager path (all batches)."""
+    from gemnet_pytorch_b200 import build_batch, graph
+    fx = H.load_npz(f"model_{name}.npz")
+    kw = H.model_kwargs(fx)
+    model = make_model(kw, go.synthetic_state_dict(kw, seed=int(fx["seed"])), dev)
+    id_sets = [fx["mol_ids"].tolist(), list(range(40, 70)), list(range(100, 164)), [7]]
+    batches = [build_batch(*H.molecules(ids), kw["cutoff"], kw["int_cutoff"], True) for ids in id_sets]
+    cap = graph.BatchCapacity.for_batches(batches, margin=1.03)
+    serve = model.make_serving(cap)
+    for rep in range(2):  # the second pass runs over stale pads of other batches
+        for j, b in enumerate(batches):
+            E, F = serve(b)
+            assert E.shape[0] == len(id_sets[j]) and F.shape[0] == b["Z"].shape[0]
+            assert torch.isfinite(E).all() and torch.isfinite(F).all()
+            E0, F0 = model.predict(to_dev(b, dev))
+            check(E, F, E0.numpy(), F0.numpy(), tol=5e-6)
+            if j == 0:
+                check(E, F, fx["E64"], fx["F64"])
+    with pytest.raises(Exception):
+        serve(build_batch(*H.molecules(list(range(0, 200))), kw["cutoff"], kw["int_cutoff"], True))
