@@ -29,6 +29,11 @@ inline unsigned flat_grid(int64_t n, int block) {
 constexpr int kMaxSpherical = 8;   // Legendre / Y_lm orders supported by the register-resident recurrences
 constexpr int kMaxRadial = 16;
 
+// Programmatic dependent launch: allow the next kernel of the stream — if it was launched as a programmatic dependent
+// (the fused dense layers are) — to start its prologue now.  It still waits for this grid to complete and flush
+// before touching any activation.  A no-op otherwise.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -73,6 +73,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -186,6 +187,11 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_off = blockIdx.y * N;  // column slab of this CTA (small-M launches split N = 128 over two CTAs)
+  // Programmatic dependent launch: let the NEXT kernel of the stream start its prologue (barriers, TMEM, weight
+  // image) while this one runs.  Everything here that touches activations waits in griddep_wait() for the
+  // PREVIOUS kernel to have completed and flushed; the weight image is older than that (see the flags argument of
+  // gemnet_dense_tc) and is fetched before the wait.  Both instructions are no-ops in a plain launch.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), PRODUCER_WARPS);
@@ -204,6 +210,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
 
   if (warp < PRODUCER_WARPS) {
     // ============================================================ producers
+    griddep_wait();
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t r0 = (int64_t)tile * TILE_M;
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
     // ============================================================ epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves
     const int ew = warp & 3;                          // a warp can only touch TMEM lanes [32*(warp%4), +32)
     const int ch = (warp - EPI_WARP0) >> 2;           // column half
+    griddep_wait();
     for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       mbar_wait(acc_full, (uint32_t)it & 1u);
       tc_fence_after();
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
 }
 
 template <int NKB, int N>
-static int launch(const Params& p, cudaStream_t st, int n_slabs = 1) {
+static int launch(const Params& p, cudaStream_t st, int n_slabs, bool pdl) {
   constexpr int W_BYTES = NKB * 3 * N * KB * 2;
   constexpr int SMEM = 1024 + W_BYTES + kStages * STAGE_BYTES + 512;
   static bool configured = false;
@@ -389,7 +397,21 @@ static int launch(const Params& p, cudaStream_t st, int n_slabs = 1) {
   const int n_tiles = (int)ceil_div(p.M, TILE_M);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  dense_tc_kernel<NKB, N><<<dim3(n_tiles < sms ? n_tiles : sms, n_slabs), THREADS, SMEM, st>>>(p, n_tiles);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_tiles < sms ? n_tiles : sms, n_slabs);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dense_tc_kernel<NKB, N>, p, n_tiles);
+  if (e != cudaSuccess) {
+    set_error("gemnet_dense_tc: launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
   return check_launch("gemnet_dense_tc");
 }
 
@@ -418,7 +440,7 @@ GEMNET_API int gemnet_dense_pack_weight(const float* W, int64_t stride_n, int64_
 
 GEMNET_API int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int32_t ldx,
                                const float* packed, int32_t N, int32_t act, float s_acc, const float* res, float s_res,
-                               float* y, float* dact, void* stream) {
+                               float* y, float* dact, int32_t flags, void* stream) {
   GEMNET_REQUIRE(M >= 0, "negative size");
   GEMNET_REQUIRE(N >= 4 && N <= 128 && N % 4 == 0 && K >= 4 && K <= 128 && K % 4 == 0 && ldx % 4 == 0 && ldx >= K,
                  "dense_tc needs N, K multiples of 4 in [4, 128] and a row stride that keeps 16-byte alignment");
@@ -429,11 +451,12 @@ GEMNET_API int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int
   const int Kp = round_k(K), Np = round_n(N);
   dtc::Params p{x, xmul, packed, res, y, dact, M, ldx, K, N, act, s_acc, s_res, Np};
   cudaStream_t st = as_stream(stream);
-  if (Kp == 64 && Np == 64) return dtc::launch<1, 64>(p, st);
-  if (Kp == 128 && Np == 64) return dtc::launch<2, 64>(p, st);
+  const bool pdl = (flags & GEMNET_DENSE_WEIGHTS_SETTLED) != 0;
+  if (Kp == 64 && Np == 64) return dtc::launch<1, 64>(p, st, 1, pdl);
+  if (Kp == 128 && Np == 64) return dtc::launch<2, 64>(p, st, 1, pdl);
   // N = 128: with few row tiles (launch-bound sizes) two CTAs share a tile, 64 output columns each, so that twice as
   // many SMs work and each loads half of the weight image; large M keeps one CTA per tile (A is read only once)
   const bool split = dtc::ceil_div_i(M, dtc::TILE_M) <= 74 && N > 64;
-  if (Kp == 64) return split ? dtc::launch<1, 64>(p, st, 2) : dtc::launch<1, 128>(p, st);
-  return split ? dtc::launch<2, 64>(p, st, 2) : dtc::launch<2, 128>(p, st);
+  if (Kp == 64) return split ? dtc::launch<1, 64>(p, st, 2, pdl) : dtc::launch<1, 128>(p, st, 1, pdl);
+  return split ? dtc::launch<2, 64>(p, st, 2, pdl) : dtc::launch<2, 128>(p, st, 1, pdl);
 }

@@ -21,6 +21,7 @@ __device__ __forceinline__ float dssilu(float x) {
 // mode 1: out = (x + ssilu(z)) * s
 __global__ void silu_fwd_kernel(const float4* __restrict__ z, const float4* __restrict__ x, float s, int64_t n4,
                                 int mode, float4* __restrict__ out) {
+  pdl_trigger();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(z + i);
@@ -36,6 +37,7 @@ __global__ void silu_fwd_kernel(const float4* __restrict__ z, const float4* __re
 // gz = g * s * dssilu(z)   (s = 1 for mode 0);  the x-branch gradient of mode 1 is g * s (scale_kernel)
 __global__ void silu_bwd_kernel(const float4* __restrict__ z, const float4* __restrict__ g, float s, int64_t n4,
                                 float4* __restrict__ gz) {
+  pdl_trigger();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(z + i), b = __ldg(g + i);
@@ -46,6 +48,7 @@ __global__ void silu_bwd_kernel(const float4* __restrict__ z, const float4* __re
 // out = (a [+ b [+ c]]) * s      (b, c optional)
 __global__ void add_scale_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                  const float4* __restrict__ c, float s, int64_t n4, float4* __restrict__ out) {
+  pdl_trigger();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 r = __ldg(a + i);
@@ -64,6 +67,7 @@ __global__ void add_scale_kernel(const float4* __restrict__ a, const float4* __r
 // out = a * b * s ; backward: ga = g * b * s, gb = g * a * s
 __global__ void mul_scale_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float s, int64_t n4,
                                  float4* __restrict__ out) {
+  pdl_trigger();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 p = __ldg(a + i), q = __ldg(b + i);
@@ -73,6 +77,7 @@ __global__ void mul_scale_kernel(const float4* __restrict__ a, const float4* __r
 __global__ void mul_scale_bwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                      const float4* __restrict__ g, float s, int64_t n4, float4* __restrict__ ga,
                                      float4* __restrict__ gb) {
+  pdl_trigger();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 p = __ldg(a + i), q = __ldg(b + i), t = __ldg(g + i);
@@ -103,6 +108,7 @@ __global__ void tail_kernel(int op, const float* a, const float* b, const float*
 // out[j,:] = x[idx[j],:]  (F % 4 == 0)
 __global__ void gather_rows_kernel(const float4* __restrict__ x, const int32_t* __restrict__ idx, int64_t n, int F4,
                                    float4* __restrict__ out) {
+  pdl_trigger();
   const int64_t total = n * F4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -116,6 +122,7 @@ __global__ void gather_rows_kernel(const float4* __restrict__ x, const int32_t* 
 __global__ void segment_sum_rows_kernel(const float4* __restrict__ src, const int32_t* __restrict__ perm,
                                         const int32_t* __restrict__ rowptr, int64_t n_rows, int F4,
                                         float4* __restrict__ out) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {

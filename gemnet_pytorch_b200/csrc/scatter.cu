@@ -9,6 +9,7 @@ namespace gemnet {
 __global__ void edge_to_atom_fwd_kernel(const float4* __restrict__ m, const float4* __restrict__ r,
                                         const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
                                         int64_t n_atoms, int F4, float scale, float4* __restrict__ out) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_atoms; a += warps) {
@@ -30,6 +31,7 @@ __global__ void edge_to_atom_fwd_kernel(const float4* __restrict__ m, const floa
 
 __global__ void hadamard_kernel(const float4* __restrict__ m, const float4* __restrict__ r, int64_t n4, float s,
                                 float4* __restrict__ out) {
+  pdl_trigger();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(m + i), b = __ldg(r + i);
@@ -43,6 +45,7 @@ __global__ void edge_to_atom_bwd_kernel(const float4* __restrict__ m, const floa
                                         const float4* __restrict__ g_out, float had_scale,
                                         const float4* __restrict__ g_had, float4* __restrict__ g_m,
                                         float4* __restrict__ g_r) {
+  pdl_trigger();
   const int64_t total = n_edges * F4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {

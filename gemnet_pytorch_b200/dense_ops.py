@@ -4,12 +4,15 @@ tape engine (engine.py) consumes — `forward(ctx, ...)` / `backward(ctx, *grads
   * ResidualTC   y = (x + f(f(x W1^T) W2^T)) * s   (base_layers.py:61-89)      backward  gx = ((g .* d2) W2 .* d1) W1 + s g
 Weights are packed once per (storage, version, orientation) into the kernel's resident shared-memory image.
 """
+import os
+
 import torch
 
 from . import _lib
 from .ops import _L, _check, _f32, _p, _stream
 
 _packs = {}
+PDL = [0 if os.environ.get("GEMNET_B200_PDL", "1") == "0" else 1]  # programmatic dependent launch of dense_tc
 
 
 def supported(N, K):
@@ -31,7 +34,8 @@ def packed_weight(W, transpose):
         _packs.clear()
     # keep W referenced: while the entry lives its storage cannot be freed and handed to another tensor with the
     # same (data_ptr, version) — which would silently serve a stale image
-    _packs[key] = (buf, N, K, W)
+    # [4]: the pack kernel is the most recent launch -> the first dense_tc call must not prefetch the image early
+    _packs[key] = [buf, N, K, W, True]
     return _packs[key]
 
 
@@ -55,8 +59,11 @@ def dense_tc(x, pack, act=0, s_acc=1.0, res=None, s_res=0.0, xmul=None, want_dac
         y, dact, pd = torch.empty((M, N), dtype=torch.float32, device=x.device), None, None
     if not _fn:
         _fn.append(_L().gemnet_dense_tc)
+    flags = PDL[0]  # GEMNET_DENSE_WEIGHTS_SETTLED
+    if pack[4]:
+        pack[4], flags = False, 0
     rc = _fn[0](x.data_ptr(), None if xmul is None else xmul.data_ptr(), M, K, ldx, buf.data_ptr(), N, act, s_acc,
-                None if res is None else res.data_ptr(), s_res, y.data_ptr(), pd,
+                None if res is None else res.data_ptr(), s_res, y.data_ptr(), pd, flags,
                 torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
     _lib.KERNEL_LAUNCHES[0] += 1
     if rc != 0:

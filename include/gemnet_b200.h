@@ -225,17 +225,22 @@ int gemnet_segment_sum_rows(const float* src, const int32_t* perm, const int32_t
  * N1: fused dense layer on tcgen05 (Dense / ResidualLayer, gemnet/model/layers/base_layers.py:5-89):
  *     y    = s_acc * f(A @ B^T) + s_res * res,   A = x or x .* xmul,   f = identity (act=0) | silu(.)/0.6 (act=1)
  *     dact = s_acc * f'(A @ B^T)                 (optional output: the factor the backward multiplies the gradient by)
- * fp32 in / fp32 out; the product is an error-compensated TF32 GEMM (hi*hi + hi*lo + lo*hi + lo*lo, fp32 accumulate
- * in TMEM) so the result is fp32-grade.  B is given pre-packed: gemnet_dense_pack_weight converts an (N x K) operand
+ * fp32 in / fp32 out; both operands are split exactly into three bf16 terms and the six significant products are
+ * accumulated in fp32 in TMEM (main and correction sums kept apart, the accumulator's toward-zero rounding
+ * compensated), so the result is fp32-grade.  B is given pre-packed: gemnet_dense_pack_weight converts an (N x K) operand
  * with arbitrary element strides (so W, W^T and column slices of W all pack without copies) into the resident
  * shared-memory image (gemnet_dense_pack_floats(N, K) floats).  N, K multiples of 4 in [4, 128]; x rows have stride ldx.
+ * flags: GEMNET_DENSE_WEIGHTS_SETTLED = the packed image was NOT produced by the kernel launched immediately before
+ * this call on `stream` (weights are packed once and reused): the kernel is then launched as a programmatic
+ * dependent of its predecessor and fetches the image while the predecessor is still running.
  * ---------------------------------------------------------------------------------------------- */
+#define GEMNET_DENSE_WEIGHTS_SETTLED 1
 int64_t gemnet_dense_pack_floats(int32_t N, int32_t K);
 int gemnet_dense_pack_weight(const float* W, int64_t stride_n, int64_t stride_k, int32_t N, int32_t K, float* packed,
                              void* stream);
 int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int32_t ldx, const float* packed,
                     int32_t N, int32_t act, float s_acc, const float* res, float s_res, float* y, float* dact,
-                    void* stream);
+                    int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * H0  host index builder: DataContainer.__getitem__ / get_triplets / get_quadruplets
