@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "../../include/gemnet_b200.h"
 
 #define GEMNET_API extern "C" __attribute__((visibility("default")))
@@ -33,6 +35,38 @@ constexpr int kMaxRadial = 16;
 // (the fused dense layers are) — to start its prologue now.  It still waits for this grid to complete and flush
 // before touching any activation.  A no-op otherwise.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// First statement of every kernel launched through launch_pdl(): let the successor start, then wait until the
+// predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("GEMNET_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// Launch `kernel` as a programmatic dependent of the preceding kernel of the stream: its blocks may become resident
+// while that kernel drains (this removes most of the kernel-to-kernel launch gap, also inside CUDA graphs); the
+// kernel must call pdl_enter() before it touches global memory.  Errors surface through check_launch().
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

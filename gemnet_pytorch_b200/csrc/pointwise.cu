@@ -21,7 +21,7 @@ __device__ __forceinline__ float dssilu(float x) {
 // mode 1: out = (x + ssilu(z)) * s
 __global__ void silu_fwd_kernel(const float4* __restrict__ z, const float4* __restrict__ x, float s, int64_t n4,
                                 int mode, float4* __restrict__ out) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(z + i);
@@ -37,7 +37,7 @@ __global__ void silu_fwd_kernel(const float4* __restrict__ z, const float4* __re
 // gz = g * s * dssilu(z)   (s = 1 for mode 0);  the x-branch gradient of mode 1 is g * s (scale_kernel)
 __global__ void silu_bwd_kernel(const float4* __restrict__ z, const float4* __restrict__ g, float s, int64_t n4,
                                 float4* __restrict__ gz) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(z + i), b = __ldg(g + i);
@@ -48,7 +48,7 @@ __global__ void silu_bwd_kernel(const float4* __restrict__ z, const float4* __re
 // out = (a [+ b [+ c]]) * s      (b, c optional)
 __global__ void add_scale_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                  const float4* __restrict__ c, float s, int64_t n4, float4* __restrict__ out) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 r = __ldg(a + i);
@@ -67,7 +67,7 @@ __global__ void add_scale_kernel(const float4* __restrict__ a, const float4* __r
 // out = a * b * s ; backward: ga = g * b * s, gb = g * a * s
 __global__ void mul_scale_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float s, int64_t n4,
                                  float4* __restrict__ out) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 p = __ldg(a + i), q = __ldg(b + i);
@@ -77,7 +77,7 @@ __global__ void mul_scale_kernel(const float4* __restrict__ a, const float4* __r
 __global__ void mul_scale_bwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                      const float4* __restrict__ g, float s, int64_t n4, float4* __restrict__ ga,
                                      float4* __restrict__ gb) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 p = __ldg(a + i), q = __ldg(b + i), t = __ldg(g + i);
@@ -90,6 +90,7 @@ __global__ void mul_scale_bwd_kernel(const float4* __restrict__ a, const float4*
 // 4 mul_scale, 5 mul_scale_bwd
 __global__ void tail_kernel(int op, const float* a, const float* b, const float* c, float s, int64_t begin, int64_t n,
                             float* o1, float* o2) {
+  pdl_enter();
   const int64_t i = begin + threadIdx.x;
   if (i >= n) return;
   switch (op) {
@@ -108,7 +109,7 @@ __global__ void tail_kernel(int op, const float* a, const float* b, const float*
 // out[j,:] = x[idx[j],:]  (F % 4 == 0)
 __global__ void gather_rows_kernel(const float4* __restrict__ x, const int32_t* __restrict__ idx, int64_t n, int F4,
                                    float4* __restrict__ out) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t total = n * F4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -122,7 +123,7 @@ __global__ void gather_rows_kernel(const float4* __restrict__ x, const int32_t* 
 __global__ void segment_sum_rows_kernel(const float4* __restrict__ src, const int32_t* __restrict__ perm,
                                         const int32_t* __restrict__ rowptr, int64_t n_rows, int F4,
                                         float4* __restrict__ out) {
-  pdl_trigger();
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
@@ -151,9 +152,9 @@ GEMNET_API int gemnet_scaled_silu_fwd(const float* z, const float* x, float s, i
   if (n == 0) return 0;
   GEMNET_REQUIRE(z && out && aligned16(z) && aligned16(x) && aligned16(out), "null or misaligned pointer");
   if (n / 4)
-    silu_fwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)z, (const float4*)x, s,
+    launch_pdl(silu_fwd_kernel, flat_grid(n / 4, 256), 256, 0, as_stream(stream), (const float4*)z, (const float4*)x, s,
                                                                          n / 4, mode, (float4*)out);
-  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(mode, z, x, nullptr, s, n - n % 4, n, out, nullptr);
+  if (n % 4) launch_pdl(tail_kernel, 1, 4, 0, as_stream(stream), mode, z, x, nullptr, s, n - n % 4, n, out, nullptr);
   return check_launch("gemnet_scaled_silu_fwd");
 }
 
@@ -162,9 +163,9 @@ GEMNET_API int gemnet_scaled_silu_bwd(const float* z, const float* g, float s, i
   if (n == 0) return 0;
   GEMNET_REQUIRE(z && g && gz && aligned16(z) && aligned16(g) && aligned16(gz), "null or misaligned pointer");
   if (n / 4)
-    silu_bwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)z, (const float4*)g, s,
+    launch_pdl(silu_bwd_kernel, flat_grid(n / 4, 256), 256, 0, as_stream(stream), (const float4*)z, (const float4*)g, s,
                                                                          n / 4, (float4*)gz);
-  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(2, z, g, nullptr, s, n - n % 4, n, gz, nullptr);
+  if (n % 4) launch_pdl(tail_kernel, 1, 4, 0, as_stream(stream), 2, z, g, nullptr, s, n - n % 4, n, gz, nullptr);
   return check_launch("gemnet_scaled_silu_bwd");
 }
 
@@ -174,9 +175,9 @@ GEMNET_API int gemnet_add_scale(const float* a, const float* b, const float* c, 
   if (n == 0) return 0;
   GEMNET_REQUIRE(a && out && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(out), "null or misaligned pointer");
   if (n / 4)
-    add_scale_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b,
+    launch_pdl(add_scale_kernel, flat_grid(n / 4, 256), 256, 0, as_stream(stream), (const float4*)a, (const float4*)b,
                                                                           (const float4*)c, s, n / 4, (float4*)out);
-  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(3, a, b, c, s, n - n % 4, n, out, nullptr);
+  if (n % 4) launch_pdl(tail_kernel, 1, 4, 0, as_stream(stream), 3, a, b, c, s, n - n % 4, n, out, nullptr);
   return check_launch("gemnet_add_scale");
 }
 
@@ -185,9 +186,9 @@ GEMNET_API int gemnet_mul_scale_fwd(const float* a, const float* b, float s, int
   if (n == 0) return 0;
   GEMNET_REQUIRE(a && b && out && aligned16(a) && aligned16(b) && aligned16(out), "null or misaligned pointer");
   if (n / 4)
-    mul_scale_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)a, (const float4*)b, s,
+    launch_pdl(mul_scale_kernel, flat_grid(n / 4, 256), 256, 0, as_stream(stream), (const float4*)a, (const float4*)b, s,
                                                                           n / 4, (float4*)out);
-  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(4, a, b, nullptr, s, n - n % 4, n, out, nullptr);
+  if (n % 4) launch_pdl(tail_kernel, 1, 4, 0, as_stream(stream), 4, a, b, nullptr, s, n - n % 4, n, out, nullptr);
   return check_launch("gemnet_mul_scale_fwd");
 }
 
@@ -198,9 +199,9 @@ GEMNET_API int gemnet_mul_scale_bwd(const float* a, const float* b, const float*
   GEMNET_REQUIRE(a && b && g && aligned16(a) && aligned16(b) && aligned16(g) && aligned16(ga) && aligned16(gb),
                  "null or misaligned pointer");
   if (n / 4)
-    mul_scale_bwd_kernel<<<flat_grid(n / 4, 256), 256, 0, as_stream(stream)>>>(
+    launch_pdl(mul_scale_bwd_kernel, flat_grid(n / 4, 256), 256, 0, as_stream(stream), 
         (const float4*)a, (const float4*)b, (const float4*)g, s, n / 4, (float4*)ga, (float4*)gb);
-  if (n % 4) tail_kernel<<<1, 4, 0, as_stream(stream)>>>(5, a, b, g, s, n - n % 4, n, ga, gb);
+  if (n % 4) launch_pdl(tail_kernel, 1, 4, 0, as_stream(stream), 5, a, b, g, s, n - n % 4, n, ga, gb);
   return check_launch("gemnet_mul_scale_bwd");
 }
 
@@ -208,7 +209,7 @@ GEMNET_API int gemnet_gather_rows(const float* x, const int32_t* idx, int64_t n,
   GEMNET_REQUIRE(n >= 0 && F > 0 && F % 4 == 0, "bad size (F must be a multiple of 4)");
   if (n == 0) return 0;
   GEMNET_REQUIRE(x && idx && out && aligned16(x) && aligned16(out), "null or misaligned pointer");
-  gather_rows_kernel<<<flat_grid(n * (F / 4), 256), 256, 0, as_stream(stream)>>>((const float4*)x, idx, n, F / 4,
+  launch_pdl(gather_rows_kernel, flat_grid(n * (F / 4), 256), 256, 0, as_stream(stream), (const float4*)x, idx, n, F / 4,
                                                                                 (float4*)out);
   return check_launch("gemnet_gather_rows");
 }
@@ -218,7 +219,7 @@ GEMNET_API int gemnet_segment_sum_rows(const float* src, const int32_t* perm, co
   GEMNET_REQUIRE(n_rows >= 0 && F > 0 && F % 4 == 0, "bad size (F must be a multiple of 4)");
   if (n_rows == 0) return 0;
   GEMNET_REQUIRE(rowptr && out && aligned16(src) && aligned16(out), "null or misaligned pointer");
-  segment_sum_rows_kernel<<<flat_grid(n_rows * 32, 256), 256, 0, as_stream(stream)>>>(
+  launch_pdl(segment_sum_rows_kernel, flat_grid(n_rows * 32, 256), 256, 0, as_stream(stream), 
       (const float4*)src, perm, rowptr, n_rows, F / 4, (float4*)out);
   return check_launch("gemnet_segment_sum_rows");
 }

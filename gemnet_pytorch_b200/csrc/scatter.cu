@@ -9,7 +9,7 @@ namespace gemnet {
 __global__ void edge_to_atom_fwd_kernel(const float4* __restrict__ m, const float4* __restrict__ r,
                                         const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
                                         int64_t n_atoms, int F4, float scale, float4* __restrict__ out) {
-  pdl_trigger();
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_atoms; a += warps) {
@@ -31,7 +31,7 @@ __global__ void edge_to_atom_fwd_kernel(const float4* __restrict__ m, const floa
 
 __global__ void hadamard_kernel(const float4* __restrict__ m, const float4* __restrict__ r, int64_t n4, float s,
                                 float4* __restrict__ out) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(m + i), b = __ldg(r + i);
@@ -45,7 +45,7 @@ __global__ void edge_to_atom_bwd_kernel(const float4* __restrict__ m, const floa
                                         const float4* __restrict__ g_out, float had_scale,
                                         const float4* __restrict__ g_had, float4* __restrict__ g_m,
                                         float4* __restrict__ g_r) {
-  pdl_trigger();
+  pdl_enter();
   const int64_t total = n_edges * F4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -72,6 +72,7 @@ __global__ void edge_to_atom_bwd_kernel(const float4* __restrict__ m, const floa
 // ------------------------------------------------------------------------------------------ H12
 __global__ void molecule_sum_fwd_kernel(const float* __restrict__ E_atom, const int32_t* __restrict__ rowptr,
                                         int64_t n_mol, int nT, int mean, float* __restrict__ E_mol) {
+  pdl_enter();
   const int64_t total = n_mol * nT;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -88,6 +89,7 @@ __global__ void molecule_sum_fwd_kernel(const float* __restrict__ E_atom, const 
 __global__ void molecule_sum_bwd_kernel(const float* __restrict__ g_E_mol, const int32_t* __restrict__ batch_seg,
                                         const int32_t* __restrict__ rowptr, int64_t n_atoms, int nT, int mean,
                                         float* __restrict__ g_E_atom) {
+  pdl_enter();
   const int64_t total = n_atoms * nT;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -104,6 +106,7 @@ __global__ void molecule_sum_bwd_kernel(const float* __restrict__ g_E_mol, const
 __global__ void force_readout_fwd_kernel(const float* __restrict__ F_ca, const float* __restrict__ V,
                                          const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
                                          int64_t n_atoms, int nT, float* __restrict__ F_atom) {
+  pdl_enter();
   const int64_t total = n_atoms * nT;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -127,6 +130,7 @@ __global__ void force_readout_bwd_kernel(const float* __restrict__ F_ca, const f
                                          const int32_t* __restrict__ id_a, int64_t n_edges, int nT,
                                          const float* __restrict__ g_F_atom, float* __restrict__ g_F_ca,
                                          float* __restrict__ g_V) {
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     const int64_t a = id_a[e];
@@ -161,11 +165,11 @@ GEMNET_API int gemnet_edge_to_atom_fwd(const float* m, const float* r, const int
   if (n_atoms > 0) {
     GEMNET_REQUIRE(rowptr && out && (n_edges == 0 || (m && r && perm)), "null pointer");
     const int64_t threads = n_atoms * 32;
-    edge_to_atom_fwd_kernel<<<flat_grid(threads, 256), 256, 0, st>>>(
+    launch_pdl(edge_to_atom_fwd_kernel, flat_grid(threads, 256), 256, 0, st, 
         (const float4*)m, (const float4*)r, perm, rowptr, n_atoms, F / 4, scale, (float4*)out);
   }
   if (had && n_edges > 0)
-    hadamard_kernel<<<flat_grid(n_edges * (F / 4), 256), 256, 0, st>>>((const float4*)m, (const float4*)r,
+    launch_pdl(hadamard_kernel, flat_grid(n_edges * (F / 4), 256), 256, 0, st, (const float4*)m, (const float4*)r,
                                                                        n_edges * (F / 4), had_scale, (float4*)had);
   return check_launch("gemnet_edge_to_atom_fwd");
 }
@@ -178,7 +182,7 @@ GEMNET_API int gemnet_edge_to_atom_bwd(const float* m, const float* r, const int
   GEMNET_REQUIRE(m && r && id_a, "null pointer");
   GEMNET_REQUIRE(((uintptr_t)m | (uintptr_t)r | (uintptr_t)g_out | (uintptr_t)g_had | (uintptr_t)g_m | (uintptr_t)g_r) % 16 == 0,
                  "pointers must be 16-byte aligned");
-  edge_to_atom_bwd_kernel<<<flat_grid(n_edges * (F / 4), 256), 256, 0, as_stream(stream)>>>(
+  launch_pdl(edge_to_atom_bwd_kernel, flat_grid(n_edges * (F / 4), 256), 256, 0, as_stream(stream), 
       (const float4*)m, (const float4*)r, id_a, n_edges, F / 4, scale, (const float4*)g_out, had_scale,
       (const float4*)g_had, (float4*)g_m, (float4*)g_r);
   return check_launch("gemnet_edge_to_atom_bwd");
@@ -189,7 +193,7 @@ GEMNET_API int gemnet_molecule_sum_fwd(const float* E_atom, const int32_t* mol_r
   GEMNET_REQUIRE(n_mol >= 0 && n_targets >= 1, "bad size");
   if (n_mol == 0) return 0;
   GEMNET_REQUIRE(E_atom && mol_rowptr && E_mol, "null pointer");
-  molecule_sum_fwd_kernel<<<flat_grid(n_mol * n_targets, 128), 128, 0, as_stream(stream)>>>(E_atom, mol_rowptr, n_mol,
+  launch_pdl(molecule_sum_fwd_kernel, flat_grid(n_mol * n_targets, 128), 128, 0, as_stream(stream), E_atom, mol_rowptr, n_mol,
                                                                                            n_targets, mean, E_mol);
   return check_launch("gemnet_molecule_sum_fwd");
 }
@@ -200,7 +204,7 @@ GEMNET_API int gemnet_molecule_sum_bwd(const float* g_E_mol, const int32_t* batc
   GEMNET_REQUIRE(n_atoms >= 0 && n_targets >= 1, "bad size");
   if (n_atoms == 0) return 0;
   GEMNET_REQUIRE(g_E_mol && batch_seg && mol_rowptr && g_E_atom, "null pointer");
-  molecule_sum_bwd_kernel<<<flat_grid(n_atoms * n_targets, 256), 256, 0, as_stream(stream)>>>(
+  launch_pdl(molecule_sum_bwd_kernel, flat_grid(n_atoms * n_targets, 256), 256, 0, as_stream(stream), 
       g_E_mol, batch_seg, mol_rowptr, n_atoms, n_targets, mean, g_E_atom);
   return check_launch("gemnet_molecule_sum_bwd");
 }
@@ -210,7 +214,7 @@ GEMNET_API int gemnet_force_readout_fwd(const float* F_ca, const float* V, const
   GEMNET_REQUIRE(n_atoms >= 0 && n_targets >= 1, "bad size");
   if (n_atoms == 0) return 0;
   GEMNET_REQUIRE(rowptr && F_atom, "null pointer");
-  force_readout_fwd_kernel<<<flat_grid(n_atoms * n_targets, 128), 128, 0, as_stream(stream)>>>(F_ca, V, perm, rowptr,
+  launch_pdl(force_readout_fwd_kernel, flat_grid(n_atoms * n_targets, 128), 128, 0, as_stream(stream), F_ca, V, perm, rowptr,
                                                                                               n_atoms, n_targets,
                                                                                               F_atom);
   return check_launch("gemnet_force_readout_fwd");
@@ -222,7 +226,7 @@ GEMNET_API int gemnet_force_readout_bwd(const float* F_ca, const float* V, const
   GEMNET_REQUIRE(n_edges >= 0 && n_targets >= 1, "bad size");
   if (n_edges == 0) return 0;
   GEMNET_REQUIRE(F_ca && V && id_a && g_F_atom, "null pointer");
-  force_readout_bwd_kernel<<<flat_grid(n_edges, 256), 256, 0, as_stream(stream)>>>(F_ca, V, id_a, n_edges, n_targets,
+  launch_pdl(force_readout_bwd_kernel, flat_grid(n_edges, 256), 256, 0, as_stream(stream), F_ca, V, id_a, n_edges, n_targets,
                                                                                   g_F_atom, g_F_ca, g_V);
   return check_launch("gemnet_force_readout_bwd");
 }

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) segbil_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ rbf_W1,
                                                          const float* __restrict__ W, float scale, int64_t n_edges,
                                                          float* __restrict__ out) {
+  pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* Bs = smem;  // [EB][LD]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ W, float scale, int64_t n_edges,
                                                          const float* __restrict__ g_out, float* __restrict__ g_x,
                                                          float* __restrict__ g_sph, float* __restrict__ g_rbf_W1) {
+  pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* dBs = smem;                        // [EB][LD]
   float* gs = smem + Cfg::EB * Cfg::LD;     // [EB][O]
@@ -397,7 +399,7 @@ static int launch_fwd(const float* x, const int32_t* expand, const int32_t* rowp
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div(n_edges, Cfg::EB);
-  segbil_fwd_kernel<Cfg><<<grid, Cfg::THREADS, smem, st>>>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out);
+  launch_pdl(segbil_fwd_kernel<Cfg>, grid, Cfg::THREADS, smem, st, x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out);
   return check_launch("gemnet_segbilinear_fwd");
 }
 
@@ -416,7 +418,7 @@ static int launch_bwd(const float* x, const int32_t* expand, const int32_t* rowp
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div(n_edges, Cfg::EB);
-  segbil_bwd_kernel<Cfg><<<grid, Cfg::THREADS, smem, st>>>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out,
+  launch_pdl(segbil_bwd_kernel<Cfg>, grid, Cfg::THREADS, smem, st, x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out,
                                                            g_x, g_sph, g_rbf_W1);
   return check_launch("gemnet_segbilinear_bwd");
 }

@@ -174,6 +174,7 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
                      const int32_t* __restrict__ rowptr, const float* __restrict__ sph,
                      const float* __restrict__ rbf_W1, const __nv_bfloat16* __restrict__ Wp, float scale,
                      int64_t n_edges, int n_tiles, float* __restrict__ out) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -427,7 +428,7 @@ int launch_segbil_fwd_tc(const float* x, const int32_t* expand, const int32_t* r
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  segbil_fwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(x, expand, rowptr, sph, rbf_W1, Wp, scale, n_edges, n_tiles,
+  launch_pdl(segbil_fwd_tc_kernel, grid, THREADS, SMEM_BYTES, st, x, expand, rowptr, sph, rbf_W1, Wp, scale, n_edges, n_tiles,
                                                          out);
   return check_launch("gemnet_segbilinear_fwd(algo=1)");
 }
