@@ -8,6 +8,8 @@ verbatim through a stand-in ctx object) on a minimal reverse-mode tape: a list o
 identity, and a "depends on R" flag that prunes everything that does not (weights, atom embeddings).  Weight
 gradients are never formed.  Used by GemNet.forward in eval mode; training keeps using torch.autograd.
 """
+import os
+
 import torch
 
 from . import dense_ops, graph, layers, ops
@@ -34,11 +36,56 @@ class _Linear:
 
 
 class Tape:
-    def __init__(self, enabled=True):
+    """Reverse-mode tape.  With `streams=(main, side)` every recorded op belongs to a lane (0 = main, 1 = side);
+    its backward runs on the same lane, and a gradient that crosses lanes makes the consumer's stream wait for the
+    producer's (an event over everything the producer lane has enqueued so far).  Cross-lane tensors are parked
+    in `keep` until the evaluation ends, so the caching allocator cannot hand their memory to the other stream."""
+
+    def __init__(self, enabled=True, streams=None):
         self.enabled = enabled
         self.closures = []
         self.grads = {}
         self.req = set()
+        self.streams = streams
+        self.lane = 0
+        self.glane = {}
+        self.keep = []
+
+    # -- lanes
+    def sync_from(self, src):
+        """the current lane's stream waits for everything enqueued so far on lane `src`"""
+        self.streams[self.lane].wait_stream(self.streams[src])
+
+    def switch(self, lane):
+        if self.streams is not None and lane != self.lane:
+            self.lane = lane
+            torch.cuda.set_stream(self.streams[lane])
+
+    def on_side(self, fn):
+        """run fn() on the side lane, after what the main lane has enqueued so far"""
+        if self.streams is None:
+            return fn()
+        self.switch(1)
+        self.sync_from(0)
+        try:
+            return fn()
+        finally:
+            self.switch(0)
+
+    def join(self):
+        """main lane waits for the side lane"""
+        if self.streams is not None:
+            self.switch(0)
+            self.sync_from(1)
+
+    def _take(self, key):
+        g = self.grads.pop(key, None)
+        if g is not None and self.streams is not None:
+            src = self.glane.pop(key, self.lane)
+            if src != self.lane:
+                self.sync_from(src)
+                self.keep.append(g)
+        return g
 
     def require(self, t):
         self.req.add(id(t))
@@ -49,6 +96,11 @@ class Tape:
     def add_grad(self, t, g):
         k = id(t)
         cur = self.grads.get(k)
+        if self.streams is not None:
+            if cur is not None and self.glane.get(k, self.lane) != self.lane:
+                self.sync_from(self.glane[k])
+                self.keep.append(cur)
+            self.glane[k] = self.lane
         if cur is None:
             self.grads[k] = g
         elif (cur.shape == g.shape and cur.dtype is torch.float32 and g.dtype is torch.float32 and cur.is_cuda
@@ -68,8 +120,11 @@ class Tape:
         for o in outs:
             self.req.add(id(o))
 
+        lane = self.lane
+
         def backward():
-            gs = [self.grads.pop(id(o), None) for o in outs]
+            self.switch(lane)
+            gs = [self._take(id(o)) for o in outs]
             if all(g is None for g in gs):
                 return
             gs = [torch.zeros_like(o) if g is None else g for g, o in zip(gs, outs)]
@@ -86,6 +141,7 @@ class Tape:
     def backward(self):
         for fn, _, _ in reversed(self.closures):
             fn()
+        self.join()
         self.closures.clear()
 
 
@@ -234,6 +290,24 @@ class _Run:
         return h, m
 
 
+def side_stream(model):
+    """the model's second stream (created on first use; graph capture calls this before it starts capturing)"""
+    side = getattr(model, "_side_stream", None)
+    if side is None:
+        side = model._side_stream = torch.cuda.Stream()
+    return side
+
+
+def _lanes(model):
+    """(main, side) streams for the two-lane evaluation, or None.  GEMNET_B200_LANES: "capture" (default) = only while
+    a CUDA graph is being captured (eager evaluation is host-bound, a second stream only adds event calls),
+    "1" = always, "0" = never."""
+    mode = os.environ.get("GEMNET_B200_LANES", "capture")
+    if mode == "0" or (mode == "capture" and not torch.cuda.is_current_stream_capturing()):
+        return None
+    return (torch.cuda.current_stream(), side_stream(model))
+
+
 @torch.no_grad()
 def energy_and_forces(model, inputs):
     """GemNet.forward (gemnet.py:453-615) for inference: returns (E (nMol, T), F (nAtoms, 3) | (nAtoms, T, 3))."""
@@ -245,8 +319,9 @@ def energy_and_forces(model, inputs):
     n_passes = model.num_targets if (need_forces and model.num_targets > 1) else 1
     forces = []
     E_mol = None
+    streams = _lanes(model)
     for target in range(n_passes):
-        tape = Tape(enabled=need_forces)
+        tape = Tape(enabled=need_forces, streams=streams)
         if need_forces:
             tape.require(R)
         run = _Run(model, tape, plan)
@@ -280,13 +355,20 @@ def energy_and_forces(model, inputs):
         basis["rbf_h"] = run.linear(model.mlp_rbf_h, rbf)
         rbf_out = run.linear(model.mlp_rbf_out, rbf)
 
-        E_a, F_ca = run.output_block(model.out_blocks[0], m, rbf_out)
+        # The output blocks (mostly atom-level layers: a dozen CTAs per launch) only feed the final sums, so they run
+        # on the side lane, next to the following interaction block — forward and backward.
+        tape.keep.append(m)
+        E_a, F_ca = tape.on_side(lambda: run.output_block(model.out_blocks[0], m, rbf_out))
         for i in range(model.num_blocks):
             h, m = run.interaction_block(model.int_blocks[i], h, m, basis, model.bilinear_algo)
-            E, F = run.output_block(model.out_blocks[i + 1], m, rbf_out)
-            E_a = run.add_scale(1.0, E_a, E)
-            if model.direct_forces:
-                F_ca = F_ca + F
+
+            def out_i(m=m, E_a=E_a, F_ca=F_ca, blk=model.out_blocks[i + 1]):
+                tape.keep.append(m)  # read on the side lane: must not be recycled by the main lane meanwhile
+                E, F = run.output_block(blk, m, rbf_out)
+                return run.add_scale(1.0, E_a, E), (F_ca + F if model.direct_forces else F_ca)
+
+            E_a, F_ca = tape.on_side(out_i)
+        tape.join()
         E_mol = A(ops._MoleculeSum, E_a, plan.batch_seg, plan.mol_rowptr, not model.extensive)
 
         if model.direct_forces:

@@ -225,6 +225,7 @@ class GraphedGemNet:
     def __init__(self, model, inputs, warmup=3):
         assert not model.training, "graph capture is for inference (model.eval())"
         self.model, self.inputs = model, inputs
+        engine.side_stream(model)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -278,6 +279,7 @@ class ServingGemNet:
             self.E_host.copy_(E, non_blocking=True)
             self.F_host.copy_(F, non_blocking=True)
 
+        engine.side_stream(model)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -247,3 +247,27 @@ def test_static_shape_serving_matches_fixture_and_eager(name, dev):
                 check(E, F, fx["E64"], fx["F64"])
     with pytest.raises(Exception):
         serve(build_batch(*H.molecules(list(range(0, 200))), kw["cutoff"], kw["int_cutoff"], True))
+
+
+@pytest.mark.parametrize("name", ["T", "dT", "Q"])
+def test_two_lane_evaluation_matches_single_stream(name, dev, monkeypatch):
+    """engine lanes: output blocks on a second stream (forward and backward) — same numbers as the one-stream run,
+    eagerly (GEMNET_B200_LANES=1) and inside a captured graph (the default there)."""
+    from gemnet_pytorch_b200 import build_batch
+    fx = H.load_npz(f"model_{name}.npz")
+    kw = H.model_kwargs(fx)
+    model = make_model(kw, go.synthetic_state_dict(kw, seed=int(fx["seed"])), dev)
+    ids = fx["mol_ids"].tolist()[:(6 if name == "Q" else 32)]
+    inputs = to_dev(build_batch(*H.molecules(ids), kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]), dev)
+    monkeypatch.setenv("GEMNET_B200_LANES", "0")
+    E0, F0 = model.predict(inputs)
+    monkeypatch.setenv("GEMNET_B200_LANES", "1")
+    for _ in range(3):
+        E1, F1 = model.predict(inputs)
+        check(E1, F1, E0.numpy(), F0.numpy(), tol=5e-6)
+    monkeypatch.setenv("GEMNET_B200_LANES", "capture")
+    graphed = model.make_graphed(inputs)
+    for _ in range(3):
+        E2, F2 = graphed()
+        torch.cuda.synchronize()
+        check(E2, F2, E0.numpy(), F0.numpy(), tol=5e-6)
