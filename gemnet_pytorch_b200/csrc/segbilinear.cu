@@ -116,14 +116,14 @@ __device__ __forceinline__ void segment_sum(const float* __restrict__ x, const i
   }
 }
 
-template <typename Cfg>
+template <typename Cfg, bool kFromA>
 __global__ void __launch_bounds__(256) segbil_fwd_kernel(const float* __restrict__ x,
                                                          const int32_t* __restrict__ expand,
                                                          const int32_t* __restrict__ rowptr,
                                                          const float* __restrict__ sph,
                                                          const float* __restrict__ rbf_W1,
                                                          const float* __restrict__ W, float scale, int64_t n_edges,
-                                                         float* __restrict__ out) {
+                                                         const float* __restrict__ A_in, float* __restrict__ out) {
   pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* Bs = smem;  // [EB][LD]
@@ -139,7 +139,14 @@ __global__ void __launch_bounds__(256) segbil_fwd_kernel(const float* __restrict
       continue;
     }
     float A[Cfg::S][Cfg::CC];
-    segment_sum<Cfg>(x, expand, sph, rowptr[e], rowptr[e + 1], lane, st, A);
+    if constexpr (kFromA) {  // split pipeline: phase 1 was done by segsum_kernel
+#pragma unroll
+      for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CC; ++cc) A[s][cc] = __ldg(A_in + e * (Cfg::S * Cfg::C) + s * Cfg::C + lane + 32 * cc);
+    } else {
+      segment_sum<Cfg>(x, expand, sph, rowptr[e], rowptr[e + 1], lane, st, A);
+    }
     // phase 2 with the (I,S) slab of rbf_W1 streamed through the same per-warp stage, SB rows of i at a time
     const float* rw = rbf_W1 + e * (Cfg::I * Cfg::S);
     UnitStager<Cfg> rs;
@@ -384,42 +391,372 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Split pipeline (workspace given): the gather-bound parts run in their own small-footprint kernels — one warp per
+// edge, 4 warps per CTA, no big shared-memory tile — so that ~4x more warps are resident to hide the gather latency
+// and the block scheduler balances the very uneven segment lengths; the GEMM-like parts keep the EB-edge tiling.
+//   forward :  segsum (A -> workspace)  ->  segbil_fwd_kernel<Cfg, true>  (phases 2 + 3 from A)
+//   backward:  segsum (A)  ->  segbil_bwd_edges_kernel (dB, dA -> workspace, g_rbf_W1)  ->  segbil_bwd_units_kernel
+constexpr int kSplitWarps = 4;
+
+template <typename Cfg>
+__global__ void __launch_bounds__(kSplitWarps * 32) segsum_kernel(const float* __restrict__ x,
+                                                                   const int32_t* __restrict__ expand,
+                                                                   const int32_t* __restrict__ rowptr,
+                                                                   const float* __restrict__ sph, int64_t n_edges,
+                                                                   float* __restrict__ A_out) {
+  pdl_enter();
+  __shared__ __align__(16) float stage[kSplitWarps][Cfg::SB * (Cfg::SP + 1)];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kSplitWarps + warp;
+  if (e >= n_edges) return;
+  float A[Cfg::S][Cfg::CC];
+  segment_sum<Cfg>(x, expand, sph, rowptr[e], rowptr[e + 1], lane, stage[warp], A);
+  float* dst = A_out + e * (Cfg::S * Cfg::C) + lane;
+#pragma unroll
+  for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+    for (int cc = 0; cc < Cfg::CC; ++cc) dst[s * Cfg::C + 32 * cc] = A[s][cc];
+}
+
+// rows of an (S, C) per-edge matrix with lanes over s: lane L holds row L (and row 32 + L when S > 32), all C columns
+template <typename Cfg>
+__device__ __forceinline__ void load_rows_by_lane(const float* __restrict__ M, int lane,
+                                                  float (&R)[(Cfg::S + 31) / 32][Cfg::C]) {
+#pragma unroll
+  for (int h = 0; h < (Cfg::S + 31) / 32; ++h) {
+    const int s = lane + 32 * h;
+    const float4* src = reinterpret_cast<const float4*>(M + (s < Cfg::S ? s : 0) * Cfg::C);
+#pragma unroll
+    for (int q = 0; q < Cfg::C / 4; ++q) {
+      const float4 v = s < Cfg::S ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      R[h][4 * q] = v.x; R[h][4 * q + 1] = v.y; R[h][4 * q + 2] = v.z; R[h][4 * q + 3] = v.w;
+    }
+  }
+}
+
+// backward, edge part: dB = g W'^T (CTA tile GEMM), then per edge dA = rbf_W1^T dB (-> workspace) and g_rbf_W1 = dB A^T
+template <typename Cfg>
+__global__ void __launch_bounds__(256) segbil_bwd_edges_kernel(const float* __restrict__ rbf_W1,
+                                                               const float* __restrict__ W, float scale,
+                                                               int64_t n_edges, const float* __restrict__ g_out,
+                                                               const float* __restrict__ A_in,
+                                                               float* __restrict__ dA_out,
+                                                               float* __restrict__ g_rbf_W1) {
+  pdl_enter();
+  extern __shared__ __align__(16) float smem[];
+  float* dBs = smem;                        // [EB][LD]
+  float* gs = smem + Cfg::EB * Cfg::LD;     // [EB][O]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* st = gs + Cfg::EB * Cfg::O + warp * (Cfg::SB * (Cfg::SP + 1));
+  const int64_t e0 = (int64_t)blockIdx.x * Cfg::EB;
+
+  for (int idx = threadIdx.x; idx < Cfg::EB * Cfg::O; idx += Cfg::THREADS) {
+    const int64_t e = e0 + idx / Cfg::O;
+    gs[idx] = e < n_edges ? g_out[e * Cfg::O + (idx % Cfg::O)] * scale : 0.f;
+  }
+  __syncthreads();
+  {  // dB[e][i*C+c] = sum_o g[e,o] W[c,i,o]; thread owns k' = tid + 256 j for all EB edges
+    const float4* W4 = reinterpret_cast<const float4*>(W);
+    const float4* gs4 = reinterpret_cast<const float4*>(gs);
+    for (int kp = threadIdx.x; kp < Cfg::K; kp += Cfg::THREADS) {
+      const int c = kp & (Cfg::C - 1), i = kp / Cfg::C;
+      const float4* wrow = W4 + (int64_t)(c * Cfg::I + i) * Cfg::TX;
+      float acc[Cfg::EB];
+#pragma unroll
+      for (int el = 0; el < Cfg::EB; ++el) acc[el] = 0.f;
+#pragma unroll 2
+      for (int oq = 0; oq < Cfg::TX; ++oq) {
+        const float4 w = __ldg(wrow + oq);
+#pragma unroll
+        for (int el = 0; el < Cfg::EB; ++el) {
+          const float4 g = gs4[el * Cfg::TX + oq];
+          acc[el] = fmaf(g.x, w.x, fmaf(g.y, w.y, fmaf(g.z, w.z, fmaf(g.w, w.w, acc[el]))));
+        }
+      }
+#pragma unroll
+      for (int el = 0; el < Cfg::EB; ++el) dBs[el * Cfg::LD + kp] = acc[el];
+    }
+  }
+  __syncthreads();
+
+  constexpr int IS = Cfg::I * Cfg::S;
+  constexpr bool kBySLane = Cfg::S > 16;  // wide bases: g_rbf_W1 with lanes over s (no cross-lane reductions)
+  constexpr int RSP = Cfg::S <= 8 ? 8 : 16;
+  constexpr int SHIFT = RSP == 8 ? 2 : 1;
+  for (int el = warp; el < Cfg::EB; el += Cfg::WARPS) {
+    const int64_t e = e0 + el;
+    if (e >= n_edges) continue;
+    const float* drow = dBs + el * Cfg::LD;
+    const float* rw = rbf_W1 + e * IS;
+    const float* Ae = A_in + e * (Cfg::S * Cfg::C);
+    float dA[Cfg::S][Cfg::CC];
+#pragma unroll
+    for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+      for (int cc = 0; cc < Cfg::CC; ++cc) dA[s][cc] = 0.f;
+    float As[kBySLane ? (Cfg::S + 31) / 32 : 1][kBySLane ? Cfg::C : 1];   // A rows by lane (wide bases)
+    float Ac[kBySLane ? 1 : Cfg::S][kBySLane ? 1 : Cfg::CC];              // A columns by lane (narrow bases)
+    if constexpr (kBySLane) {
+      load_rows_by_lane<Cfg>(Ae, lane, As);
+    } else {
+#pragma unroll
+      for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CC; ++cc) Ac[s][cc] = __ldg(Ae + s * Cfg::C + lane + 32 * cc);
+    }
+    UnitStager<Cfg> rs;
+    rs.fetch(nullptr, rw, 0, Cfg::I, lane);
+#pragma unroll 1
+    for (int i0 = 0; i0 < Cfg::I; i0 += Cfg::SB) {
+      rs.commit(st, lane);
+      if (i0 + Cfg::SB < Cfg::I) rs.fetch(nullptr, rw, i0 + Cfg::SB, Cfg::I, lane);
+#pragma unroll 1
+      for (int u = 0; u < Cfg::SB; ++u) {
+        const int i = i0 + u;
+        const float* wrow = st + u * Cfg::SP;
+        float d[Cfg::CC];
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CC; ++cc) d[cc] = drow[i * Cfg::C + lane + 32 * cc];
+#pragma unroll
+        for (int s = 0; s < Cfg::S; ++s) {
+          const float w = wrow[s];
+#pragma unroll
+          for (int cc = 0; cc < Cfg::CC; ++cc) dA[s][cc] = fmaf(w, d[cc], dA[s][cc]);
+        }
+        if (g_rbf_W1) {
+          if constexpr (kBySLane) {
+            // g_rbf_W1[e,i,s] = sum_c dB[i,c] A[s,c]: dB row broadcast from shared memory, A row in registers
+            float p[(Cfg::S + 31) / 32];
+#pragma unroll
+            for (int h = 0; h < (Cfg::S + 31) / 32; ++h) p[h] = 0.f;
+            const float4* d4 = reinterpret_cast<const float4*>(drow + i * Cfg::C);
+#pragma unroll
+            for (int q = 0; q < Cfg::C / 4; ++q) {
+              const float4 dv = d4[q];
+#pragma unroll
+              for (int h = 0; h < (Cfg::S + 31) / 32; ++h)
+                p[h] = fmaf(dv.x, As[h][4 * q], fmaf(dv.y, As[h][4 * q + 1],
+                       fmaf(dv.z, As[h][4 * q + 2], fmaf(dv.w, As[h][4 * q + 3], p[h]))));
+            }
+#pragma unroll
+            for (int h = 0; h < (Cfg::S + 31) / 32; ++h)
+              if (lane + 32 * h < Cfg::S) g_rbf_W1[e * IS + i * Cfg::S + lane + 32 * h] = p[h];
+          } else {
+#pragma unroll
+            for (int s0 = 0; s0 < Cfg::S; s0 += RSP) {
+              float v[RSP];
+#pragma unroll
+              for (int k = 0; k < RSP; ++k) {
+                float p = 0.f;
+                if (s0 + k < Cfg::S) {
+#pragma unroll
+                  for (int cc = 0; cc < Cfg::CC; ++cc) p = fmaf(d[cc], Ac[(s0 + k) < Cfg::S ? (s0 + k) : 0][cc], p);
+                }
+                v[k] = p;
+              }
+              const float tot = warp_multi_reduce<RSP>(v, lane);
+              const int k = lane >> SHIFT;
+              if ((lane & ((1 << SHIFT) - 1)) == 0 && s0 + k < Cfg::S) g_rbf_W1[e * IS + i * Cfg::S + s0 + k] = tot;
+            }
+          }
+        }
+      }
+    }
+    float* dst = dA_out + e * (Cfg::S * Cfg::C) + lane;
+#pragma unroll
+    for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+      for (int cc = 0; cc < Cfg::CC; ++cc) dst[s * Cfg::C + 32 * cc] = dA[s][cc];
+  }
+}
+
+// backward, unit part (one warp per edge): g_sph[t,s] = sum_c dA[s,c] x[exp,c];  g_x[exp,c] += sum_s sph[t,s] dA[s,c]
+template <typename Cfg>
+__global__ void __launch_bounds__(kSplitWarps * 32) segbil_bwd_units_kernel(const float* __restrict__ x,
+                                                                             const int32_t* __restrict__ expand,
+                                                                             const int32_t* __restrict__ rowptr,
+                                                                             const float* __restrict__ sph,
+                                                                             int64_t n_edges,
+                                                                             const float* __restrict__ dA_in,
+                                                                             float* __restrict__ g_x,
+                                                                             float* __restrict__ g_sph) {
+  pdl_enter();
+  constexpr bool kBySLane = Cfg::S > 16;
+  __shared__ __align__(16) float stage[kSplitWarps][Cfg::SB * (Cfg::SP + 1)];
+  __shared__ __align__(16) float xrows[kBySLane ? kSplitWarps : 1][kBySLane ? Cfg::SB * Cfg::C : 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kSplitWarps + warp;
+  if (e >= n_edges) return;
+  const int32_t beg = rowptr[e], end = rowptr[e + 1];
+  if (beg >= end) return;
+  float* st = stage[warp];
+  const float* dAe = dA_in + e * (Cfg::S * Cfg::C);
+  float dA[Cfg::S][Cfg::CC];
+#pragma unroll
+  for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+    for (int cc = 0; cc < Cfg::CC; ++cc) dA[s][cc] = __ldg(dAe + s * Cfg::C + lane + 32 * cc);
+  float dAs[kBySLane ? (Cfg::S + 31) / 32 : 1][kBySLane ? Cfg::C : 1];
+  if constexpr (kBySLane) load_rows_by_lane<Cfg>(dAe, lane, dAs);
+  constexpr int RSP = Cfg::S <= 8 ? 8 : 16;
+  constexpr int SHIFT = RSP == 8 ? 2 : 1;
+
+  UnitStager<Cfg> stg;
+  stg.fetch(expand, sph, beg, end, lane);
+  for (int32_t t0 = beg; t0 < end; t0 += Cfg::SB) {
+    const int nb = min(Cfg::SB, end - t0);
+    stg.commit(st, lane);
+    if (t0 + Cfg::SB < end) stg.fetch(expand, sph, t0 + Cfg::SB, end, lane);
+    float xb[Cfg::SB][Cfg::CC];
+#pragma unroll
+    for (int u = 0; u < Cfg::SB; ++u) {
+      if (u < nb) {
+        const float* xr = x + (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CC; ++cc) xb[u][cc] = __ldg(xr + 32 * cc);
+      }
+    }
+    if constexpr (kBySLane) {  // park the gathered rows in shared memory: the g_sph product reads them as broadcasts
+      if (g_sph) {
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < Cfg::SB; ++u)
+          if (u < nb) {
+#pragma unroll
+            for (int cc = 0; cc < Cfg::CC; ++cc) xrows[warp][u * Cfg::C + lane + 32 * cc] = xb[u][cc];
+          }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < Cfg::SB; ++u) {
+      if (u >= nb) break;
+      const int32_t t = t0 + u;
+      const float* sp = st + u * Cfg::SP;
+      if (g_x) {
+        float gx[Cfg::CC];
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CC; ++cc) gx[cc] = 0.f;
+        const float4* sp4 = reinterpret_cast<const float4*>(sp);
+#pragma unroll
+        for (int s4 = 0; s4 < Cfg::SP / 4; ++s4) {
+          const float4 w = sp4[s4];
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (4 * s4 + j < Cfg::S) {
+#pragma unroll
+              for (int cc = 0; cc < Cfg::CC; ++cc) gx[cc] = fmaf(wv[j], dA[4 * s4 + j][cc], gx[cc]);
+            }
+        }
+        float* gr = g_x + (int64_t)__float_as_int(st[Cfg::SB * Cfg::SP + u]) * Cfg::C + lane;
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CC; ++cc) atomicAdd(gr + 32 * cc, gx[cc]);
+      }
+      if (g_sph) {
+        if constexpr (kBySLane) {
+          float p[(Cfg::S + 31) / 32];
+#pragma unroll
+          for (int h = 0; h < (Cfg::S + 31) / 32; ++h) p[h] = 0.f;
+          const float4* x4 = reinterpret_cast<const float4*>(xrows[warp] + u * Cfg::C);
+#pragma unroll
+          for (int q = 0; q < Cfg::C / 4; ++q) {
+            const float4 xv = x4[q];
+#pragma unroll
+            for (int h = 0; h < (Cfg::S + 31) / 32; ++h)
+              p[h] = fmaf(xv.x, dAs[h][4 * q], fmaf(xv.y, dAs[h][4 * q + 1],
+                     fmaf(xv.z, dAs[h][4 * q + 2], fmaf(xv.w, dAs[h][4 * q + 3], p[h]))));
+          }
+#pragma unroll
+          for (int h = 0; h < (Cfg::S + 31) / 32; ++h)
+            if (lane + 32 * h < Cfg::S) g_sph[(int64_t)t * Cfg::S + lane + 32 * h] = p[h];
+        } else {
+#pragma unroll
+          for (int s0 = 0; s0 < Cfg::S; s0 += RSP) {
+            float v[RSP];
+#pragma unroll
+            for (int k = 0; k < RSP; ++k) {
+              float p = 0.f;
+              if (s0 + k < Cfg::S) {
+#pragma unroll
+                for (int cc = 0; cc < Cfg::CC; ++cc) p = fmaf(dA[(s0 + k) < Cfg::S ? (s0 + k) : 0][cc], xb[u][cc], p);
+              }
+              v[k] = p;
+            }
+            const float tot = warp_multi_reduce<RSP>(v, lane);
+            const int k = lane >> SHIFT;
+            if ((lane & ((1 << SHIFT) - 1)) == 0 && s0 + k < Cfg::S) g_sph[(int64_t)t * Cfg::S + s0 + k] = tot;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename Kernel>
+static int set_smem(Kernel kernel, size_t smem, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// workspace (floats): forward E*S*C (A), backward 2*E*S*C (A, dA); nullptr = fused single-kernel variants
 template <typename Cfg>
 static int launch_fwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
                       const float* rbf_W1, const float* W, float scale, int64_t n_edges, float* out,
-                      cudaStream_t st) {
+                      float* workspace, cudaStream_t st) {
   const size_t smem = sizeof(float) * (Cfg::EB * Cfg::LD + Cfg::STAGE_FLOATS);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(segbil_fwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("segbilinear fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return 1;
-    }
+    if (set_smem(segbil_fwd_kernel<Cfg, false>, smem, "segbilinear fwd")) return 1;
+    if (set_smem(segbil_fwd_kernel<Cfg, true>, smem, "segbilinear fwd")) return 1;
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div(n_edges, Cfg::EB);
-  launch_pdl(segbil_fwd_kernel<Cfg>, grid, Cfg::THREADS, smem, st, x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out);
+  if (workspace) {
+    launch_pdl(segsum_kernel<Cfg>, (unsigned)ceil_div(n_edges, kSplitWarps), kSplitWarps * 32, 0, st, x, expand, rowptr,
+               sph, n_edges, workspace);
+    launch_pdl(segbil_fwd_kernel<Cfg, true>, grid, Cfg::THREADS, smem, st, x, expand, rowptr, sph, rbf_W1, W, scale,
+               n_edges, workspace, out);
+  } else {
+    launch_pdl(segbil_fwd_kernel<Cfg, false>, grid, Cfg::THREADS, smem, st, x, expand, rowptr, sph, rbf_W1, W, scale,
+               n_edges, nullptr, out);
+  }
   return check_launch("gemnet_segbilinear_fwd");
 }
 
 template <typename Cfg>
 static int launch_bwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
                       const float* rbf_W1, const float* W, float scale, int64_t n_edges, const float* g_out,
-                      float* g_x, float* g_sph, float* g_rbf_W1, cudaStream_t st) {
+                      float* g_x, float* g_sph, float* g_rbf_W1, float* workspace, cudaStream_t st) {
   const size_t smem = sizeof(float) * (Cfg::EB * Cfg::LD + Cfg::EB * Cfg::O + Cfg::STAGE_FLOATS);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(segbil_bwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("segbilinear bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return 1;
-    }
+    if (set_smem(segbil_bwd_kernel<Cfg>, smem, "segbilinear bwd")) return 1;
+    if (set_smem(segbil_bwd_edges_kernel<Cfg>, smem, "segbilinear bwd")) return 1;
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div(n_edges, Cfg::EB);
-  launch_pdl(segbil_bwd_kernel<Cfg>, grid, Cfg::THREADS, smem, st, x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out,
-                                                           g_x, g_sph, g_rbf_W1);
+  if (workspace) {
+    const unsigned wgrid = (unsigned)ceil_div(n_edges, kSplitWarps);
+    float* A = workspace;
+    float* dA = workspace + n_edges * (Cfg::S * Cfg::C);
+    if (g_rbf_W1)
+      launch_pdl(segsum_kernel<Cfg>, wgrid, kSplitWarps * 32, 0, st, x, expand, rowptr, sph, n_edges, A);
+    launch_pdl(segbil_bwd_edges_kernel<Cfg>, grid, Cfg::THREADS, smem, st, rbf_W1, W, scale, n_edges, g_out, A, dA,
+               g_rbf_W1);
+    if (g_x || g_sph)
+      launch_pdl(segbil_bwd_units_kernel<Cfg>, wgrid, kSplitWarps * 32, 0, st, x, expand, rowptr, sph, n_edges, dA, g_x,
+                 g_sph);
+  } else {
+    launch_pdl(segbil_bwd_kernel<Cfg>, grid, Cfg::THREADS, smem, st, x, expand, rowptr, sph, rbf_W1, W, scale, n_edges,
+               g_out, g_x, g_sph, g_rbf_W1);
+  }
   return check_launch("gemnet_segbilinear_bwd");
 }
 
@@ -436,11 +773,24 @@ using QuadCfg = SegCfg<49, 32, 32, 32, 32>;
 
 using namespace gemnet;
 
+static bool split_enabled();
+
 GEMNET_API int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O,
                                                       int32_t algo, int32_t backward) {
-  (void)n_edges;
   if (algo == 1 && !backward && S == 7 && C == 64 && I == 16 && O == 64) return segbil_tc_workspace_bytes();
-  return 0;
+  if (!split_enabled()) return 0;
+  // split pipeline of the fp32 kernels: A (E,S,C) for the forward, A and dA for the backward.  The narrow triplet
+  // forward stays fused (measured: 83 us fused vs 140 us split at batch 64; its segments are short and balanced).
+  if (!backward && S <= 16) return 0;
+  return (int64_t)sizeof(float) * n_edges * S * C * (backward ? 2 : 1);
+}
+
+static bool split_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("GEMNET_B200_H7_SPLIT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 static int shape_id(int32_t S, int32_t C, int32_t I, int32_t O) {
@@ -463,8 +813,9 @@ GEMNET_API int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, con
   GEMNET_REQUIRE(((uintptr_t)W | (uintptr_t)out) % 16 == 0, "W/out must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (algo == 1) return launch_segbil_fwd_tc(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, workspace, st);
-  if (sid == 1) return launch_fwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, st);
-  return launch_fwd<QuadCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, st);
+  float* ws = split_enabled() ? static_cast<float*>(workspace) : nullptr;
+  if (sid == 1) return launch_fwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, nullptr, st);
+  return launch_fwd<QuadCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, ws, st);
 }
 
 GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
@@ -472,7 +823,6 @@ GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, con
                                       int64_t n_units, int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo,
                                       const float* g_out, float* g_x, float* g_sph, float* g_rbf_W1, float* g_W,
                                       void* workspace, void* stream) {
-  (void)workspace;
   (void)algo;  // the backward runs on the fp32 CUDA-core kernel for every algo in this library version
   GEMNET_REQUIRE(n_edges >= 0 && n_units >= 0, "negative size");
   GEMNET_REQUIRE(g_W == nullptr, "g_W is computed by the host wrapper in this library version; pass NULL");
@@ -482,7 +832,8 @@ GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, con
   GEMNET_REQUIRE(rowptr && rbf_W1 && W && g_out && (n_units == 0 || (x && expand && sph)), "null pointer");
   GEMNET_REQUIRE(((uintptr_t)W) % 16 == 0, "W must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
+  float* ws = split_enabled() ? static_cast<float*>(workspace) : nullptr;
   if (sid == 1)
-    return launch_bwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, st);
-  return launch_bwd<QuadCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, st);
+    return launch_bwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, ws, st);
+  return launch_bwd<QuadCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, ws, st);
 }

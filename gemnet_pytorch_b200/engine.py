@@ -50,6 +50,7 @@ class Tape:
         self.lane = 0
         self.glane = {}
         self.keep = []
+        self.used = set()  # side lanes that have work (only those are joined: an idle stream is not part of a capture)
 
     # -- lanes
     def sync_from(self, src):
@@ -61,22 +62,24 @@ class Tape:
             self.lane = lane
             torch.cuda.set_stream(self.streams[lane])
 
-    def on_side(self, fn):
-        """run fn() on the side lane, after what the main lane has enqueued so far"""
+    def on_side(self, fn, lane=1):
+        """run fn() on side lane `lane`, after what the main lane has enqueued so far"""
         if self.streams is None:
             return fn()
-        self.switch(1)
+        self.used.add(lane)
+        self.switch(lane)
         self.sync_from(0)
         try:
             return fn()
         finally:
             self.switch(0)
 
-    def join(self):
-        """main lane waits for the side lane"""
+    def join(self, lane=None):
+        """main lane waits for side lane `lane` (default: all of them)"""
         if self.streams is not None:
             self.switch(0)
-            self.sync_from(1)
+            for src in (sorted(self.used) if lane is None else (lane,)):
+                self.sync_from(src)
 
     def _take(self, key):
         g = self.grads.pop(key, None)
@@ -273,8 +276,11 @@ class _Run:
             x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)
             x = self.add_scale(layers.INV_SQRT_2, x_skip, x3)
         else:
-            x4 = self.quadruplet_interaction(blk.quad_interaction, m, basis, algo)
+            # the quadruplet branch fills the GPU; the triplet branch (small, latency-bound launches) hides next to it
+            self.t.keep.append(m)
+            x4 = self.t.on_side(lambda: self.quadruplet_interaction(blk.quad_interaction, m, basis, algo), lane=2)
             x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)
+            self.t.join(2)
             x = self.add_scale(layers.INV_SQRT_3, x_skip, x3, x4)
         for layer in blk.layers_before_skip:
             x = self.residual(layer, x)
@@ -291,21 +297,22 @@ class _Run:
 
 
 def side_stream(model):
-    """the model's second stream (created on first use; graph capture calls this before it starts capturing)"""
-    side = getattr(model, "_side_stream", None)
+    """the model's side streams (created on first use; graph capture calls this before it starts capturing):
+    lane 1 = output blocks, lane 2 = the quadruplet branch of an interaction block"""
+    side = getattr(model, "_side_streams", None)
     if side is None:
-        side = model._side_stream = torch.cuda.Stream()
+        side = model._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
     return side
 
 
 def _lanes(model):
-    """(main, side) streams for the two-lane evaluation, or None.  GEMNET_B200_LANES: "capture" (default) = only while
+    """(main, side, side2) streams for the multi-lane evaluation, or None.  GEMNET_B200_LANES: "capture" (default) = only while
     a CUDA graph is being captured (eager evaluation is host-bound, a second stream only adds event calls),
     "1" = always, "0" = never."""
     mode = os.environ.get("GEMNET_B200_LANES", "capture")
     if mode == "0" or (mode == "capture" and not torch.cuda.is_current_stream_capturing()):
         return None
-    return (torch.cuda.current_stream(), side_stream(model))
+    return (torch.cuda.current_stream(),) + side_stream(model)
 
 
 @torch.no_grad()

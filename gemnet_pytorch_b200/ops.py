@@ -363,7 +363,7 @@ class _SegBilinear(Function):
         ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
         _check(_L().gemnet_segbilinear_fwd(_p(x), _p(_i32(expand)), _p(_i32(rowptr)), _p(sph), _p(rbf_W1), _p(W),
                                            scale, E, U, S, C, I, O, algo, _p(out), _p(ws), _stream()),
-               "gemnet_segbilinear_fwd", kernels=1 if algo == 0 else 2)
+               "gemnet_segbilinear_fwd", kernels=1 if (algo == 0 and ws is None) else 2)
         ctx.save_for_backward(x, sph, rbf_W1, W, expand, rowptr)
         ctx.cfg = (scale, algo)
         return out
@@ -381,9 +381,11 @@ class _SegBilinear(Function):
         g_sph = torch.empty_like(sph) if ctx.needs_input_grad[1] else None
         g_rw = torch.empty_like(rbf_W1) if ctx.needs_input_grad[2] else None
         if g_x is not None or g_sph is not None or g_rw is not None:
+            nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, algo, 1)
+            ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
             _check(_L().gemnet_segbilinear_bwd(_p(x), _p(expand), _p(rowptr), _p(sph), _p(rbf_W1), _p(W), scale, E, U,
-                                               S, C, I, O, algo, _p(g), _p(g_x), _p(g_sph), _p(g_rw), None, None,
-                                               _stream()), "gemnet_segbilinear_bwd")
+                                               S, C, I, O, algo, _p(g), _p(g_x), _p(g_sph), _p(g_rw), None, _p(ws),
+                                               _stream()), "gemnet_segbilinear_bwd", kernels=3 if ws is not None else 1)
         g_W = _segbilinear_weight_grad(x, expand, rowptr, sph, rbf_W1, g * scale) if ctx.needs_input_grad[3] else None
         return g_x, g_sph, g_rw, g_W, None, None, None, None
 
