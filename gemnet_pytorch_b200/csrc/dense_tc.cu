@@ -162,6 +162,7 @@ struct Params {
   int act;             // 0 identity, 1 ScaledSiLU
   float s_acc, s_res;
   int N_img;           // rows per (kb, split) block of the packed image (64 or 128)
+  int coop;            // allow the epilogue warps to produce the second K chunk of single-tile CTAs
 };
 
 template <int NKB, int N>
@@ -208,55 +209,63 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // One K chunk (kb) of one row tile: 128 rows x 64 columns of x (.* xmul) -> exact bf16 triple -> operand stage.
+  // `ptid` = index of the thread in its 256-thread producer group.
+  auto produce = [&](int64_t r0, int kb, uint32_t g, int ptid) {
+    const int stage = g % kStages;
+    const uint32_t parity = (g / kStages) & 1u;
+    // 128 rows x 8 pieces of 8 elements per chunk = 1024 pieces, 4 per thread; 8 consecutive threads = one row
+    float4 v[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int piece = ptid + q * PRODUCER_THREADS;
+      const int row = piece >> 3, j = piece & 7;
+      const int64_t r = r0 + row;
+      const int k = kb * KB + j * 8;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        v[q][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < p.M && k + 4 * u < p.K_src) {
+          v[q][u] = __ldg(reinterpret_cast<const float4*>(p.x + r * p.ldx + k + 4 * u));
+          if (p.xmul) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(p.xmul + r * p.ldx + k + 4 * u));
+            v[q][u] = make_float4(v[q][u].x * m.x, v[q][u].y * m.y, v[q][u].z * m.z, v[q][u].w * m.w);
+          }
+        }
+      }
+    }
+    mbar_wait(empty_bar(stage), parity ^ 1u);
+    uint8_t* st = sm + W_BYTES + stage * STAGE_BYTES;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int piece = ptid + q * PRODUCER_THREADS;
+      const int row = piece >> 3, j = piece & 7;
+      const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+      uint32_t h[4], m[4], l[4];
+      split3(v[q][0].x, v[q][0].y, h[0], m[0], l[0]);
+      split3(v[q][0].z, v[q][0].w, h[1], m[1], l[1]);
+      split3(v[q][1].x, v[q][1].y, h[2], m[2], l[2]);
+      split3(v[q][1].z, v[q][1].w, h[3], m[3], l[3]);
+      *reinterpret_cast<uint4*>(st + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(st + A_SPLIT_BYTES + off) = make_uint4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<uint4*>(st + 2 * A_SPLIT_BYTES + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar(stage));
+  };
+  // Launch-bound sizes give every CTA at most ONE tile: the epilogue warps would idle until the accumulator is
+  // complete, so with two K chunks they produce chunk 1 while the producer warps produce chunk 0 — both chunks'
+  // loads are in flight together and the operand conversion takes half as long.
+  const bool coop = NKB == 2 && p.coop && n_tiles <= (int)gridDim.x;
+
   if (warp < PRODUCER_WARPS) {
     // ============================================================ producers
     griddep_wait();
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t r0 = (int64_t)tile * TILE_M;
-      for (int kb = 0; kb < NKB; ++kb, ++g) {
-        const int stage = g % kStages;
-        const uint32_t parity = (g / kStages) & 1u;
-        // 128 rows x 8 pieces of 8 elements per chunk = 1024 pieces, 4 per thread; 8 consecutive threads = one row
-        float4 v[4][2];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int piece = tid + q * PRODUCER_THREADS;
-          const int row = piece >> 3, j = piece & 7;
-          const int64_t r = r0 + row;
-          const int k = kb * KB + j * 8;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            v[q][u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < p.M && k + 4 * u < p.K_src) {
-              v[q][u] = __ldg(reinterpret_cast<const float4*>(p.x + r * p.ldx + k + 4 * u));
-              if (p.xmul) {
-                const float4 m = __ldg(reinterpret_cast<const float4*>(p.xmul + r * p.ldx + k + 4 * u));
-                v[q][u] = make_float4(v[q][u].x * m.x, v[q][u].y * m.y, v[q][u].z * m.z, v[q][u].w * m.w);
-              }
-            }
-          }
-        }
-        mbar_wait(empty_bar(stage), parity ^ 1u);
-        uint8_t* st = sm + W_BYTES + stage * STAGE_BYTES;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int piece = tid + q * PRODUCER_THREADS;
-          const int row = piece >> 3, j = piece & 7;
-          const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
-          uint32_t h[4], m[4], l[4];
-          split3(v[q][0].x, v[q][0].y, h[0], m[0], l[0]);
-          split3(v[q][0].z, v[q][0].w, h[1], m[1], l[1]);
-          split3(v[q][1].x, v[q][1].y, h[2], m[2], l[2]);
-          split3(v[q][1].z, v[q][1].w, h[3], m[3], l[3]);
-          *reinterpret_cast<uint4*>(st + off) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(st + A_SPLIT_BYTES + off) = make_uint4(m[0], m[1], m[2], m[3]);
-          *reinterpret_cast<uint4*>(st + 2 * A_SPLIT_BYTES + off) = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(stage));
-      }
+      for (int kb = 0; kb < (coop ? 1 : NKB); ++kb, ++g) produce(r0, kb, g, tid);
     }
   } else if (warp == PRODUCER_WARPS) {
     // ============================================================ MMA issuer
@@ -304,6 +313,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
     const int ew = warp & 3;                          // a warp can only touch TMEM lanes [32*(warp%4), +32)
     const int ch = (warp - EPI_WARP0) >> 2;           // column half
     griddep_wait();
+    if (coop && (int)blockIdx.x < n_tiles) produce((int64_t)blockIdx.x * TILE_M, 1, 1u, tid - EPI_WARP0 * 32);
     for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       mbar_wait(acc_full, (uint32_t)it & 1u);
       tc_fence_after();
@@ -449,7 +459,11 @@ GEMNET_API int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int
   GEMNET_REQUIRE((((uintptr_t)x | (uintptr_t)xmul | (uintptr_t)packed | (uintptr_t)res | (uintptr_t)y | (uintptr_t)dact) % 16) == 0,
                  "pointers must be 16-byte aligned");
   const int Kp = round_k(K), Np = round_n(N);
-  dtc::Params p{x, xmul, packed, res, y, dact, M, ldx, K, N, act, s_acc, s_res, Np};
+  static const int coop = [] {
+    const char* e = getenv("GEMNET_B200_DENSE_COOP");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  dtc::Params p{x, xmul, packed, res, y, dact, M, ldx, K, N, act, s_acc, s_res, Np, coop};
   cudaStream_t st = as_stream(stream);
   const bool pdl = (flags & GEMNET_DENSE_WEIGHTS_SETTLED) != 0;
   if (Kp == 64 && Np == 64) return dtc::launch<1, 64>(p, st, 1, pdl);

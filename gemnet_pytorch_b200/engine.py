@@ -64,7 +64,7 @@ class Tape:
 
     def on_side(self, fn, lane=1):
         """run fn() on side lane `lane`, after what the main lane has enqueued so far"""
-        if self.streams is None:
+        if self.streams is None or lane >= len(self.streams):
             return fn()
         self.used.add(lane)
         self.switch(lane)
@@ -79,7 +79,8 @@ class Tape:
         if self.streams is not None:
             self.switch(0)
             for src in (sorted(self.used) if lane is None else (lane,)):
-                self.sync_from(src)
+                if src in self.used:
+                    self.sync_from(src)
 
     def _take(self, key):
         g = self.grads.pop(key, None)
@@ -253,8 +254,11 @@ class _Run:
         x = self.dense(ti.down_projection, x)
         x = self.bilinear(ti.mlp_cbf, basis["rbf_W1_3"], basis["sph3"], x, p.id3_expand, p.rowptr3,
                           ti.scale_cbf_sum.value(), algo)
+        self.t.keep.append(x)
+        x_ac = self.t.on_side(lambda: self.gather(self.dense(ti.up_projection_ac, x), p.id_swap, p.swap_perm,
+                                                  p.swap_rowptr), lane=3)
         x_ca = self.dense(ti.up_projection_ca, x)
-        x_ac = self.gather(self.dense(ti.up_projection_ac, x), p.id_swap, p.swap_perm, p.swap_rowptr)
+        self.t.join(3)
         return self.add_scale(layers.INV_SQRT_2, x_ca, x_ac)
 
     def quadruplet_interaction(self, qi, m, basis, algo):
@@ -271,15 +275,16 @@ class _Run:
         return self.add_scale(layers.INV_SQRT_2, x_ca, x_ac)
 
     def interaction_block(self, blk, h, m, basis, algo):
-        x_skip = self.dense(blk.dense_ca, m)
+        self.t.keep.append(m)
+        x_skip = self.t.on_side(lambda: self.dense(blk.dense_ca, m), lane=3)
         if blk.triplets_only:
-            x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)
+            x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)  # joins lane 3
             x = self.add_scale(layers.INV_SQRT_2, x_skip, x3)
         else:
             # the quadruplet branch fills the GPU; the triplet branch (small, latency-bound launches) hides next to it
             self.t.keep.append(m)
             x4 = self.t.on_side(lambda: self.quadruplet_interaction(blk.quad_interaction, m, basis, algo), lane=2)
-            x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)
+            x3 = self.triplet_interaction(blk.trip_interaction, m, basis, algo)  # joins lane 3
             self.t.join(2)
             x = self.add_scale(layers.INV_SQRT_3, x_skip, x3, x4)
         for layer in blk.layers_before_skip:
@@ -298,10 +303,11 @@ class _Run:
 
 def side_stream(model):
     """the model's side streams (created on first use; graph capture calls this before it starts capturing):
-    lane 1 = output blocks, lane 2 = the quadruplet branch of an interaction block"""
+    lane 1 = output blocks, lane 2 = the quadruplet branch of an interaction block, lane 3 = short independent
+    branches inside an interaction block (the skip projection, the second up-projection)"""
     side = getattr(model, "_side_streams", None)
     if side is None:
-        side = model._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        side = model._side_streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
     return side
 
 
@@ -312,7 +318,8 @@ def _lanes(model):
     mode = os.environ.get("GEMNET_B200_LANES", "capture")
     if mode == "0" or (mode == "capture" and not torch.cuda.is_current_stream_capturing()):
         return None
-    return (torch.cuda.current_stream(),) + side_stream(model)
+    n_side = int(os.environ.get("GEMNET_B200_SIDE_LANES", "3"))
+    return (torch.cuda.current_stream(),) + side_stream(model)[:n_side]
 
 
 @torch.no_grad()
