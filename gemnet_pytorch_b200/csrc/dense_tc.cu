@@ -27,6 +27,8 @@
 //   warps 10-17 epilogue: tcgen05.ld, accumulator sum, activation / scale / residual, 128-bit stores
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gemnet {
@@ -113,6 +115,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[CW]) {
+  if constexpr (CW == 32) tmem_ld32(taddr, r);
+  else tmem_ld16(taddr, r);
 }
 
 // exact three-way bf16 split of two fp32 values: v = h + m + l (each packed as bf16x2, .x = first value)
@@ -259,6 +276,73 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
   // loads are in flight together and the operand conversion takes half as long.
   const bool coop = NKB == 2 && p.coop && n_tiles <= (int)gridDim.x;
 
+  // Epilogue of columns [c_begin, c_end) of this CTA's slab for the 32 rows of the warp's TMEM lane quadrant, CW columns
+  // at a time: accumulators -> compensated sum -> activation / residual -> y (and dact).
+  auto epilogue_cols = [&](auto cw_tag, int tile, int c_begin, int c_end) {
+    constexpr int CW = decltype(cw_tag)::value;
+    const int ew = warp & 3;                          // a warp can only touch TMEM lanes [32*(warp%4), +32)
+    const int64_t r = (int64_t)tile * TILE_M + ew * 32 + lane;
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += CW) {
+      uint32_t acc[CW], t2[CW];
+      const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + c0;
+      // Rounding-bias compensation: every tcgen05 accumulate rounds its fp32 result TOWARD ZERO, which shrinks a
+      // chain of n non-trivial K16 steps by a mean factor (1 - 1.25e-8 n) (measured: profiles/diag_shrink.py).
+      // The mean loss c*main is below half an ulp of main, so it is added to the (2^-8 smaller, finer-grained)
+      // correction sum first; the final main + correction add then rounds once, to nearest.  What remains is
+      // zero-mean (rms 7e-8; cuBLAS SIMT fp32: 2e-7).
+      const float c0f = kShrinkPerStep * (float)min(4, (p.K_src + 15) / 16);
+      tmem_ld_cols<CW>(lane_base, acc);                  // main accumulator of chunk 0
+      tmem_ld_cols<CW>(lane_base + NKB * N, t2);         // correction accumulator
+#pragma unroll
+      for (int v = 0; v < CW; ++v) t2[v] = __float_as_uint(fmaf(__uint_as_float(acc[v]), c0f, __uint_as_float(t2[v])));
+      if (NKB == 2) {
+        uint32_t t3[CW];
+        const float c1f = kShrinkPerStep * (float)max(0, min(4, (p.K_src - KB + 15) / 16));
+        tmem_ld_cols<CW>(lane_base + N, t3);             // main accumulator of chunk 1
+#pragma unroll
+        for (int v = 0; v < CW; ++v) {
+          t2[v] = __float_as_uint(fmaf(__uint_as_float(t3[v]), c1f, __uint_as_float(t2[v])));
+          acc[v] = __float_as_uint(__uint_as_float(acc[v]) + __uint_as_float(t3[v]));
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < CW; ++v) acc[v] = __float_as_uint(__uint_as_float(acc[v]) + __uint_as_float(t2[v]));
+      const int col0 = n_off + c0;
+      if (r < p.M && col0 < p.N_out) {
+        float* yrow = p.y + r * p.N_out + col0;
+        const float* rrow = p.res ? p.res + r * p.N_out + col0 : nullptr;
+        float* drow = p.dact ? p.dact + r * p.N_out + col0 : nullptr;
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+          if (col0 + 4 * q >= p.N_out) break;
+          float o[4], d[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float z = __uint_as_float(acc[4 * q + u]);
+            if (p.act) {
+              // silu(z)/0.6 and its derivative; sigmoid and 1 - sigmoid from exp(-|z|): no overflow / cancellation
+              const float t = expf(-fabsf(z));   // in (0, 1]: no overflow
+              const float rr = 1.0f / (1.0f + t);
+              const float sg = z >= 0.f ? rr : t * rr, oms = z >= 0.f ? t * rr : rr;
+              o[u] = z * sg * kSiluScale * p.s_acc;
+              d[u] = sg * fmaf(z, oms, 1.0f) * kSiluScale * p.s_acc;
+            } else {
+              o[u] = z * p.s_acc;
+              d[u] = p.s_acc;
+            }
+          }
+          if (rrow) {
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + 4 * q));
+            o[0] += p.s_res * rv.x; o[1] += p.s_res * rv.y; o[2] += p.s_res * rv.z; o[3] += p.s_res * rv.w;
+          }
+          *reinterpret_cast<float4*>(yrow + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+          if (drow) *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
+        }
+      }
+    }
+  };
+
   if (warp < PRODUCER_WARPS) {
     // ============================================================ producers
     griddep_wait();
@@ -266,6 +350,13 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t r0 = (int64_t)tile * TILE_M;
       for (int kb = 0; kb < (coop ? 1 : NKB); ++kb, ++g) produce(r0, kb, g, tid);
+    }
+    if (coop && (int)blockIdx.x < n_tiles) {  // ... and take the other half of the epilogue columns
+      mbar_wait(acc_full, 0u);
+      tc_fence_after();
+      const int cq = 2 + (warp >> 2);
+      epilogue_cols(std::integral_constant<int, 16>{}, blockIdx.x, cq * (N / 4), (cq + 1) * (N / 4));
+      tc_fence_before();
     }
   } else if (warp == PRODUCER_WARPS) {
     // ============================================================ MMA issuer
@@ -310,73 +401,14 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
     }
   } else {
     // ============================================================ epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves
-    const int ew = warp & 3;                          // a warp can only touch TMEM lanes [32*(warp%4), +32)
-    const int ch = (warp - EPI_WARP0) >> 2;           // column half
+    const int ch = (warp - EPI_WARP0) >> 2;           // column half (quarter pair in cooperative mode)
     griddep_wait();
     if (coop && (int)blockIdx.x < n_tiles) produce((int64_t)blockIdx.x * TILE_M, 1, 1u, tid - EPI_WARP0 * 32);
     for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       mbar_wait(acc_full, (uint32_t)it & 1u);
       tc_fence_after();
-      const int64_t r = (int64_t)tile * TILE_M + ew * 32 + lane;
-#pragma unroll 1
-      for (int c0 = ch * (N / 2); c0 < (ch + 1) * (N / 2); c0 += 32) {
-        uint32_t acc[32], t2[32];
-        const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + c0;
-        // Rounding-bias compensation: every tcgen05 accumulate rounds its fp32 result TOWARD ZERO, which shrinks a
-        // chain of n non-trivial K16 steps by a mean factor (1 - 1.25e-8 n) (measured: profiles/diag_shrink.py).
-        // The mean loss c*main is below half an ulp of main, so it is added to the (2^-8 smaller, finer-grained)
-        // correction sum first; the final main + correction add then rounds once, to nearest.  What remains is
-        // zero-mean (rms 7e-8; cuBLAS SIMT fp32: 2e-7).
-        const float c0f = kShrinkPerStep * (float)min(4, (p.K_src + 15) / 16);
-        uint32_t t3[32];
-        tmem_ld32(lane_base, acc);                       // main accumulator of chunk 0
-        tmem_ld32(lane_base + NKB * N, t2);              // correction accumulator
-#pragma unroll
-        for (int v = 0; v < 32; ++v) t2[v] = __float_as_uint(fmaf(__uint_as_float(acc[v]), c0f, __uint_as_float(t2[v])));
-        if (NKB == 2) {
-          const float c1f = kShrinkPerStep * (float)max(0, min(4, (p.K_src - KB + 15) / 16));
-          tmem_ld32(lane_base + N, t3);                  // main accumulator of chunk 1
-#pragma unroll
-          for (int v = 0; v < 32; ++v) {
-            t2[v] = __float_as_uint(fmaf(__uint_as_float(t3[v]), c1f, __uint_as_float(t2[v])));
-            acc[v] = __float_as_uint(__uint_as_float(acc[v]) + __uint_as_float(t3[v]));
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < 32; ++v) acc[v] = __float_as_uint(__uint_as_float(acc[v]) + __uint_as_float(t2[v]));
-        const int col0 = n_off + c0;
-        if (r < p.M && col0 < p.N_out) {
-          float* yrow = p.y + r * p.N_out + col0;
-          const float* rrow = p.res ? p.res + r * p.N_out + col0 : nullptr;
-          float* drow = p.dact ? p.dact + r * p.N_out + col0 : nullptr;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (col0 + 4 * q >= p.N_out) break;
-            float o[4], d[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float z = __uint_as_float(acc[4 * q + u]);
-              if (p.act) {
-                // silu(z)/0.6 and its derivative; sigmoid and 1 - sigmoid from exp(-|z|): no overflow / cancellation
-                const float t = expf(-fabsf(z));   // in (0, 1]: no overflow
-                const float r = 1.0f / (1.0f + t);
-                const float sg = z >= 0.f ? r : t * r, oms = z >= 0.f ? t * r : r;
-                o[u] = z * sg * kSiluScale * p.s_acc;
-                d[u] = sg * fmaf(z, oms, 1.0f) * kSiluScale * p.s_acc;
-              } else {
-                o[u] = z * p.s_acc;
-                d[u] = p.s_acc;
-              }
-            }
-            if (rrow) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + 4 * q));
-              o[0] += p.s_res * rv.x; o[1] += p.s_res * rv.y; o[2] += p.s_res * rv.z; o[3] += p.s_res * rv.w;
-            }
-            *reinterpret_cast<float4*>(yrow + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-            if (drow) *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
-          }
-        }
-      }
+      if (coop) epilogue_cols(std::integral_constant<int, 16>{}, tile, ch * (N / 4), (ch + 1) * (N / 4));
+      else epilogue_cols(std::integral_constant<int, 32>{}, tile, ch * (N / 2), (ch + 1) * (N / 2));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);

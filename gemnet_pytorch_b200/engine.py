@@ -318,7 +318,7 @@ def _lanes(model):
     mode = os.environ.get("GEMNET_B200_LANES", "capture")
     if mode == "0" or (mode == "capture" and not torch.cuda.is_current_stream_capturing()):
         return None
-    n_side = int(os.environ.get("GEMNET_B200_SIDE_LANES", "3"))
+    n_side = int(os.environ.get("GEMNET_B200_SIDE_LANES", "2"))
     return (torch.cuda.current_stream(),) + side_stream(model)[:n_side]
 
 
