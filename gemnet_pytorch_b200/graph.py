@@ -129,6 +129,7 @@ class GraphPlan:
             self.cab_center = inputs["id_a"][r_ca].to(torch.int32).contiguous()
             self.cab_first = ib[r_ab].to(torch.int32).contiguous()
             self.cab_second = inputs["id_c"][r_ca].to(torch.int32).contiguous()
+        self.flags = flags  # int32[1] each, non-zero = not grouped/sorted; read by callers that skip the check here
         if check:
             bad = torch.cat(flags).max().item()
             if bad:
@@ -207,6 +208,17 @@ def serving_buffers(cap, pin_memory=False):
     return out
 
 
+def _pad_tables(cap):
+    """capacity-sized index tables of the pad pattern (computed once per capacity)"""
+    t = getattr(cap, "_tables", None)
+    if t is None:
+        j = np.arange(cap.edges, dtype=np.int64)
+        t = cap._tables = {"j": j, "c": _PAD_C[j % 6], "a": _PAD_A[j % 6], "grp": j // 6, "swap": j ^ 1, "half": j // 2,
+                           "partner": (j // 6) * 6 + _PAD_PARTNER[j % 6],
+                           "atom": np.arange(cap.atoms, dtype=np.int64)}
+    return t
+
+
 def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
     """Write the triplet-model batch `inputs` (reference format, host) into capacity-sized buffers (see above).
 
@@ -216,12 +228,13 @@ def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
         v = inputs[k]
         return v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
 
-    A, E, T, M = arr("Z").shape[0], arr("id_c").shape[0], arr("id3_reduce_ca").shape[0], arr("N").shape[0]
+    Z, R, seg, N = arr("Z"), arr("R"), arr("batch_seg"), arr("N")
+    red, exp = arr("id3_reduce_ca"), arr("id3_expand_ba")
+    A, E, T, M = Z.shape[0], inputs["id_c"].shape[0], red.shape[0], N.shape[0]
     if not cap.fits(A, E, T, M):
         raise _lib.GemnetB200Error(f"batch (atoms={A}, edges={E}, triplets={T}, molecules={M}) exceeds {cap}")
     if check and A:
-        seg, red = arr("batch_seg"), arr("id3_reduce_ca")
-        ok = (np.all(np.diff(seg) >= 0) and seg[0] >= 0 and seg[-1] < M and np.all(np.diff(red) >= 0)
+        ok = ((seg[1:] >= seg[:-1]).all() and seg[0] >= 0 and seg[-1] < M and (red[1:] >= red[:-1]).all()
               and (T == 0 or (red[0] >= 0 and red[-1] < E)))
         if not ok:
             raise _lib.GemnetB200Error(
@@ -229,15 +242,23 @@ def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
                 "(batch_seg, id3_reduce_ca must be non-decreasing and in range)")
     if out is None:
         out = serving_buffers(cap)
-    o = {k: v.numpy() for k, v in out.items()}
-    for k in ("Z", "R", "batch_seg"):
-        o[k][:A] = arr(k)
+    tb = _pad_tables(cap)
+    views = tb.setdefault("views", {})  # numpy views of the (long-lived) staging buffers, keyed by dict identity
+    hit = views.get(id(out))
+    if hit is None or hit[0] is not out:
+        if len(views) > 8:
+            views.clear()
+        hit = views[id(out)] = (out, {k: v.numpy() for k, v in out.items()})
+    o = hit[1]
+    o["Z"][:A] = Z
+    o["R"][:A] = R
+    o["batch_seg"][:A] = seg
     for k in ("id_c", "id_a", "id_swap", "id_undir"):
         o[k][:E] = arr(k)
-    for k in ("id3_expand_ba", "id3_reduce_ca"):
-        o[k][:T] = arr(k)
+    o["id3_expand_ba"][:T] = exp
+    o["id3_reduce_ca"][:T] = red
     # pad molecule: index cap.molecules (molecules M..cap-1 of a short batch stay empty)
-    o["N"][:M] = arr("N")
+    o["N"][:M] = N
     o["N"][M:cap.molecules] = 0
     o["N"][cap.molecules] = cap.atoms - A
     o["Z"][A:] = 1
@@ -245,25 +266,25 @@ def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
     # pad atoms form triangles (3 atoms each, 10 A apart, far from the real atoms); left-over atoms stay isolated
     n_pad = cap.atoms - A
     n_tri = max(1, n_pad // 3)
-    far = (float(np.abs(arr("R")).max()) if A else 0.0) + 100.0
-    k = np.arange(n_pad)
-    tri_of_atom = np.minimum(k // 3, n_tri - 1)
+    far = (float(np.abs(R).max()) if A else 0.0) + 100.0
+    k = tb["atom"][:n_pad]
     pos = _PAD_XYZ[np.where(k < 3 * n_tri, k % 3, 0)] + far
-    pos[:, 0] += 10.0 * tri_of_atom
+    pos[:, 0] += 10.0 * np.minimum(k // 3, n_tri - 1)
     o["R"][A:] = pos
     # pad edges: groups of 6 = the directed edges of one triangle (so the per-atom degree stays molecule-like)
     n_pe = cap.edges - E
-    j = np.arange(n_pe)
-    base = A + 3 * ((j // 6) % n_tri)
-    o["id_c"][E:] = base + _PAD_C[j % 6]
-    o["id_a"][E:] = base + _PAD_A[j % 6]
-    o["id_swap"][E:] = E + (j ^ 1)
-    o["id_undir"][E:] = E // 2 + j // 2
-    # pad triplets spread evenly over the complete groups of pad edges, CSR order kept (reduce ids non-decreasing);
-    # the expand edge is the edge of the same group with the same target atom and the other source atom
+    base = A + 3 * (tb["grp"][:n_pe] % n_tri)
+    o["id_c"][E:] = base + tb["c"][:n_pe]
+    o["id_a"][E:] = base + tb["a"][:n_pe]
+    o["id_swap"][E:] = E + tb["swap"][:n_pe]
+    o["id_undir"][E:] = E // 2 + tb["half"][:n_pe]
+    # pad triplets: `per` of them on each pad edge of the complete groups, CSR order kept (reduce ids
+    # non-decreasing); the expand edge is the edge of the same group with the same target atom and the other source
     nt = cap.triplets - T
     if nt:
-        r_local = (np.arange(nt) * ((n_pe // 6) * 6)) // nt
+        n_full = (n_pe // 6) * 6
+        per = -(-nt // n_full)
+        r_local = np.repeat(tb["j"][:-(-nt // per)], per)[:nt]
         o["id3_reduce_ca"][T:] = E + r_local
-        o["id3_expand_ba"][T:] = E + (r_local // 6) * 6 + _PAD_PARTNER[r_local % 6]
+        o["id3_expand_ba"][T:] = E + tb["partner"][r_local]
     return out, (A, E, T, M)

@@ -12,7 +12,7 @@ fp64, scatters are CSR segment sums without atomics, and scale factors are folde
 """
 import torch
 
-from . import engine, graph, layers, ops
+from . import _lib, engine, graph, layers, ops
 from .layers import (AtomEmbedding, BesselBasisLayer, Dense, EdgeEmbedding, EfficientInteractionDownProjection,
                      InteractionBlock, InteractionBlockTripletsOnly, OutputBlock, SphericalBasisLayer,
                      TensorBasisLayer)
@@ -265,7 +265,7 @@ class ServingGemNet:
         self.dev = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
         empty = {k: v[:0] for k, v in self.host.items()}
         graph.pad_batch(empty, capacity, out=self.host)  # an all-pad batch for warm-up and capture
-        self.E_host = self.F_host = None
+        self.E_host = self.F_host = self.flag_host = None
 
         def step():
             for k, h in self.host.items():
@@ -273,11 +273,14 @@ class ServingGemNet:
             inputs = dict(self.dev)  # a fresh dict: the index plan is rebuilt (inside the graph) for every batch
             inputs[graph._VALIDATED_KEY] = True
             E, F = model(inputs)
+            flags = torch.cat(inputs[graph._PLAN_KEY][1].flags)  # device-side order/range check of the index lists
             if self.E_host is None:
                 self.E_host = torch.empty(E.shape, dtype=E.dtype).pin_memory()
                 self.F_host = torch.empty(F.shape, dtype=F.dtype).pin_memory()
+                self.flag_host = torch.zeros(flags.shape, dtype=flags.dtype).pin_memory()
             self.E_host.copy_(E, non_blocking=True)
             self.F_host.copy_(F, non_blocking=True)
+            self.flag_host.copy_(flags, non_blocking=True)
 
         engine.side_stream(model)
         side = torch.cuda.Stream()
@@ -295,7 +298,11 @@ class ServingGemNet:
 
     def __call__(self, inputs):
         """inputs: reference-format batch on the HOST (torch CPU tensors or numpy arrays) -> (E, F) host tensors."""
-        _, (A, _, _, M) = graph.pad_batch(inputs, self.cap, out=self.host)
+        _, (A, _, _, M) = graph.pad_batch(inputs, self.cap, out=self.host, check=False)
         self.graph.replay()
         torch.cuda.current_stream().synchronize()
+        if self.flag_host.any():  # the plan kernels validate what the host-side check would (no extra sync: same D2H)
+            raise _lib.GemnetB200Error(
+                "index tensors are not grouped/sorted as the reference DataContainer produces them "
+                "(batch_seg, id3_reduce_ca must be non-decreasing and in range)")
         return self.E_host[:M].clone(), self.F_host[:A].clone()

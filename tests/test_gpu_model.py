@@ -247,6 +247,13 @@ def test_static_shape_serving_matches_fixture_and_eager(name, dev):
                 check(E, F, fx["E64"], fx["F64"])
     with pytest.raises(Exception):
         serve(build_batch(*H.molecules(list(range(0, 200))), kw["cutoff"], kw["int_cutoff"], True))
+    bad = dict(batches[1])
+    bad["id3_reduce_ca"] = batches[1]["id3_reduce_ca"].flip(0)  # not grouped as the DataContainer produces it
+    with pytest.raises(Exception, match="sorted"):
+        serve(bad)
+    E, F = serve(batches[1])  # and the runner keeps working afterwards
+    E0, F0 = model.predict(to_dev(batches[1], dev))
+    check(E, F, E0.numpy(), F0.numpy(), tol=5e-6)
 
 
 @pytest.mark.parametrize("name", ["T", "dT", "Q"])
