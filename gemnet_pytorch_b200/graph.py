@@ -203,7 +203,8 @@ def serving_buffers(cap, pin_memory=False):
               "id3_expand_ba": (cap.triplets,), "id3_reduce_ca": (cap.triplets,)}
     out = {}
     for k, shp in shapes.items():
-        t = torch.zeros(shp, dtype=torch.float32 if k == "R" else torch.int64)
+        # int32 staging: half the host copy and H2D bytes of the reference's int64 lists, and what the kernels consume
+        t = torch.zeros(shp, dtype=torch.float32 if k == "R" else torch.int32)
         out[k] = t.pin_memory() if pin_memory else t
     return out
 

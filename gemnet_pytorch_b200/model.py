@@ -212,6 +212,12 @@ class GemNet(torch.nn.Module):
         takes the reference-format HOST batch and returns (E, F) on the host."""
         return ServingGemNet(self, capacity, warmup)
 
+    def make_serving_pool(self, molecules, max_atoms, growth=1.12, max_graphs=16, warmup=2):
+        """Serving for a stream of batches of unknown size: capacities on a geometric ladder (each batch runs in
+        the smallest bucket that holds it, so padding costs at most ~`growth` - 1 in edges and triplets), one captured
+        graph per bucket, captured on first use.  Returns a ServingPool (same call convention as ServingGemNet)."""
+        return ServingPool(self, molecules, max_atoms, growth, max_graphs, warmup)
+
     def load_weights(self, path):
         self.load_state_dict(torch.load(path))
 
@@ -306,3 +312,43 @@ class ServingGemNet:
                 "index tensors are not grouped/sorted as the reference DataContainer produces them "
                 "(batch_seg, id3_reduce_ca must be non-decreasing and in range)")
         return self.E_host[:M].clone(), self.F_host[:A].clone()
+
+
+class ServingPool:
+    """ServingGemNet runners keyed by (edge capacity, triplet capacity) on a geometric ladder; least-recently-used
+    eviction beyond `max_graphs` (a captured bucket keeps its activations' memory pool, ~1 GB at batch 64)."""
+
+    def __init__(self, model, molecules, max_atoms, growth=1.12, max_graphs=16, warmup=2):
+        assert growth > 1.0
+        self.model, self.molecules, self.growth, self.max_graphs, self.warmup = model, molecules, growth, max_graphs, warmup
+        self.atoms = -(-(int(max_atoms) + graph.BatchCapacity.PAD_ATOMS) // 8) * 8
+        self.runners = {}  # insertion order = recency
+
+    def _ladder(self, n, base):
+        cap = base
+        while cap < n:
+            cap = int(cap * self.growth) + 1
+        return -(-cap // 8) * 8
+
+    def capacity_for(self, n_edges, n_triplets):
+        return graph.BatchCapacity(self.atoms, self._ladder(n_edges + graph.BatchCapacity.PAD_EDGES, 1024),
+                                   self._ladder(max(n_triplets, 1), 4096), self.molecules)
+
+    def __call__(self, inputs):
+        cap = self.capacity_for(int(inputs["id_c"].shape[0]), int(inputs["id3_reduce_ca"].shape[0]))
+        key = (cap.edges, cap.triplets)
+        runner = self.runners.pop(key, None)
+        if runner is None:
+            while len(self.runners) >= self.max_graphs:
+                self.runners.pop(next(iter(self.runners)))
+            runner = ServingGemNet(self.model, cap, self.warmup)
+        self.runners[key] = runner
+        return runner(inputs)
+
+    @property
+    def h2d_bytes(self):
+        return max((r.h2d_bytes for r in self.runners.values()), default=0)
+
+    @property
+    def d2h_bytes(self):
+        return max((r.d2h_bytes for r in self.runners.values()), default=0)

@@ -278,3 +278,21 @@ def test_two_lane_evaluation_matches_single_stream(name, dev, monkeypatch):
         E2, F2 = graphed()
         torch.cuda.synchronize()
         check(E2, F2, E0.numpy(), F0.numpy(), tol=5e-6)
+
+
+def test_serving_pool_buckets(dev):
+    """ServingPool: batches of different size run in different capacity buckets (one captured graph each)."""
+    from gemnet_pytorch_b200 import build_batch
+    fx = H.load_npz("model_T.npz")
+    kw = H.model_kwargs(fx)
+    model = make_model(kw, go.synthetic_state_dict(kw, seed=int(fx["seed"])), dev)
+    id_sets = [list(range(0, 8)), list(range(8, 40)), list(range(40, 48)), list(range(100, 164))]
+    batches = [build_batch(*H.molecules(ids), kw["cutoff"], kw["int_cutoff"], True) for ids in id_sets]
+    pool = model.make_serving_pool(64, max(int(b["Z"].shape[0]) for b in batches), growth=1.25)
+    for rep in range(2):
+        for ids, b in zip(id_sets, batches):
+            E, F = pool(b)
+            assert E.shape[0] == len(ids) and F.shape[0] == b["Z"].shape[0]
+            E0, F0 = model.predict(to_dev(b, dev))
+            check(E, F, E0.numpy(), F0.numpy(), tol=5e-6)
+    assert 2 <= len(pool.runners) <= 4
