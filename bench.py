@@ -136,6 +136,20 @@ def time_bilinear(plan, dev, flush, reps, algo=0):
     return t, bilinear_bytes(E, T, 7, 64, 16, 64), bilinear_flops(E, T, 7, 64, 16, 64)
 
 
+def ncu_traffic_large(n_mol):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the H7 tcgen05 kernel on the 2048-molecule batch, from the
+    committed `ncu --set full` capture of the same launch (profiles/final_run.sh); None for any other size."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_r01_final_segbil_fwd_tc_large.txt")
+    if n_mol != 2048 or not os.path.exists(path):
+        return None
+    tot = 0.0
+    for ln in open(path):
+        f = ln.split()
+        if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+    return tot or None
+
+
 def pick_cpu_threads(fn):
     """The reference is a chain of small torch CPU ops: using every hardware thread of a 100+ core host makes it
     slower, not faster.  Time one call at a few thread counts (bounded) and keep the fastest."""
@@ -302,6 +316,7 @@ def main():
     model = model.to(dev).eval()
 
     Rl, Zl = synthetic_molecules(args.batch, 1234 + rank)
+    build_batch(Rl[:2], Zl[:2], kw["cutoff"], kw["int_cutoff"], kw["triplets_only"])  # loads the library
     t0 = time.perf_counter()
     host_inputs = build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"], pin_memory=True)
     t_index = time.perf_counter() - t0
@@ -463,7 +478,8 @@ def main():
                                   "frac": bts / t_k / 1e9 / hbm_peak, "us_per_launch": t_k * 1e6,
                                   "tflops": fl / t_k / 1e12,
                                   "tensor_frac_of_bf16_peak": 3 * 2 * bplan.n_edges * 1024 * 64 / t_k / 1e12 / tc_peak,
-                                  "fp32_cuda_core_kernel_us": t_k0 * 1e6}
+                                  "fp32_cuda_core_kernel_us": t_k0 * 1e6,
+                                  "bytes_per_launch": bts, "traffic": ncu_traffic_large(args.large_batch)}
         del big, bplan
 
     # ---------------- CPU baseline beside it (oracle port of the reference path, bounded sample)
