@@ -45,6 +45,7 @@ _SIGNATURES = {
     "gemnet_scaled_silu_fwd": [_P, _P, _F, _I64, _I32, _P, _P],
     "gemnet_scaled_silu_bwd": [_P, _P, _F, _I64, _P, _P],
     "gemnet_add_scale": [_P, _P, _P, _F, _I64, _P, _P],
+    "gemnet_lincomb3": [_P, _F, _P, _F, _P, _F, _I64, _P, _P],
     "gemnet_mul_scale_fwd": [_P, _P, _F, _I64, _P, _P],
     "gemnet_mul_scale_bwd": [_P, _P, _P, _F, _I64, _P, _P, _P],
     "gemnet_gather_rows": [_P, _P, _I64, _I32, _P, _P],

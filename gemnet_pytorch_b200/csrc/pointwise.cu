@@ -45,6 +45,35 @@ __global__ void silu_bwd_kernel(const float4* __restrict__ z, const float4* __re
   }
 }
 
+// out = sa*a [+ sb*b [+ sc*c]]   (b, c optional; any n: the last n % 4 elements are done by one thread)
+__global__ void lincomb3_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b, float sb,
+                                const float* __restrict__ c, float sc, int64_t n, float* __restrict__ out) {
+  pdl_enter();
+  const int64_t n4 = n / 4, stride = (int64_t)gridDim.x * blockDim.x;
+  const float4 *a4 = reinterpret_cast<const float4*>(a), *b4 = reinterpret_cast<const float4*>(b),
+               *c4 = reinterpret_cast<const float4*>(c);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 r = __ldg(a4 + i);
+    r = make_float4(r.x * sa, r.y * sa, r.z * sa, r.w * sa);
+    if (b) {
+      const float4 t = __ldg(b4 + i);
+      r = make_float4(fmaf(sb, t.x, r.x), fmaf(sb, t.y, r.y), fmaf(sb, t.z, r.z), fmaf(sb, t.w, r.w));
+    }
+    if (c) {
+      const float4 t = __ldg(c4 + i);
+      r = make_float4(fmaf(sc, t.x, r.x), fmaf(sc, t.y, r.y), fmaf(sc, t.z, r.z), fmaf(sc, t.w, r.w));
+    }
+    reinterpret_cast<float4*>(out)[i] = r;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = 4 * n4; i < n; ++i) {
+      float r = a[i] * sa;
+      if (b) r = fmaf(sb, b[i], r);
+      if (c) r = fmaf(sc, c[i], r);
+      out[i] = r;
+    }
+}
+
 // out = (a [+ b [+ c]]) * s      (b, c optional)
 __global__ void add_scale_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                  const float4* __restrict__ c, float s, int64_t n4, float4* __restrict__ out) {
@@ -167,6 +196,15 @@ GEMNET_API int gemnet_scaled_silu_bwd(const float* z, const float* g, float s, i
                                                                          n / 4, (float4*)gz);
   if (n % 4) launch_pdl(tail_kernel, 1, 4, 0, as_stream(stream), 2, z, g, nullptr, s, n - n % 4, n, gz, nullptr);
   return check_launch("gemnet_scaled_silu_bwd");
+}
+
+GEMNET_API int gemnet_lincomb3(const float* a, float sa, const float* b, float sb, const float* c, float sc, int64_t n,
+                               float* out, void* stream) {
+  GEMNET_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return 0;
+  GEMNET_REQUIRE(a && out && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(out), "null or misaligned pointer");
+  launch_pdl(lincomb3_kernel, flat_grid(n / 4 + 1, 256), 256, 0, as_stream(stream), a, sa, b, sb, c, sc, n, out);
+  return check_launch("gemnet_lincomb3");
 }
 
 GEMNET_API int gemnet_add_scale(const float* a, const float* b, const float* c, float s, int64_t n, float* out,

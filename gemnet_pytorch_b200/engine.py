@@ -48,7 +48,6 @@ class Tape:
         self.req = set()
         self.streams = streams
         self.lane = 0
-        self.glane = {}
         self.keep = []
         self.used = set()  # side lanes that have work (only those are joined: an idle stream is not part of a capture)
 
@@ -82,14 +81,33 @@ class Tape:
                 if src in self.used:
                     self.sync_from(src)
 
-    def _take(self, key):
-        g = self.grads.pop(key, None)
-        if g is not None and self.streams is not None:
-            src = self.glane.pop(key, self.lane)
-            if src != self.lane:
+    def _take_terms(self, key):
+        """pending gradient terms [(tensor, scale)] of a tensor; makes this lane wait for the lanes that wrote them"""
+        terms = self.grads.pop(key, None)
+        if terms is None:
+            return None
+        out = []
+        for g, sc, src in terms:
+            if self.streams is not None and src != self.lane:
                 self.sync_from(src)
                 self.keep.append(g)
-        return g
+            out.append((g, sc))
+        return out
+
+    def _take(self, key):
+        """the gradient of a tensor, materialised: sum_i scale_i * term_i in ceil((n-1)/2) launches"""
+        terms = self._take_terms(key)
+        if terms is None:
+            return None
+        if len(terms) == 1 and terms[0][1] == 1.0:
+            return terms[0][0]
+        g0 = terms[0][0]
+        if all(g.shape == g0.shape and g.dtype is torch.float32 and g.is_cuda and g.is_contiguous() for g, _ in terms):
+            return ops.lincomb(terms)
+        tot = None
+        for g, sc in terms:
+            tot = g * sc if tot is None else tot + g * sc
+        return tot
 
     def require(self, t):
         self.req.add(id(t))
@@ -97,21 +115,11 @@ class Tape:
     def needs(self, t):
         return isinstance(t, torch.Tensor) and id(t) in self.req
 
-    def add_grad(self, t, g):
-        k = id(t)
-        cur = self.grads.get(k)
-        if self.streams is not None:
-            if cur is not None and self.glane.get(k, self.lane) != self.lane:
-                self.sync_from(self.glane[k])
-                self.keep.append(cur)
-            self.glane[k] = self.lane
-        if cur is None:
-            self.grads[k] = g
-        elif (cur.shape == g.shape and cur.dtype is torch.float32 and g.dtype is torch.float32 and cur.is_cuda
-              and cur.is_contiguous() and g.is_contiguous()):
-            self.grads[k] = ops._AddScale.forward(_Ctx(), 1.0, cur, g, None)  # our kernel: chains as a dependent launch
-        else:
-            self.grads[k] = cur + g
+    def add_grad(self, t, g, scale=1.0):
+        """Gradients are kept as lists of (tensor, scale, lane) terms and summed only when they are consumed: a tensor
+        with n consumers costs ceil((n-1)/2) launches instead of n-1, and the 1/sqrt(2) factors of the skip
+        connections ride along as scales instead of costing a launch each."""
+        self.grads.setdefault(id(t), []).append((g, scale, self.lane))
 
     def apply(self, Fn, *args):
         """Run Fn.forward; if any tensor argument depends on R, record Fn.backward."""
@@ -126,6 +134,17 @@ class Tape:
 
         lane = self.lane
 
+        def backward_add_scale():
+            # y = (a [+ b [+ c]]) * s: the gradient terms of y pass to every input with their scale multiplied by s
+            self.switch(lane)
+            terms = self._take_terms(id(out))
+            if terms is None:
+                return
+            for a, need in zip(args[1:], ctx.needs_input_grad[1:]):
+                if need:
+                    for g, sc in terms:
+                        self.add_grad(a, g, sc * args[0])
+
         def backward():
             self.switch(lane)
             gs = [self._take(id(o)) for o in outs]
@@ -139,7 +158,8 @@ class Tape:
                 if need and g is not None:
                     self.add_grad(a, g)
 
-        self.closures.append((backward, outs, args))  # keep tensors alive: gradients are keyed by id()
+        # keep tensors alive: gradients are keyed by id()
+        self.closures.append((backward_add_scale if Fn is ops._AddScale else backward, outs, args))
         return out
 
     def backward(self):
@@ -403,7 +423,7 @@ def energy_and_forces(model, inputs):
             seed.fill_(1.0)
         tape.add_grad(E_mol, seed)
         tape.backward()
-        gR = tape.grads.pop(id(R), None)
+        gR = tape._take(id(R))
         forces.append(-gR if gR is not None else torch.zeros_like(R))
     F_j = torch.stack(forces, dim=1) if model.num_targets > 1 else forces[0]
     return E_mol, F_j

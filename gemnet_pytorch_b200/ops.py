@@ -575,6 +575,20 @@ class _AddScale(Function):
         return None, gs, gs if ctx.has[0] else None, gs if ctx.has[1] else None
 
 
+def lincomb(terms):
+    """sum_i s_i * t_i over a list of (tensor, scale) with equal shapes (fp32, contiguous): ceil((n-1)/2) launches."""
+    terms = [(_f32(t), float(s)) for t, s in terms]
+    while True:
+        (a, sa), rest = terms[0], terms[1:3]
+        (b, sb) = rest[0] if len(rest) > 0 else (None, 0.0)
+        (c, sc) = rest[1] if len(rest) > 1 else (None, 0.0)
+        out = torch.empty_like(a)
+        _check(_L().gemnet_lincomb3(_p(a), sa, _p(b), sb, _p(c), sc, a.numel(), _p(out), _stream()), "gemnet_lincomb3")
+        terms = [(out, 1.0)] + terms[3:]
+        if len(terms) == 1:
+            return out
+
+
 def add_scale(s, a, b=None, c=None):
     """(a [+ b [+ c]]) * s — skip connections with their 1/sqrt(2), 1/sqrt(3) (interaction_block.py:202-233)."""
     return _AddScale.apply(float(s), a, b, c)

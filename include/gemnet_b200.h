@@ -214,6 +214,10 @@ int gemnet_force_readout_bwd(const float* F_ca, const float* V, const int32_t* i
 int gemnet_scaled_silu_fwd(const float* z, const float* x, float s, int64_t n, int32_t mode, float* out, void* stream);
 int gemnet_scaled_silu_bwd(const float* z, const float* g, float s, int64_t n, float* gz, void* stream);
 int gemnet_add_scale(const float* a, const float* b, const float* c, float s, int64_t n, float* out, void* stream);
+/* out = sa*a [+ sb*b [+ sc*c]] (b, c may be NULL): gradient accumulation of tensors with several consumers, with the
+ * 1/sqrt(2), 1/sqrt(3) factors of the skip connections (interaction_block.py:202-233) folded in. */
+int gemnet_lincomb3(const float* a, float sa, const float* b, float sb, const float* c, float sc, int64_t n, float* out,
+                    void* stream);
 int gemnet_mul_scale_fwd(const float* a, const float* b, float s, int64_t n, float* out, void* stream);
 int gemnet_mul_scale_bwd(const float* a, const float* b, const float* g, float s, int64_t n, float* ga, float* gb,
                          void* stream);
