@@ -136,6 +136,28 @@ def time_bilinear(plan, dev, flush, reps, algo=0):
     return t, bilinear_bytes(E, T, 7, 64, 16, 64), bilinear_flops(E, T, 7, 64, 16, 64)
 
 
+def time_dense(M, dev, flush, reps):
+    """CUDA-event time of isolated launches of the fused dense layer (M x 128) -> 128 with ScaledSiLU and the
+    derivative output (the shape of most layers of the step); algorithmic bytes = x + y + dact + packed weight image."""
+    from gemnet_pytorch_b200 import dense_ops
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(M, 128, generator=g).to(dev)
+    W = (torch.randn(128, 128, generator=g) / 11).to(dev)
+    pk = dense_ops.packed_weight(W, False)
+    for _ in range(3):
+        dense_ops.dense_tc(x, pk, act=1, want_dact=True)
+    times = []
+    for _ in range(reps):
+        flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        dense_ops.dense_tc(x, pk, act=1, want_dact=True)
+        e.record()
+        e.synchronize()
+        times.append(s.elapsed_time(e) * 1e-3)
+    return float(np.mean(times)), 4 * M * 128 * 3 + 6 * 128 * 128, 2 * M * 128 * 128
+
+
 def ncu_traffic_large(n_mol):
     """dram__bytes_read.sum + dram__bytes_write.sum of the H7 tcgen05 kernel on the 2048-molecule batch, from the
     committed `ncu --set full` capture of the same launch (profiles/final_run.sh); None for any other size."""
@@ -467,6 +489,12 @@ def main():
                         "tensor_frac_of_bf16_peak": 3 * 2 * plan.n_edges * 1024 * 64 / t_k / 1e12 / tc_peak,
                         "bytes_per_triplet": bts / max(plan.n_triplets, 1),
                         "fp32_cuda_core_kernel_us": t_k0 * 1e6}
+    # the kernel with the largest share of the step's GPU time (57 %, profiles/launches_*_summary.txt): fused dense layer
+    t_d, b_d, f_d = time_dense(plan.n_edges, dev, flush, 30)
+    line["roofline_dense"] = {"kernel": "dense_tc_kernel (fused Dense + ScaledSiLU + derivative, tcgen05 bf16x3x3)",
+                              "rows": plan.n_edges, "bound": "hbm", "achieved": b_d / t_d / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": b_d / t_d / 1e9 / hbm_peak, "us_per_launch": t_d * 1e6,
+                              "bytes_per_launch": b_d, "fp32_tflops": f_d / t_d / 1e12, "traffic": None}
     if args.large_batch and world == 1:
         Rb, Zb = synthetic_molecules(args.large_batch, 4321)
         big = {k: v.to(dev) for k, v in build_batch(Rb, Zb, kw["cutoff"], kw["int_cutoff"], True).items()}
@@ -480,6 +508,11 @@ def main():
                                   "tensor_frac_of_bf16_peak": 3 * 2 * bplan.n_edges * 1024 * 64 / t_k / 1e12 / tc_peak,
                                   "fp32_cuda_core_kernel_us": t_k0 * 1e6,
                                   "bytes_per_launch": bts, "traffic": ncu_traffic_large(args.large_batch)}
+        t_d, b_d, f_d = time_dense(bplan.n_edges, dev, flush, 10)
+        line["roofline_dense_large"] = {"rows": bplan.n_edges, "bound": "hbm", "achieved": b_d / t_d / 1e9,
+                                        "peak": hbm_peak, "unit": "GB/s", "frac": b_d / t_d / 1e9 / hbm_peak,
+                                        "us_per_launch": t_d * 1e6, "bytes_per_launch": b_d,
+                                        "fp32_tflops": f_d / t_d / 1e12}
         del big, bplan
 
     # ---------------- CPU baseline beside it (oracle port of the reference path, bounded sample)
