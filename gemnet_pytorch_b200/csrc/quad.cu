@@ -58,15 +58,24 @@ __device__ __forceinline__ void assoc_legendre(float z, float st, int S, float* 
   }
 }
 
+constexpr int kYlmThreads = 128;
+
 __global__ void quad_ylm_fwd_kernel(const float* __restrict__ cossin, const float* __restrict__ ac_proj,
                                     const float* __restrict__ bd_proj, const int32_t* __restrict__ red_cab,
                                     const int32_t* __restrict__ exp_abd, int64_t n, int S,
                                     const float* __restrict__ pref, float* __restrict__ ylm,
                                     float* __restrict__ theta_phi) {
+  // A thread owns one quadruplet = one row of S^2 values; the rows of the block's kYlmThreads consecutive quadruplets
+  // are contiguous in memory, so they are assembled in shared memory (row stride S^2 is odd: conflict-free) and
+  // written out as one coalesced block instead of 32 scattered 196-byte rows per store instruction.
+  pdl_enter();
+  __shared__ float rows[kYlmThreads * kMaxL * kMaxL];
   const int S2 = S * S;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
-    const int32_t i1 = red_cab[q], i2 = exp_abd[q];
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < n; q0 += stride) {
+    const int64_t q = q0 + threadIdx.x;
+    const bool valid = q < n;
+    const int32_t i1 = valid ? red_cab[q] : 0, i2 = valid ? exp_abd[q] : 0;
     const float z = __ldg(cossin + 2 * i1), st = __ldg(cossin + 2 * i1 + 1);
     const f3 p1 = ld3(ac_proj, i1), p2 = ld3(bd_proj, i2);
     const AnglePair a = angle_pair(p1, p2);
@@ -83,7 +92,7 @@ __global__ void quad_ylm_fwd_kernel(const float* __restrict__ cossin, const floa
       cm[m] = 2.f * cp * cm[m - 1] - cm[m - 2];
       sm[m] = 2.f * cp * sm[m - 1] - sm[m - 2];
     }
-    float* o = ylm + q * S2;
+    float* o = rows + threadIdx.x * S2;
 #pragma unroll
     for (int l = 0; l < kMaxL; ++l) {
       if (l < S) {
@@ -98,10 +107,15 @@ __global__ void quad_ylm_fwd_kernel(const float* __restrict__ cossin, const floa
         }
       }
     }
-    if (theta_phi) {
+    if (theta_phi && valid) {
       theta_phi[2 * q] = atan2f(st, z);
       theta_phi[2 * q + 1] = atan2f(a.y, a.x);
     }
+    __syncthreads();
+    const int64_t cnt = min((int64_t)blockDim.x, n - q0) * S2;
+    float* dst = ylm + q0 * S2;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = rows[i];
+    __syncthreads();
   }
 }
 
@@ -110,9 +124,20 @@ __global__ void quad_ylm_bwd_kernel(const float* __restrict__ cossin, const floa
                                     const int32_t* __restrict__ exp_abd, int64_t n, int S,
                                     const float* __restrict__ pref, const float* __restrict__ g_ylm,
                                     float* __restrict__ g_cossin, float* __restrict__ g_ac, float* __restrict__ g_bd) {
+  pdl_enter();
+  __shared__ float rows[kYlmThreads * kMaxL * kMaxL];  // the block's gradient rows, fetched as one coalesced block
   const int S2 = S * S;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < n; q0 += stride) {
+    __syncthreads();
+    {
+      const int64_t cnt = min((int64_t)blockDim.x, n - q0) * S2;
+      const float* src = g_ylm + q0 * S2;
+      for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) rows[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int64_t q = q0 + threadIdx.x;
+    if (q >= n) continue;
     const int32_t i1 = red_cab[q], i2 = exp_abd[q];
     const float z = __ldg(cossin + 2 * i1), st = __ldg(cossin + 2 * i1 + 1);
     const f3 p1 = ld3(ac_proj, i1), p2 = ld3(bd_proj, i2);
@@ -133,7 +158,7 @@ __global__ void quad_ylm_bwd_kernel(const float* __restrict__ cossin, const floa
       dsm_s[m] = 2.f * cp * dsm_s[m - 1] - dsm_s[m - 2];
     }
     float gz = 0.f, gst = 0.f, gcp = 0.f, gsp = 0.f;
-    const float* g = g_ylm + q * S2;
+    const float* g = rows + threadIdx.x * S2;
 #pragma unroll
     for (int l = 0; l < kMaxL; ++l) {
       if (l < S) {
@@ -178,7 +203,7 @@ GEMNET_API int gemnet_quad_ylm_fwd(const float* cossin_cab, const float* ac_proj
   GEMNET_REQUIRE(num_spherical >= 2 && num_spherical <= kMaxSpherical, "num_spherical must be in [2, 8]");
   if (n_quads == 0) return 0;
   GEMNET_REQUIRE(cossin_cab && ac_proj && bd_proj && id4_reduce_cab && id4_expand_abd && pref_lm && ylm, "null pointer");
-  quad_ylm_fwd_kernel<<<flat_grid(n_quads, 128), 128, 0, as_stream(stream)>>>(
+  launch_pdl(quad_ylm_fwd_kernel, flat_grid(n_quads, kYlmThreads), kYlmThreads, 0, as_stream(stream),
       cossin_cab, ac_proj, bd_proj, id4_reduce_cab, id4_expand_abd, n_quads, num_spherical, pref_lm, ylm, theta_phi);
   return check_launch("gemnet_quad_ylm_fwd");
 }
@@ -192,7 +217,7 @@ GEMNET_API int gemnet_quad_ylm_bwd(const float* cossin_cab, const float* ac_proj
   if (n_quads == 0) return 0;
   GEMNET_REQUIRE(cossin_cab && ac_proj && bd_proj && id4_reduce_cab && id4_expand_abd && pref_lm && g_ylm &&
                      g_cossin_cab && g_ac_proj && g_bd_proj, "null pointer");
-  quad_ylm_bwd_kernel<<<flat_grid(n_quads, 128), 128, 0, as_stream(stream)>>>(
+  launch_pdl(quad_ylm_bwd_kernel, flat_grid(n_quads, kYlmThreads), kYlmThreads, 0, as_stream(stream),
       cossin_cab, ac_proj, bd_proj, id4_reduce_cab, id4_expand_abd, n_quads, num_spherical, pref_lm, g_ylm,
       g_cossin_cab, g_ac_proj, g_bd_proj);
   return check_launch("gemnet_quad_ylm_bwd");
