@@ -64,3 +64,19 @@ def test_padding_is_inert(name):
     assert torch.isfinite(E1).all() and torch.isfinite(F1).all()
     assert (E1[:M] - E0).abs().max() <= 1e-12 * E0.abs().max()
     assert (F1[:A] - F0).abs().max() <= 1e-12 * F0.abs().max()
+
+
+def test_serving_pool_capacity_ladder():
+    """ServingPool buckets: monotone geometric ladder, every batch fits its bucket, padding overhead bounded."""
+    from gemnet_pytorch_b200.model import ServingPool
+    pool = ServingPool(model=None, molecules=64, max_atoms=1000, growth=1.12)
+    last = None
+    for e, t in [(10, 0), (1000, 5000), (5046, 52360), (6254, 61204), (8186, 95444), (20000, 400000)]:
+        cap = pool.capacity_for(e, t)
+        assert cap.fits(1000, e, t, 64) and cap.edges % 8 == 0 and cap.triplets % 8 == 0
+        if e >= 1024:
+            assert cap.edges <= 1.14 * (e + 6) + 16 and cap.triplets <= 1.14 * t + 16
+        if last is not None:
+            assert cap.edges >= last.edges and cap.triplets >= last.triplets
+        last = cap
+    assert pool.capacity_for(8186, 95444).edges == pool.capacity_for(8100, 95000).edges  # neighbours share a bucket
