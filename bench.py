@@ -230,14 +230,13 @@ def run_train(args, kw, rank, local_rank, world):
     import torch.distributed as dist
     from gemnet_pytorch_b200 import GemNet, build_batch
     from gemnet_pytorch_b200 import dist as gdist
-    from oracle import gemnet_oracle as go
+    from gemnet_pytorch_b200.weights import seed_synthetic_weights_
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     kw = dict(kw, triplets_only=True, direct_forces=True)
-    model = GemNet(**kw)
-    model.load_state_dict(go.synthetic_state_dict(kw, seed=1234), strict=True)
+    model = seed_synthetic_weights_(GemNet(**kw), seed=1234)
     model = model.to(dev).train()
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, amsgrad=True)
@@ -330,11 +329,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from gemnet_pytorch_b200 import GemNet, _lib, build_batch, graph
-    from oracle import gemnet_oracle as go  # weights generator + CPU baseline only
+    from gemnet_pytorch_b200.weights import seed_synthetic_weights_
 
-    sd = go.synthetic_state_dict(kw, seed=1234)
-    model = GemNet(**kw)
-    model.load_state_dict(sd, strict=True)
+    model = seed_synthetic_weights_(GemNet(**kw), seed=1234)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}  # (CPU copy, for the cpu_baseline leg)
     model = model.to(dev).eval()
 
     Rl, Zl = synthetic_molecules(args.batch, 1234 + rank)
@@ -517,6 +515,7 @@ def main():
 
     # ---------------- CPU baseline beside it (oracle port of the reference path, bounded sample)
     if world == 1 and not args.no_cpu_baseline:
+        from oracle import gemnet_oracle as go  # the checker / CPU baseline: the only use of oracle/ in this arm
         from oracle import graph_oracle as gr
         cpu_inputs = gr.to_torch_inputs(gr.build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]))
         orc = go.OracleGemNet(kw, sd)

@@ -147,3 +147,20 @@ def test_hot_path_fails_loudly_without_cuda():
     with pytest.raises(Exception) as ei:
         model(inputs)
     assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
+
+
+def test_seeded_synthetic_weights_are_deterministic_and_reference_format():
+    """gemnet_pytorch_b200.weights: the benchmark's weights come from the package (not from oracle/), are reproducible
+    and form a reference-format state_dict that the oracle model accepts."""
+    from gemnet_pytorch_b200 import GemNet
+    from gemnet_pytorch_b200.weights import seed_synthetic_weights_
+    from oracle import gemnet_oracle as go
+    fx = H.load_npz("model_T.npz")
+    kw = H.model_kwargs(fx)
+    a = seed_synthetic_weights_(GemNet(**kw), 7).state_dict()
+    b = seed_synthetic_weights_(GemNet(**kw), 7).state_dict()
+    c = seed_synthetic_weights_(GemNet(**kw), 8).state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert any(not torch.equal(a[k], c[k]) for k in a)
+    assert set(a.keys()) == set(go.synthetic_state_dict(kw).keys())
+    GemNet(**kw).load_state_dict(a, strict=True)
