@@ -25,6 +25,10 @@
 //   warp 8      one thread issues tcgen05.mma.kind::f16 (M128, N, K16) into the TMEM accumulators
 //   warp 9      one thread loads the whole packed weight image once per CTA with cp.async.bulk
 //   warps 10-17 epilogue: tcgen05.ld, accumulator sum, activation / scale / residual, 128-bit stores
+// Launch-bound sizes (every CTA has at most one tile; N = 128 is then also split over two CTAs): the roles cooperate
+// instead of waiting for each other — warps 10-17 produce K chunk 1 while warps 0-7 produce chunk 0, and warps 0-7
+// take half of the epilogue columns.  The kernel is a programmatic dependent launch: barrier setup, TMEM allocation
+// and the weight-image fetch run while the preceding kernel drains (griddepcontrol.wait guards every activation).
 #include <cuda_bf16.h>
 
 #include <type_traits>

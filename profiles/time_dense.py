@@ -42,6 +42,6 @@ for K in (32, 128):
     x = torch.rand(4096, K, device=dev) + 0.5          # positive operands: no cancellation, errors are pure rounding
     W = torch.rand(128, K, device=dev) + 0.5
     ref = x.double() @ W.double().t()
-    for name, y in (("dense_tc 3xTF32", D.dense_tc(x, D.packed_weight(W, False))), ("cuBLAS fp32", torch.mm(x, W.t()))):
+    for name, y in (("dense_tc bf16x3x3", D.dense_tc(x, D.packed_weight(W, False))), ("cuBLAS fp32", torch.mm(x, W.t()))):
         rel = (y.double() - ref) / ref
         print(f"K={K:4d} {name:16s}: mean signed rel err {rel.mean().item():+.3e}, rms {rel.pow(2).mean().sqrt().item():.3e}, max {rel.abs().max().item():.3e}")
