@@ -57,6 +57,7 @@ _SIGNATURES = {
     "gemnet_graph_size": [_P, ctypes.c_char_p],
     "gemnet_graph_copy_host": [_P, ctypes.c_char_p, _P],
     "gemnet_graph_free": [_P],
+    "gemnet_pad_batch_host": [_P] * 10 + [_I64] * 8 + [_P] * 10,
 }
 _RESTYPES = {
     "gemnet_last_error": ctypes.c_char_p,

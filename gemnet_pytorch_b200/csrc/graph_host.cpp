@@ -240,3 +240,81 @@ extern "C" __attribute__((visibility("default"))) int gemnet_graph_copy_host(con
 }
 
 extern "C" __attribute__((visibility("default"))) void gemnet_graph_free(gemnet_graph* g) { delete g; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Static-shape serving: write a reference-format (int64 / float32) triplet batch into capacity-sized int32 / float32
+// staging arrays and fill the rest with the inert pad pattern (graph.py: pad molecule of far-away triangles whose
+// atoms / edges / triplets only reference each other).  One pass per array; the Python implementation
+// (graph.pad_batch) is the specification and the test oracle for this function.
+extern "C" __attribute__((visibility("default"))) int gemnet_pad_batch_host(
+    const int64_t* Z, const float* R, const int64_t* batch_seg, const int64_t* N, const int64_t* id_c, const int64_t* id_a,
+    const int64_t* id_swap, const int64_t* id_undir, const int64_t* id3_expand, const int64_t* id3_reduce, int64_t A,
+    int64_t E, int64_t T, int64_t M, int64_t capA, int64_t capE, int64_t capT, int64_t capM, int32_t* oZ, float* oR,
+    int32_t* oSeg, int32_t* oN, int32_t* o_c, int32_t* o_a, int32_t* o_swap, int32_t* o_undir, int32_t* o_expand,
+    int32_t* o_reduce) {
+  if (A < 0 || E < 0 || T < 0 || M < 0 || A + 3 > capA || E + 6 > capE || T > capT || M > capM || (capE & 1)) {
+    gemnet::set_error("gemnet_pad_batch_host: batch (atoms=%lld, edges=%lld, triplets=%lld, molecules=%lld) exceeds the "
+                      "capacity (%lld, %lld, %lld, %lld)", (long long)A, (long long)E, (long long)T, (long long)M,
+                      (long long)capA, (long long)capE, (long long)capT, (long long)capM);
+    return 1;
+  }
+  static const int32_t kC[6] = {0, 1, 0, 2, 1, 2}, kA[6] = {1, 0, 2, 0, 2, 1}, kPartner[6] = {5, 3, 4, 1, 2, 0};
+  static const float kXYZ[3][3] = {{0.0f, 0.0f, 0.0f}, {1.2f, 0.0f, 0.0f}, {0.5f, 1.1f, 0.0f}};
+  // atoms
+  float amax = 0.f;
+  for (int64_t i = 0; i < A; ++i) {
+    oZ[i] = (int32_t)Z[i];
+    oSeg[i] = (int32_t)batch_seg[i];
+    for (int k = 0; k < 3; ++k) {
+      const float v = R[3 * i + k];
+      oR[3 * i + k] = v;
+      amax = std::fmax(amax, std::fabs(v));
+    }
+  }
+  const int64_t n_pad = capA - A;
+  const int64_t n_tri = n_pad / 3 > 0 ? n_pad / 3 : 1;
+  const float far = (A ? amax : 0.f) + 100.0f;
+  for (int64_t k = 0; k < n_pad; ++k) {
+    oZ[A + k] = 1;
+    oSeg[A + k] = (int32_t)capM;
+    const int v = k < 3 * n_tri ? (int)(k % 3) : 0;
+    const int64_t tri = k / 3 < n_tri - 1 ? k / 3 : n_tri - 1;
+    oR[3 * (A + k) + 0] = (kXYZ[v][0] + far) + 10.0f * (float)tri;
+    oR[3 * (A + k) + 1] = kXYZ[v][1] + far;
+    oR[3 * (A + k) + 2] = kXYZ[v][2] + far;
+  }
+  for (int64_t m = 0; m < M; ++m) oN[m] = (int32_t)N[m];
+  for (int64_t m = M; m < capM; ++m) oN[m] = 0;
+  oN[capM] = (int32_t)n_pad;
+  // edges
+  for (int64_t e = 0; e < E; ++e) {
+    o_c[e] = (int32_t)id_c[e];
+    o_a[e] = (int32_t)id_a[e];
+    o_swap[e] = (int32_t)id_swap[e];
+    o_undir[e] = (int32_t)id_undir[e];
+  }
+  const int64_t n_pe = capE - E;
+  for (int64_t j = 0; j < n_pe; ++j) {
+    const int32_t base = (int32_t)(A + 3 * ((j / 6) % n_tri));
+    o_c[E + j] = base + kC[j % 6];
+    o_a[E + j] = base + kA[j % 6];
+    o_swap[E + j] = (int32_t)(E + (j ^ 1));
+    o_undir[E + j] = (int32_t)(E / 2 + j / 2);
+  }
+  // triplets
+  for (int64_t t = 0; t < T; ++t) {
+    o_expand[t] = (int32_t)id3_expand[t];
+    o_reduce[t] = (int32_t)id3_reduce[t];
+  }
+  const int64_t nt = capT - T;
+  if (nt > 0) {
+    const int64_t n_full = (n_pe / 6) * 6;
+    const int64_t per = (nt + n_full - 1) / n_full;
+    for (int64_t j = 0; j < nt; ++j) {
+      const int64_t r = j / per;
+      o_reduce[T + j] = (int32_t)(E + r);
+      o_expand[T + j] = (int32_t)(E + (r / 6) * 6 + kPartner[r % 6]);
+    }
+  }
+  return 0;
+}

@@ -220,11 +220,41 @@ def _pad_tables(cap):
     return t
 
 
+_NATIVE_KEYS = ("Z", "R", "batch_seg", "N", "id_c", "id_a", "id_swap", "id_undir", "id3_expand_ba", "id3_reduce_ca")
+
+
+def _pad_batch_native(inputs, cap, out):
+    """gemnet_pad_batch_host (one native pass per array) when the batch is in the reference's tensor format: int64
+    index tensors and float32 R, contiguous, on the host.  Returns the real sizes, or None (caller falls back)."""
+    ptrs = []
+    for k in _NATIVE_KEYS:
+        v = inputs.get(k)
+        want = torch.float32 if k == "R" else torch.int64
+        if not (isinstance(v, torch.Tensor) and v.dtype is want and v.device.type == "cpu" and v.is_contiguous()):
+            return None
+        ptrs.append(v.data_ptr())
+    for k in _NATIVE_KEYS:
+        o = out[k]
+        if not (o.dtype is (torch.float32 if k == "R" else torch.int32) and o.is_contiguous()):
+            return None
+    A, E, T, M = (int(inputs["Z"].shape[0]), int(inputs["id_c"].shape[0]), int(inputs["id3_reduce_ca"].shape[0]),
+                  int(inputs["N"].shape[0]))
+    lib = _lib.load()
+    _lib.check(lib.gemnet_pad_batch_host(*ptrs, A, E, T, M, cap.atoms, cap.edges, cap.triplets, cap.molecules,
+                                         *[out[k].data_ptr() for k in _NATIVE_KEYS]), "gemnet_pad_batch_host")
+    return A, E, T, M
+
+
 def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
     """Write the triplet-model batch `inputs` (reference format, host) into capacity-sized buffers (see above).
 
     Returns (buffers, (n_atoms, n_edges, n_triplets, n_molecules)) — the real sizes, for cutting the outputs.
     `check`: validate on the host what GraphPlan otherwise validates on the device (grouping / index ranges)."""
+    if out is not None and not check:
+        sizes = _pad_batch_native(inputs, cap, out)
+        if sizes is not None:
+            return out, sizes
+
     def arr(k):
         v = inputs[k]
         return v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)

@@ -264,6 +264,22 @@ int64_t gemnet_graph_size(const gemnet_graph* g, const char* name);
 int gemnet_graph_copy_host(const gemnet_graph* g, const char* name, int32_t* dst_host);
 void gemnet_graph_free(gemnet_graph* g);
 
+/* ------------------------------------------------------------------------------------------------
+ * N4  static-shape serving: HOST function.  Writes a reference-format triplet batch (int64 index lists as
+ * DataContainer / convert_to_tensor produce them, data_container.py:491-518; float32 R) into capacity-sized int32 /
+ * float32 staging arrays and appends inert pad entries (a pad molecule with index cap_molecules whose atoms, edges and
+ * triplets only reference each other), so that one captured CUDA graph serves batches of any size up to the capacity.
+ * Requires n_atoms + 3 <= cap_atoms, n_edges + 6 <= cap_edges (even), n_triplets <= cap_triplets; o_N has
+ * cap_molecules + 1 entries.  Sortedness of batch_seg / id3_reduce_ca is validated on the device by gemnet_csr_from_sorted.
+ * ---------------------------------------------------------------------------------------------- */
+int gemnet_pad_batch_host(const int64_t* Z, const float* R, const int64_t* batch_seg, const int64_t* N,
+                          const int64_t* id_c, const int64_t* id_a, const int64_t* id_swap, const int64_t* id_undir,
+                          const int64_t* id3_expand_ba, const int64_t* id3_reduce_ca, int64_t n_atoms, int64_t n_edges,
+                          int64_t n_triplets, int64_t n_molecules, int64_t cap_atoms, int64_t cap_edges,
+                          int64_t cap_triplets, int64_t cap_molecules, int32_t* o_Z, float* o_R, int32_t* o_batch_seg,
+                          int32_t* o_N, int32_t* o_id_c, int32_t* o_id_a, int32_t* o_id_swap, int32_t* o_id_undir,
+                          int32_t* o_id3_expand_ba, int32_t* o_id3_reduce_ca);
+
 #ifdef __cplusplus
 }
 #endif

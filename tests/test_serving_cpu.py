@@ -80,3 +80,29 @@ def test_serving_pool_capacity_ladder():
             assert cap.edges >= last.edges and cap.triplets >= last.triplets
         last = cap
     assert pool.capacity_for(8186, 95444).edges == pool.capacity_for(8100, 95000).edges  # neighbours share a bucket
+
+
+def test_native_padding_equals_python_padding():
+    """gemnet_pad_batch_host (C ABI, one pass per array) is bit-identical to the Python specification graph.pad_batch,
+    including over stale buffer contents, for tiny, empty and full-size batches."""
+    from gemnet_pytorch_b200 import build_batch
+    id_sets = [[0, 3, 5], list(range(10, 74)), [7], []]
+    batches = [build_batch(*H.molecules(ids), 5.0, 10.0, True) if ids else None for ids in id_sets]
+    cap = graph.BatchCapacity.for_batches([b for b in batches if b is not None], margin=1.05)
+    bufs = graph.serving_buffers(cap)
+    empty = {k: v[:0].to(torch.float32 if k == "R" else torch.int64) for k, v in bufs.items()}
+    for b in batches:
+        b = empty if b is None else b
+        o1, o2 = graph.serving_buffers(cap), graph.serving_buffers(cap)
+        for o in (o1, o2):
+            for v in o.values():
+                v.fill_(-7)
+        assert graph._pad_batch_native(b, cap, o1) is not None                      # the native path took it
+        _, s2 = graph.pad_batch({k: np.asarray(v) for k, v in b.items()}, cap, out=o2, check=False)  # numpy -> Python path
+        _, s1 = graph.pad_batch(b, cap, out=o1, check=False)
+        assert s1 == s2
+        for k in o1:
+            assert torch.equal(o1[k], o2[k]), k
+    with pytest.raises(Exception, match="exceeds"):
+        graph.pad_batch(batches[1], graph.BatchCapacity(8, 16, 8, 64), out=graph.serving_buffers(graph.BatchCapacity(8, 16, 8, 64)),
+                        check=False)
