@@ -220,6 +220,7 @@ def _pad_tables(cap):
     return t
 
 
+_NATIVE_PAD = os.environ.get("GEMNET_B200_NATIVE_PAD", "1") != "0"
 _NATIVE_KEYS = ("Z", "R", "batch_seg", "N", "id_c", "id_a", "id_swap", "id_undir", "id3_expand_ba", "id3_reduce_ca")
 
 
@@ -250,7 +251,7 @@ def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
 
     Returns (buffers, (n_atoms, n_edges, n_triplets, n_molecules)) — the real sizes, for cutting the outputs.
     `check`: validate on the host what GraphPlan otherwise validates on the device (grouping / index ranges)."""
-    if out is not None and not check:
+    if out is not None and not check and _NATIVE_PAD:
         sizes = _pad_batch_native(inputs, cap, out)
         if sizes is not None:
             return out, sizes
