@@ -56,6 +56,7 @@ _SIGNATURES = {
     "gemnet_graph_build_host": [_P, _P, _I64, _D, _D, _I32, ctypes.POINTER(_P)],
     "gemnet_graph_size": [_P, ctypes.c_char_p],
     "gemnet_graph_copy_host": [_P, ctypes.c_char_p, _P],
+    "gemnet_graph_copy_host_i64": [_P, ctypes.c_char_p, _P],
     "gemnet_graph_free": [_P],
     "gemnet_pad_batch_host": [_P] * 10 + [_I64] * 8 + [_P] * 10,
 }

@@ -3,12 +3,16 @@
 // scipy.sparse fancy indexing, np.argsort and numba.  Plain C++: per-molecule dense distance test in fp64
 // (as the reference, :258-267), then counting-sort style emission that is already grouped by the reduce edge,
 // so no argsort is needed.  Semantics documented in include/gemnet_b200.h.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gemnet_b200.h"
@@ -49,6 +53,63 @@ void directed_pairs(const double* R, const int32_t* n_per_mol, int64_t n_mol, do
   }
 }
 
+// Run fn(chunk) for chunk in [0, n_chunks) on up to `max_threads` host threads (chunk c on thread c % T).
+template <typename Fn>
+void parallel_chunks(int n_chunks, int max_threads, Fn fn) {
+  const int T = std::max(1, std::min(n_chunks, max_threads));
+  if (T == 1) {
+    for (int c = 0; c < n_chunks; ++c) fn(c);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(T);
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([=] {
+      for (int c = t; c < n_chunks; c += T) fn(c);
+    });
+  for (auto& x : th) x.join();
+}
+
+int host_threads() {
+  static const int n = [] {
+    if (const char* e = getenv("GEMNET_B200_HOST_THREADS")) return std::max(1, atoi(e));
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(hc ? hc : 1u, 16u));
+  }();
+  return n;
+}
+
+// One retired graph object is kept for reuse: its vectors keep their capacity, so the next batch of similar size
+// writes into already-mapped memory instead of page-faulting through ~20 MB of fresh allocations (10 ms of a 30 ms
+// quadruplet build).
+std::mutex g_pool_mutex;
+gemnet_graph* g_pool = nullptr;
+
+gemnet_graph* acquire_graph() {
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool) {
+      gemnet_graph* g = g_pool;
+      g_pool = nullptr;
+      for (auto& kv : g->arrays) kv.second.clear();
+      return g;
+    }
+  }
+  return new gemnet_graph();
+}
+
+void release_graph(gemnet_graph* g) {
+  if (!g) return;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pool) {
+      g_pool = g;
+      return;
+    }
+  }
+  delete g;
+}
+
 }  // namespace
 
 extern "C" __attribute__((visibility("default"))) int gemnet_graph_build_host(const double* R, const int32_t* n_per_mol,
@@ -59,7 +120,7 @@ extern "C" __attribute__((visibility("default"))) int gemnet_graph_build_host(co
     gemnet::set_error("gemnet_graph_build_host: bad arguments");
     return 1;
   }
-  auto* g = new gemnet_graph();
+  auto* g = acquire_graph();
   auto& A = g->arrays;
   int64_t n_atoms = 0;
   for (int64_t m = 0; m < n_mol; ++m) {
@@ -172,16 +233,39 @@ extern "C" __attribute__((visibility("default"))) int gemnet_graph_build_host(co
       exp_intm_ab[off_s[i] + j] = (int32_t)i;
     }
   }
-  // pass 1: count quadruplets per reduce edge
-  std::vector<int64_t> qptr(nE + 1, 0);
+  // Quadruplets of different molecules touch disjoint reduce edges, so the interaction edges are cut at molecule
+  // boundaries into chunks of similar work and the two passes (count, emit) run chunk-parallel on the host threads.
   auto valid = [&](int64_t i, int32_t ec, int32_t ed) {
     const int32_t c = id_c[ec], a = it[i], b = is[i], d = id_c[ed];
     return c != b && a != d && c != d;
   };
-  for (int64_t i = 0; i < nI; ++i)
-    for (int64_t jd = off_s[i]; jd < off_s[i + 1]; ++jd)
-      for (int64_t jc = off_t[i]; jc < off_t[i + 1]; ++jc)
-        if (valid(i, intm_ca[jc], intm_db[jd])) qptr[intm_ca[jc] + 1]++;
+  std::vector<int64_t> chunk_begin{0};
+  {
+    const int64_t total_work = [&] {
+      int64_t w = 0;
+      for (int64_t i = 0; i < nI; ++i) w += (off_t[i + 1] - off_t[i]) * (off_s[i + 1] - off_s[i]);
+      return w;
+    }();
+    const int64_t target = total_work / (8 * host_threads()) + 1;
+    int64_t acc = 0;
+    for (int64_t i = 0; i < nI; ++i) {
+      if (i > 0 && batch_seg[it[i]] != batch_seg[it[i - 1]] && acc >= target) {
+        chunk_begin.push_back(i);
+        acc = 0;
+      }
+      acc += (off_t[i + 1] - off_t[i]) * (off_s[i + 1] - off_s[i]);
+    }
+    chunk_begin.push_back(nI);
+  }
+  const int n_chunks = (int)chunk_begin.size() - 1;
+  // pass 1: count quadruplets per reduce edge
+  std::vector<int64_t> qptr(nE + 1, 0);
+  parallel_chunks(n_chunks, host_threads(), [&](int ch) {
+    for (int64_t i = chunk_begin[ch]; i < chunk_begin[ch + 1]; ++i)
+      for (int64_t jd = off_s[i]; jd < off_s[i + 1]; ++jd)
+        for (int64_t jc = off_t[i]; jc < off_t[i + 1]; ++jc)
+          if (valid(i, intm_ca[jc], intm_db[jd])) qptr[intm_ca[jc] + 1]++;
+  });
   for (int32_t r = 0; r < nE; ++r) qptr[r + 1] += qptr[r];
   const int64_t nQ = qptr[nE];
   if (nQ > INT32_MAX) {
@@ -196,17 +280,20 @@ extern "C" __attribute__((visibility("default"))) int gemnet_graph_build_host(co
   ivec& kidx4 = A["Kidx4"];
   red_ca.resize(nQ); exp_db.resize(nQ); red_cab.resize(nQ); exp_abd.resize(nQ); kidx4.resize(nQ);
   {
+    // pass 2: emit, grouped by the reduce edge; within a group the order is the reference's (i, jd, jc) scan order
     std::vector<int64_t> cur(qptr.begin(), qptr.end() - 1);
-    for (int64_t i = 0; i < nI; ++i)
-      for (int64_t jd = off_s[i]; jd < off_s[i + 1]; ++jd)
-        for (int64_t jc = off_t[i]; jc < off_t[i + 1]; ++jc) {
-          const int32_t ec = intm_ca[jc], ed = intm_db[jd];
-          if (!valid(i, ec, ed)) continue;
-          const int64_t pos = cur[ec]++;
-          red_ca[pos] = ec; exp_db[pos] = ed;
-          red_cab[pos] = (int32_t)jc; exp_abd[pos] = (int32_t)jd;
-          kidx4[pos] = (int32_t)(pos - qptr[ec]);
-        }
+    parallel_chunks(n_chunks, host_threads(), [&](int ch) {
+      for (int64_t i = chunk_begin[ch]; i < chunk_begin[ch + 1]; ++i)
+        for (int64_t jd = off_s[i]; jd < off_s[i + 1]; ++jd)
+          for (int64_t jc = off_t[i]; jc < off_t[i + 1]; ++jc) {
+            const int32_t ec = intm_ca[jc], ed = intm_db[jd];
+            if (!valid(i, ec, ed)) continue;
+            const int64_t pos = cur[ec]++;
+            red_ca[pos] = ec; exp_db[pos] = ed;
+            red_cab[pos] = (int32_t)jc; exp_abd[pos] = (int32_t)jd;
+            kidx4[pos] = (int32_t)(pos - qptr[ec]);
+          }
+    });
   }
   *out = g;
   return 0;
@@ -239,7 +326,34 @@ extern "C" __attribute__((visibility("default"))) int gemnet_graph_copy_host(con
   return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) void gemnet_graph_free(gemnet_graph* g) { delete g; }
+extern "C" __attribute__((visibility("default"))) int gemnet_graph_copy_host_i64(const gemnet_graph* g, const char* name,
+                                                                                  int64_t* dst_host) {
+  if (!g || !name) {
+    gemnet::set_error("gemnet_graph_copy_host_i64: null argument");
+    return 1;
+  }
+  auto it = g->arrays.find(name);
+  if (it == g->arrays.end()) {
+    gemnet::set_error("gemnet_graph_copy_host_i64: unknown array '%s'", name);
+    return 1;
+  }
+  const std::vector<int32_t>& v = it->second;
+  const int64_t n = (int64_t)v.size();
+  if (n > 0 && !dst_host) {
+    gemnet::set_error("gemnet_graph_copy_host_i64: null destination");
+    return 1;
+  }
+  const int64_t kChunk = 1 << 18;  // widen in parallel: the reference's tensors are int64 (data_container.py:505-512)
+  const int n_chunks = (int)((n + kChunk - 1) / kChunk);
+  const int32_t* src = v.data();
+  parallel_chunks(n_chunks, host_threads(), [=](int c) {
+    const int64_t b = (int64_t)c * kChunk, e = std::min(n, b + kChunk);
+    for (int64_t i = b; i < e; ++i) dst_host[i] = src[i];
+  });
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) void gemnet_graph_free(gemnet_graph* g) { release_graph(g); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // Static-shape serving: write a reference-format (int64 / float32) triplet batch into capacity-sized int32 / float32

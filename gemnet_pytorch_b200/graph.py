@@ -46,8 +46,13 @@ def build_batch(R_list, Z_list, cutoff=5.0, int_cutoff=10.0, triplets_only=True,
             n = lib.gemnet_graph_size(handle, k.encode())
             if n < 0:
                 raise _lib.GemnetB200Error(f"graph builder did not produce '{k}'")
-            arr = np.empty(n, dtype=np.int32)
-            _lib.check(lib.gemnet_graph_copy_host(handle, k.encode(), arr.ctypes.data), "gemnet_graph_copy_host")
+            if as_torch:  # the reference's tensors are int64: widened by the library (multi-threaded), not by numpy
+                arr = np.empty(n, dtype=np.int64)
+                _lib.check(lib.gemnet_graph_copy_host_i64(handle, k.encode(), arr.ctypes.data),
+                           "gemnet_graph_copy_host_i64")
+            else:
+                arr = np.empty(n, dtype=np.int32)
+                _lib.check(lib.gemnet_graph_copy_host(handle, k.encode(), arr.ctypes.data), "gemnet_graph_copy_host")
             data[k] = arr
     finally:
         lib.gemnet_graph_free(handle)
@@ -55,7 +60,9 @@ def build_batch(R_list, Z_list, cutoff=5.0, int_cutoff=10.0, triplets_only=True,
         return data
     out = {}
     for k, v in data.items():
-        t = torch.from_numpy(v).to(torch.float32 if k == "R" else torch.int64)
+        # widen in numpy (single-threaded memcpy speed); a torch .to() here fans out over every host thread and costs
+        # milliseconds per array on many-core hosts
+        t = torch.from_numpy(v if (k == "R" or v.dtype == np.int64) else v.astype(np.int64))
         out[k] = t.pin_memory() if pin_memory else t
     return out
 

@@ -262,6 +262,8 @@ int gemnet_graph_build_host(const double* R_host, const int32_t* n_per_mol_host,
 int64_t gemnet_graph_size(const gemnet_graph* g, const char* name);
 /* copies array `name` into dst_host (int32, gemnet_graph_size elements) */
 int gemnet_graph_copy_host(const gemnet_graph* g, const char* name, int32_t* dst_host);
+/* the same, widened to the int64 the reference's tensors use (data_container.py:505-512); multi-threaded */
+int gemnet_graph_copy_host_i64(const gemnet_graph* g, const char* name, int64_t* dst_host);
 void gemnet_graph_free(gemnet_graph* g);
 
 /* ------------------------------------------------------------------------------------------------
