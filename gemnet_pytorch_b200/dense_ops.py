@@ -20,23 +20,39 @@ def supported(N, K):
 
 
 def packed_weight(W, transpose):
-    """B operand of acc = A @ B^T.  transpose=False: B = W (N x K) -> y = x W^T;  True: B = W^T -> gx = g W."""
-    key = (W.data_ptr(), W._version, tuple(W.shape), tuple(W.stride()), transpose)
+    """B operand of acc = A @ B^T.  transpose=False: B = W (N x K) -> y = x W^T;  True: B = W^T -> gx = g W.
+
+    One cache entry per (storage, shape, strides, orientation); it is re-packed when the tensor's version counter moves
+    (optimizer steps, copy_, load_state_dict).  In-place writes through `.data` do NOT move the counter
+    (ExponentialMovingAverage.copy_to / restore of the reference, ema_decay.py:110,145): GemNet.train()/eval() mode
+    changes, load_state_dict and .to() call `invalidate()`, which covers the reference Trainer's
+    load_averaged_variables -> eval -> restore -> train cycle; anything else must call GemNet.invalidate_caches()."""
+    key = (W.data_ptr(), tuple(W.shape), tuple(W.stride()), transpose)
     hit = _packs.get(key)
-    if hit is not None:
+    if hit is not None and hit[6] == W._version:
         return hit
     N, K = (W.shape[1], W.shape[0]) if transpose else (W.shape[0], W.shape[1])
     sn, sk = (W.stride(1), W.stride(0)) if transpose else (W.stride(0), W.stride(1))
+    if PACKER[0] is not None:  # CPU tests of the chain programs' algebra (tests/chain_emulator.py): no image
+        return [None, N, K, W, False, transpose, W._version]
     n = _L().gemnet_dense_pack_floats(N, K)
-    buf = torch.empty(n, dtype=torch.float32, device=W.device)
+    buf = hit[0] if hit is not None else torch.empty(n, dtype=torch.float32, device=W.device)
     _check(_L().gemnet_dense_pack_weight(_p(W), sn, sk, N, K, _p(buf), _stream()), "gemnet_dense_pack_weight")
-    if len(_packs) > 4096:
+    if hit is None and len(_packs) > 8192:
         _packs.clear()
     # keep W referenced: while the entry lives its storage cannot be freed and handed to another tensor with the
-    # same (data_ptr, version) — which would silently serve a stale image
-    # [4]: the pack kernel is the most recent launch -> the first dense_tc call must not prefetch the image early
-    _packs[key] = [buf, N, K, W, True]
+    # same data_ptr — which would silently serve a stale image
+    # [4]: the pack kernel is the most recent launch -> the first consumer must not prefetch the image early
+    _packs[key] = [buf, N, K, W, True, transpose, W._version]
     return _packs[key]
+
+
+PACKER = [None]
+
+
+def invalidate():
+    """Drop every packed weight image (they are rebuilt on next use)."""
+    _packs.clear()
 
 
 _fn = []

@@ -12,7 +12,7 @@ import os
 
 import torch
 
-from . import dense_ops, graph, layers, ops
+from . import chain, dense_ops, fused, graph, layers, ops
 
 
 class _Ctx:
@@ -81,18 +81,41 @@ class Tape:
                 if src in self.used:
                     self.sync_from(src)
 
-    def _take_terms(self, key):
-        """pending gradient terms [(tensor, scale)] of a tensor; makes this lane wait for the lanes that wrote them"""
+    def _take_terms(self, key, lazy_ok=False):
+        """pending gradient summands [(tensor, scale, idx, mul)] of a tensor; makes this lane wait for the lanes that
+        wrote them.  A summand with idx / mul is LAZY: it stands for scale * tensor[idx] * mul (row gather, Hadamard
+        product) and is evaluated inside the consumer's operand fill (fused.py); consumers that cannot do that get it
+        materialised here (lazy_ok=False)."""
         terms = self.grads.pop(key, None)
         if terms is None:
             return None
         out = []
-        for g, sc, src in terms:
+        for g, sc, src, idx, mul in terms:
             if self.streams is not None and src != self.lane:
                 self.sync_from(src)
                 self.keep.append(g)
-            out.append((g, sc))
+            if not lazy_ok and (idx is not None or mul is not None):
+                g, sc, idx, mul = ops.materialize_term(g, idx, mul, sc), 1.0, None, None
+            out.append((g, sc, idx, mul))
         return out
+
+    def reduce_terms(self, terms, limit, plain=False):
+        """at most `limit` summands (the plain ones are pre-summed by lincomb3 when there are too many); plain=True
+        also materialises lazy summands"""
+        if plain:
+            terms = [(ops.materialize_term(g, idx, mul, sc), 1.0, None, None) if (idx is not None or mul is not None)
+                     else (g, sc, idx, mul) for g, sc, idx, mul in terms]
+        if len(terms) <= limit:
+            return terms
+        lazy = [t for t in terms if t[2] is not None or t[3] is not None]
+        flat = [t for t in terms if t[2] is None and t[3] is None]
+        while len(lazy) >= limit:  # cannot keep them all lazy
+            g, sc, idx, mul = lazy.pop()
+            flat.append((ops.materialize_term(g, idx, mul, sc), 1.0, None, None))
+        keep = limit - len(lazy) - 1
+        head, tail = flat[:keep], flat[keep:]
+        summed = ops.lincomb([(g, sc) for g, sc, _, _ in tail]) if len(tail) > 1 or tail[0][1] != 1.0 else tail[0][0]
+        return head + [(summed, 1.0, None, None)] + lazy
 
     def _take(self, key):
         """the gradient of a tensor, materialised: sum_i scale_i * term_i in ceil((n-1)/2) launches"""
@@ -102,10 +125,10 @@ class Tape:
         if len(terms) == 1 and terms[0][1] == 1.0:
             return terms[0][0]
         g0 = terms[0][0]
-        if all(g.shape == g0.shape and g.dtype is torch.float32 and g.is_cuda and g.is_contiguous() for g, _ in terms):
-            return ops.lincomb(terms)
+        if all(g.shape == g0.shape and g.dtype is torch.float32 and g.is_cuda and g.is_contiguous() for g, _, _, _ in terms):
+            return ops.lincomb([(g, sc) for g, sc, _, _ in terms])
         tot = None
-        for g, sc in terms:
+        for g, sc, _, _ in terms:
             tot = g * sc if tot is None else tot + g * sc
         return tot
 
@@ -115,11 +138,12 @@ class Tape:
     def needs(self, t):
         return isinstance(t, torch.Tensor) and id(t) in self.req
 
-    def add_grad(self, t, g, scale=1.0):
-        """Gradients are kept as lists of (tensor, scale, lane) terms and summed only when they are consumed: a tensor
-        with n consumers costs ceil((n-1)/2) launches instead of n-1, and the 1/sqrt(2) factors of the skip
-        connections ride along as scales instead of costing a launch each."""
-        self.grads.setdefault(id(t), []).append((g, scale, self.lane))
+    def add_grad(self, t, g, scale=1.0, idx=None, mul=None):
+        """Gradients are kept as lists of (tensor, scale, lane, idx, mul) summands and summed only when they are
+        consumed: a tensor with n consumers costs ceil((n-1)/2) launches instead of n-1 (none at all when the consumer
+        is a fused chain, whose operand fill sums them), and the 1/sqrt(2) factors of the skip connections ride along
+        as scales instead of costing a launch each."""
+        self.grads.setdefault(id(t), []).append((g, scale, self.lane, idx, mul))
 
     def apply(self, Fn, *args):
         """Run Fn.forward; if any tensor argument depends on R, record Fn.backward."""
@@ -137,13 +161,28 @@ class Tape:
         def backward_add_scale():
             # y = (a [+ b [+ c]]) * s: the gradient terms of y pass to every input with their scale multiplied by s
             self.switch(lane)
-            terms = self._take_terms(id(out))
+            terms = self._take_terms(id(out), lazy_ok=True)
             if terms is None:
                 return
             for a, need in zip(args[1:], ctx.needs_input_grad[1:]):
                 if need:
-                    for g, sc in terms:
-                        self.add_grad(a, g, sc * args[0])
+                    for g, sc, idx, mul in terms:
+                        self.add_grad(a, g, sc * args[0], idx, mul)
+
+        def backward_fused():
+            # fused chains (fused.py) take the pending summands as they are and may return lazy summands
+            self.switch(lane)
+            terms = [self._take_terms(id(o), lazy_ok=True) for o in outs]
+            if all(t is None for t in terms):
+                return
+            gin = Fn.backward_terms(ctx, self, terms)
+            for a, need, g in zip(args, ctx.needs_input_grad, gin):
+                if need and g is not None:
+                    if isinstance(g, list):
+                        for gt, sc, idx, mul in g:
+                            self.add_grad(a, gt, sc, idx, mul)
+                    else:
+                        self.add_grad(a, g)
 
         def backward():
             self.switch(lane)
@@ -159,7 +198,8 @@ class Tape:
                     self.add_grad(a, g)
 
         # keep tensors alive: gradients are keyed by id()
-        self.closures.append((backward_add_scale if Fn is ops._AddScale else backward, outs, args))
+        fn = backward_add_scale if Fn is ops._AddScale else (backward_fused if getattr(Fn, "fused", False) else backward)
+        self.closures.append((fn, outs, args))
         return out
 
     def backward(self):
@@ -176,6 +216,9 @@ class _Run:
     def __init__(self, model, tape, plan):
         self.m, self.t, self.p = model, tape, plan
         self.tc = getattr(model, "dense_algo", 1) == 1  # fused tcgen05 dense layers where the shape is supported
+        # chain-fused blocks (fused.py): one launch per dense stack instead of one per layer
+        self.fuse = self.tc and getattr(model, "chain_fusion", True) and fuse_ok(model)
+        self.fuse_out = self.fuse and model.num_targets == 1
 
     # -- primitives
     def _tc_ok(self, W, x):
@@ -294,7 +337,57 @@ class _Run:
         x_ac = self.gather(self.dense(qi.up_projection_ac, x), p.id_swap, p.swap_perm, p.swap_rowptr)
         return self.add_scale(layers.INV_SQRT_2, x_ca, x_ac)
 
+    # -- chain-fused blocks (fused.py)
+    def quad_path_fused(self, qi, m, basis, algo):
+        p = self.p
+        r4 = self.linear(qi.mlp_rbf, basis["rbf4"])
+        x = self.t.apply(fused.TripPrologue, m, r4, qi.dense_db, qi.down_projection, qi.scale_rbf.value())
+        x = self.gather(x, p.id4_expand_intm_db, p.intm_db_perm, p.intm_db_rowptr)
+        x = self.mul_scale(x, self.linear(qi.mlp_cbf, basis["cbf4"]), qi.scale_cbf.value())
+        return self.bilinear(qi.mlp_sbf, basis["rbf_W1_4"], basis["ylm"], x, p.id4_expand_abd, p.rowptr4,
+                             qi.scale_sbf_sum.value(), algo)
+
+    def interaction_block_fused(self, blk, h, m, basis, algo):
+        """InteractionBlock.forward (interaction_block.py:186-233 / 385-421) as 5 chain launches + the bilinear layers
+        + the edge->atom scatter."""
+        t, p, A = self.t, self.p, self.t.apply
+        ti = blk.trip_interaction
+        t.keep.append(m)
+        x4 = None
+        if not blk.triplets_only:
+            # the quadruplet branch fills the GPU; the triplet branch (small, latency-bound launches) hides next to it
+            x4 = t.on_side(lambda: self.quad_path_fused(blk.quad_interaction, m, basis, algo), lane=2)
+        r3 = self.linear(ti.mlp_rbf, basis["rbf3"])
+        x = A(fused.TripPrologue, m, r3, ti.dense_ba, ti.down_projection, ti.scale_rbf.value())
+        x3 = self.bilinear(ti.mlp_cbf, basis["rbf_W1_3"], basis["sph3"], x, p.id3_expand, p.rowptr3,
+                           ti.scale_cbf_sum.value(), algo)
+        if x4 is not None:
+            t.join(2)
+            t.keep.append(x4)
+        m2 = A(fused.Post, m, x3, x4, blk, p)
+        au = blk.atom_update
+        rh = self.linear(au.dense_rbf, basis["rbf_h"])
+        x0 = A(fused.EdgeToAtomLazy, m2, rh, p.id_a, p.atom_perm, p.atom_rowptr, au.scale_sum.value(), None)
+        h2, p_c, p_a = A(fused.AtomChain, x0, h, blk)
+        m3 = A(fused.EdgeEmb, m2, p_c, p_a, blk, p)
+        return h2, m3
+
+    def output_block_fused(self, blk, m, rbf_out, E_prev, F_prev):
+        """OutputBlock.forward (atom_update_block.py:157-193) accumulated onto the previous blocks' sums."""
+        p, A = self.p, self.t.apply
+        ro = self.linear(blk.dense_rbf, rbf_out)
+        if blk.direct_forces:
+            x_E, x_F = A(fused.EdgeToAtomLazy, m, ro, p.id_a, p.atom_perm, p.atom_rowptr, blk.scale_sum.value(),
+                         blk.scale_rbf.value())
+        else:
+            x_E = A(fused.EdgeToAtomLazy, m, ro, p.id_a, p.atom_perm, p.atom_rowptr, blk.scale_sum.value(), None)
+        E = A(fused.OutChain, x_E, E_prev, blk.seq_energy, blk.out_energy)
+        F = A(fused.OutChain, x_F, F_prev, blk.seq_forces, blk.out_forces) if blk.direct_forces else F_prev
+        return E, F
+
     def interaction_block(self, blk, h, m, basis, algo):
+        if self.fuse:
+            return self.interaction_block_fused(blk, h, m, basis, algo)
         self.t.keep.append(m)
         x_skip = self.t.on_side(lambda: self.dense(blk.dense_ca, m), lane=3)
         if blk.triplets_only:
@@ -319,6 +412,43 @@ class _Run:
             m2 = self.residual(layer, m2)
         m = self.add_scale(layers.INV_SQRT_2, m, m2)
         return h, m
+
+
+def fuse_ok(model):
+    """Can the dense stacks of this model run as chain programs (fused.py)?  Needs the published block structure
+    (>= 1 residual layer before / after the skip and in the atom MLPs, one concat residual, bias-free ScaledSiLU dense
+    layers with sizes that are multiples of 8 up to 128); anything else keeps the layer-by-layer kernels."""
+    cached = getattr(model, "_fuse_ok", None)
+    if cached is not None:
+        return cached
+    ok = True
+    try:
+        for blk in model.int_blocks:
+            paths = [blk.trip_interaction] + ([] if blk.triplets_only else [blk.quad_interaction])
+            nb, na = len(blk.layers_before_skip), len(blk.layers_after_skip)
+            ok &= nb >= 1 and na >= 1 and len(blk.residual_m) == 1 and len(blk.atom_update.layers) >= 2
+            ok &= 2 * len(paths) + 1 + 2 * (nb + na) <= chain.MAX_STEPS and 2 * len(blk.atom_update.layers) + 1 <= chain.MAX_STEPS
+            res = list(blk.layers_before_skip) + list(blk.layers_after_skip) + list(blk.residual_m) + list(blk.atom_update.layers)[1:]
+            ok &= all(fused.residual_ok(r) for r in res)
+            dense = [blk.dense_ca, blk.atom_update.layers[0]]
+            for pth in paths:
+                dense += [pth.down_projection, pth.up_projection_ca, pth.up_projection_ac,
+                          pth.dense_ba if hasattr(pth, "dense_ba") else pth.dense_db]
+            ok &= all(fused.dense_ok(d) for d in dense)
+            W = blk.concat_layer.dense.linear.weight
+            ok &= blk.concat_layer.dense.linear.bias is None and isinstance(blk.concat_layer.dense._activation, layers.ScaledSiLU)
+            A = blk.atom_update.layers[0].linear.weight.shape[0]
+            ok &= chain.supported(W.shape[0], A, W.shape[1] - 2 * A)
+        for ob in model.out_blocks:
+            heads = [ob.seq_energy] + ([ob.seq_forces] if ob.direct_forces else [])
+            for mlp in heads:
+                ok &= len(mlp) >= 2 and fused.dense_ok(mlp[0]) and all(fused.residual_ok(r) for r in list(mlp)[1:])
+                ok &= 2 * len(mlp) - 1 <= chain.MAX_STEPS
+            ok &= ob.out_energy.linear.bias is None and chain.supported(ob.out_energy.linear.weight.shape[1])
+    except AttributeError:
+        ok = False
+    model._fuse_ok = bool(ok)
+    return model._fuse_ok
 
 
 def side_stream(model):
@@ -392,12 +522,17 @@ def energy_and_forces(model, inputs):
         # The output blocks (mostly atom-level layers: a dozen CTAs per launch) only feed the final sums, so they run
         # on the side lane, next to the following interaction block — forward and backward.
         tape.keep.append(m)
-        E_a, F_ca = tape.on_side(lambda: run.output_block(model.out_blocks[0], m, rbf_out))
+        if run.fuse_out:
+            E_a, F_ca = tape.on_side(lambda: run.output_block_fused(model.out_blocks[0], m, rbf_out, None, None))
+        else:
+            E_a, F_ca = tape.on_side(lambda: run.output_block(model.out_blocks[0], m, rbf_out))
         for i in range(model.num_blocks):
             h, m = run.interaction_block(model.int_blocks[i], h, m, basis, model.bilinear_algo)
 
             def out_i(m=m, E_a=E_a, F_ca=F_ca, blk=model.out_blocks[i + 1]):
                 tape.keep.append(m)  # read on the side lane: must not be recycled by the main lane meanwhile
+                if run.fuse_out:
+                    return run.output_block_fused(blk, m, rbf_out, E_a, F_ca)
                 E, F = run.output_block(blk, m, rbf_out)
                 return run.add_scale(1.0, E_a, E), (F_ca + F if model.direct_forces else F_ca)
 

@@ -649,3 +649,49 @@ def gather_rows(x, idx, perm, rowptr):
     """x[idx] with a CSR (perm, rowptr = csr_by_key(idx, x.shape[0])) so that the backward is a deterministic
     segment sum instead of ATen's sort + atomics index_put (embedding_block.py:70-71, interaction_block.py:693)."""
     return _GatherRows.apply(x, idx, perm, rowptr)
+
+
+# ----------------------------------------------------------------------------- helpers of the fused engine (fused.py)
+def segment_sum_rows(src, perm, rowptr, n_rows):
+    """out[r,:] = sum_{k in [rowptr[r], rowptr[r+1])} src[perm[k],:] — the backward of a row gather, no atomics."""
+    src = _f32(src)
+    F = src.shape[1]
+    out = torch.empty(n_rows, F, dtype=torch.float32, device=src.device)
+    _check(_L().gemnet_segment_sum_rows(_p(src), _p(_i32(perm)), _p(_i32(rowptr)), n_rows, F, _p(out), _stream()),
+           "gemnet_segment_sum_rows")
+    return out
+
+
+def edge_to_atom_grad_r(m, id_a, g_out, s_out, g_had, s_had):
+    """g_r[e,:] = (s_out * g_out[id_a[e],:] + s_had * g_had[e,:]) * m[e,:]  — the rbf-side gradient of the edge->atom
+    aggregation (atom_update_block.py:64-68) on its own (the edge side stays lazy, fused.EdgeToAtomLazy)."""
+    m = _f32(m)
+    E, F = m.shape
+    g_r = torch.empty_like(m)
+    _check(_L().gemnet_edge_to_atom_bwd(_p(m), _p(m), _p(_i32(id_a)), E, F, float(s_out), _p(_f32(g_out)),
+                                        float(s_had), _p(_f32(g_had)), None, _p(g_r), _stream()),
+           "gemnet_edge_to_atom_bwd")
+    return g_r
+
+
+def materialize_term(g, idx, mul, scale):
+    """scale * g[idx] * mul as a tensor (idx / mul optional): a lazy gradient summand for a consumer that is not a
+    fused chain."""
+    g = _f32(g)
+    if idx is not None and mul is not None:
+        mul = _f32(mul)
+        out = torch.empty_like(mul)
+        _check(_L().gemnet_edge_to_atom_bwd(_p(mul), _p(mul), _p(_i32(idx)), mul.shape[0], mul.shape[1], float(scale),
+                                            _p(g), 0.0, None, _p(out), None, _stream()), "gemnet_edge_to_atom_bwd")
+        return out
+    if mul is not None:
+        mul = _f32(mul)
+        out = torch.empty_like(mul)
+        _check(_L().gemnet_mul_scale_fwd(_p(g), _p(mul), float(scale), _n4(g), _p(out), _stream()), "gemnet_mul_scale_fwd")
+        return out
+    if idx is not None:
+        n, F = idx.numel(), g.shape[1]
+        out = torch.empty(n, F, dtype=torch.float32, device=g.device)
+        _check(_L().gemnet_gather_rows(_p(g), _p(_i32(idx)), n, F, _p(out), _stream()), "gemnet_gather_rows")
+        return out if scale == 1.0 else lincomb([(out, scale)])
+    return g if scale == 1.0 else lincomb([(g, scale)])

@@ -247,6 +247,91 @@ int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int
                     int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N1 (chain fusion): a whole stack of dense layers with the pointwise work between them in ONE kernel —
+ * ResidualLayer (base_layers.py:61-89), the dense_ba -> Hadamard -> down_projection prologue and the
+ * up_projection / skip / residual tail of TripletInteraction / QuadrupletInteraction / InteractionBlock
+ * (interaction_block.py:186-233, 385-421, 517-566, 653-696), the atom MLPs of AtomUpdateBlock / OutputBlock
+ * (atom_update_block.py:55-72, 157-193), EdgeEmbedding without the concat (embedding_block.py:70-74) — and the
+ * input-gradient of each of them (forces are -dE/dR, gemnet.py:598-613).
+ *
+ * A 128-row tile of the activation stays on chip for the whole chain: the operand lives in shared memory as an
+ * exact three-way bf16 split (gemnet_dense_tc's numerics), the accumulators in TMEM, a skip-connection value
+ * ("carry") in registers; only what the backward pass needs (activation derivatives) and the chain's outputs go to
+ * HBM.  The chain is described by a small program of up to GEMNET_CHAIN_MAX_STEPS steps; every step is
+ *
+ *   1. (optional) operand fill   v[r,:] = sum_t scale_t * src_t[idx_t ? idx_t[r] : r, :] (* mul_t[r,:])   t < n_terms
+ *                                (kind 1: v[r,c] = scale * src[r] * mul[c], an outer product: the N=1 output layer's
+ *                                backward); carry = v if load_set_carry; A = split3(v * amul) (K columns)
+ *   2. GEMM                      acc = A @ B^T, B = packed (N x K) image of gemnet_dense_pack_weight
+ *   3. epilogue (per element)    z = acc + pre0[pre0_idx ? pre0_idx[r] : r, c] + pre1[...]
+ *                                v = act ? silu(z)/0.6 : z ;  d = act ? d/dz : 1
+ *                                mul_early:  aux = v*s_acc (if aux) ; v *= mul_early ; d *= mul_early
+ *                                v = v*s_acc + carry*s_carry + post0*s_post0 + post1*s_post1 ;  d *= s_acc
+ *                                mul_late:   v *= mul_late
+ *                                dact = d ; out[out_idx ? out_idx[r] : r] = v * s_store (* smul) ; carry = v * s_set_carry
+ *                                next operand: A = split3(v * s_a * next_amul)   (GEMNET_CHAIN_TO_A)
+ *                                           or A = split3(carry * s_a * next_amul) (GEMNET_CHAIN_A_FROM_CARRY)
+ *                                dot:        dot_out[r] = sum_c v[r,c] * dot_w[c] (+ dot_in[r])   (N = 1 output layer)
+ * All tensors are fp32 row-major with row stride = their logical width (K for operand-side tensors, N for
+ * epilogue-side tensors); K, N multiples of 8 in [8, 128]; pointers 16-byte aligned.  The first step of a program must
+ * have n_terms > 0; a later step with n_terms == 0 uses the operand its predecessor left (TO_A / A_FROM_CARRY, or
+ * the unchanged operand).  flags of gemnet_chain_tc: GEMNET_DENSE_WEIGHTS_SETTLED as for gemnet_dense_tc.
+ * ---------------------------------------------------------------------------------------------- */
+#define GEMNET_CHAIN_MAX_STEPS 12
+#define GEMNET_CHAIN_MAX_TERMS 3
+#define GEMNET_CHAIN_ACT 1          /* ScaledSiLU */
+#define GEMNET_CHAIN_CARRY_ADD 2    /* v += carry * s_carry */
+#define GEMNET_CHAIN_SET_CARRY 4    /* carry = v * s_set_carry */
+#define GEMNET_CHAIN_TO_A 8         /* next operand from v */
+#define GEMNET_CHAIN_A_FROM_CARRY 16 /* next operand from carry */
+
+typedef struct {
+  const float* src;
+  const int32_t* idx;
+  const float* mul;
+  float scale;
+  int32_t kind; /* 0 rows, 1 outer product */
+} gemnet_chain_term;
+
+typedef struct {
+  int32_t n_terms;
+  int32_t load_set_carry;
+  gemnet_chain_term term[GEMNET_CHAIN_MAX_TERMS];
+  const float* amul;
+  const void* Wp;
+  int32_t K, N;
+  int32_t flags;
+  int32_t reserved;
+  const float* pre0;
+  const int32_t* pre0_idx;
+  const float* pre1;
+  const int32_t* pre1_idx;
+  const float* mul_early;
+  const float* mul_late;
+  const float* post0;
+  const float* post1;
+  float s_acc, s_carry, s_post0, s_post1, s_store, s_set_carry, s_a, s_pad;
+  float* aux;
+  float* dact;
+  float* out;
+  const float* smul;
+  const int32_t* out_idx;
+  const float* next_amul;
+  const float* dot_w;
+  float* dot_out;
+  const float* dot_in;
+} gemnet_chain_step;
+
+typedef struct {
+  int64_t M;
+  int32_t n_steps;
+  int32_t reserved;
+  gemnet_chain_step step[GEMNET_CHAIN_MAX_STEPS];
+} gemnet_chain_program;
+
+int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * H0  host index builder: DataContainer.__getitem__ / get_triplets / get_quadruplets
  *     (gemnet/training/data_container.py:156-408, 411-489).  HOST function, native C++.
  * Input: molecules concatenated, R_host float64 (n_atoms,3), n_per_mol int32[n_mol].
