@@ -33,6 +33,8 @@ _SIGNATURES = {
     "gemnet_downproj_fwd": [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P],
     "gemnet_downproj_bwd": [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P],
     "gemnet_segbilinear_workspace_bytes": [_I64, _I32, _I32, _I32, _I32, _I32, _I32],
+    "gemnet_segbilinear_pack_bytes": [_I32, _I32, _I32, _I32, _I32],
+    "gemnet_segbilinear_pack": [_P, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "gemnet_segbilinear_fwd": [_P, _P, _P, _P, _P, _P, _F, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P],
     "gemnet_segbilinear_bwd": [_P, _P, _P, _P, _P, _P, _F, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P,
                                _P, _P, _P, _P],
@@ -54,6 +56,7 @@ _SIGNATURES = {
     "gemnet_dense_pack_weight": [_P, _I64, _I64, _I32, _I32, _P, _P],
     "gemnet_dense_tc": [_P, _P, _I64, _I32, _I32, _P, _I32, _I32, _F, _P, _F, _P, _P, _I32, _P],
     "gemnet_chain_tc": [_P, _I32, _P],
+    "gemnet_chain_set_profile_buffer": [_P],
     "gemnet_graph_build_host": [_P, _P, _I64, _D, _D, _I32, ctypes.POINTER(_P)],
     "gemnet_graph_size": [_P, ctypes.c_char_p],
     "gemnet_graph_copy_host": [_P, ctypes.c_char_p, _P],
@@ -64,9 +67,11 @@ _SIGNATURES = {
 _RESTYPES = {
     "gemnet_last_error": ctypes.c_char_p,
     "gemnet_segbilinear_workspace_bytes": _I64,
+    "gemnet_segbilinear_pack_bytes": _I64,
     "gemnet_dense_pack_floats": _I64,
     "gemnet_graph_size": _I64,
     "gemnet_graph_free": None,
+    "gemnet_chain_set_profile_buffer": None,
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -8,7 +8,8 @@
 //                  the next layer's weights arrive while the current layer's epilogue runs
 //   accumulators   TMEM: one main accumulator per K chunk + one correction accumulator (dense_tc.cu's numerics:
 //                  six significant products, the toward-zero rounding of the accumulator compensated)
-//   skip value     "carry": 32 registers per worker thread (its row x 32-column patch)
+//   skip value     "carry": the last 128 TMEM columns (tcgen05.st / tcgen05.ld of the thread's row x 32-column patch):
+//                  it costs no registers and no shared memory
 //
 // 512 threads (16 warps: 128 registers per thread), one CTA per SM, persistent over row tiles.  Every thread is a
 // worker: operand fill from global memory (coalesced; gathers and several summed terms allowed) and the epilogue of
@@ -19,6 +20,8 @@
 // has completed (mbarrier acc_full), the cp.async.bulk of the NEXT GEMM's packed weight image into the two chunk
 // slots — the weights stream in while the epilogue runs.  The step program is a kernel parameter (__grid_constant__).
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -38,7 +41,7 @@ constexpr int THREADS = 512;
 constexpr int MISC_BYTES = 1024;               // barriers, TMEM slot, dot buffer
 constexpr int SMEM_BYTES = 1024 + A_BYTES + W_SLOTS * WSLOT_BYTES + MISC_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t ACC_STRIDE = 128, CORR_COL = 256;
+constexpr uint32_t ACC_STRIDE = 128, CORR_COL = 256, CARRY_COL = 384;
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // coherent load: for tensors that an earlier step of the SAME kernel (the same thread) may have written
@@ -66,7 +69,8 @@ __device__ __forceinline__ void load_granule(const uint8_t* A, int row, int g, f
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, int weights_settled) {
+chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, int weights_settled,
+                long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -81,6 +85,12 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   float* dotbuf = reinterpret_cast<float*>(sm + A_BYTES + W_SLOTS * WSLOT_BYTES + 64);  // 128 floats
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // diagnostics (gemnet_chain_set_profile_buffer): thread 0 of CTA 0 records clock64() at the phase boundaries
+  int prof_n = 0;
+  auto stamp = [&]() {
+    if (prof != nullptr && blockIdx.x == 0 && tid == 0 && prof_n < 250) prof[prof_n++] = clock64();
+  };
+  stamp();
   const int64_t M = prog.M;
   const int n_steps = prog.n_steps;
 
@@ -97,6 +107,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  stamp();  // 1: prologue done
 
   // weight image of one GEMM -> the chunk slots (thread 0 only; the slots are free: every MMA that read them is done)
   auto fetch_weights = [&](const gemnet_chain_step& st) {
@@ -113,31 +124,50 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
     fetch_weights(prog.step[0]);
   }
   griddep_wait();
+  stamp();  // 2: predecessor complete
 
   const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (rows 32q..32q+31), column group
   const int row = q * 32 + lane;                // epilogue row of this thread inside the tile
-  float carry[32];
+  // carry: 16 columns of this thread's row at TMEM column CARRY_COL + col
+  auto carry_ld = [&](int col, float (&c)[16]) {
+    uint32_t raw[16];
+    tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + CARRY_COL + (uint32_t)col, raw);
+    tmem_wait_ld();
 #pragma unroll
-  for (int j = 0; j < 32; ++j) carry[j] = 0.f;
+    for (int j = 0; j < 16; ++j) c[j] = __uint_as_float(raw[j]);
+  };
+  auto carry_st = [&](int col, const float (&c)[16]) {
+    uint32_t raw[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) raw[j] = __float_as_uint(c[j]);
+    tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + CARRY_COL + (uint32_t)col, raw);
+  };
   uint32_t gemm = 0;                            // GEMMs issued by this CTA (parity of acc_full)
   uint32_t wuse0 = 0, wuse1 = 0;                // fills of weight slot 0 / 1 consumed so far (thread 0)
 
-  // the thread's epilogue patch of the NEXT operand (width W = Kpad / 4 columns starting at W * cg) from vals[]
-  auto write_patch = [&](const float (&vals)[32], int Knext, float s_a, const float* amul, int64_t r, bool rv) {
+  // the thread's epilogue patch of the NEXT operand (width W = Kpad / 4 columns starting at W * cg) from the carry
+  auto patch_from_carry = [&](int Knext, float s_a, const float* amul, int64_t rcl, bool rv) {
     const int Wd = Knext > 64 ? 32 : 16;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (u * 8 >= Wd) break;
-      const int col = Wd * cg + u * 8;
-      float v[8];
+    for (int h = 0; h < 2; ++h) {
+      if (h * 16 >= Wd) break;
+      float c[16];
+      carry_ld(Wd * cg + h * 16, c);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (rv && col < Knext) ? vals[u * 8 + j] * s_a : 0.f;
-      if (amul && rv && col < Knext) {
-        const float4 m0 = ldg4(amul + r * Knext + col), m1 = ldg4(amul + r * Knext + col + 4);
-        v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w;
-        v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+      for (int g2 = 0; g2 < 2; ++g2) {
+        const int col = Wd * cg + h * 16 + g2 * 8;
+        const bool gv = rv && col < Knext;
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = gv ? c[g2 * 8 + j] * s_a : 0.f;
+        if (amul) {
+          const int cn = min(col, Knext - 8);
+          const float4 m0 = ldg4(amul + rcl * Knext + cn), m1 = ldg4(amul + rcl * Knext + cn + 4);
+          w[0] *= m0.x; w[1] *= m0.y; w[2] *= m0.z; w[3] *= m0.w;
+          w[4] *= m1.x; w[5] *= m1.y; w[6] *= m1.z; w[7] *= m1.w;
+        }
+        store_granule(A, row, col >> 3, w);
       }
-      store_granule(A, row, col >> 3, v);
     }
   };
 
@@ -154,79 +184,111 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       if (st.n_terms > 0) {
         const int gpr = 8 * NKB;                                   // granules (8 columns) per operand row
         const bool fold_amul = st.amul != nullptr && !st.load_set_carry;
+        // PG (row, granule) pieces per thread and pass: all loads of a pass are in flight together.  The common fill
+        // (one plain or gathered term) takes its 4 pieces in ONE pass; fills with Hadamard factors or several terms
+        // take 2 per pass (registers).
+        auto fill = [&](auto pg_tag) {
+          constexpr int PG = decltype(pg_tag)::value;
 #pragma unroll 1
-        for (int p0 = tid; p0 < TM * gpr; p0 += 2 * THREADS) {     // two (row, granule) pieces per thread and pass
-          float v[2][8];
-          int prow[2], pg[2];
+          for (int p0 = tid; p0 < TM * gpr; p0 += PG * THREADS) {
+            float v[PG][8];
+            int prow[PG], pgr[PG];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int p = p0 + h * THREADS;
-            prow[h] = p / gpr;
-            pg[h] = p % gpr;
+            for (int h = 0; h < PG; ++h) {
+              const int p = p0 + h * THREADS;
+              prow[h] = p / gpr;
+              pgr[h] = p % gpr;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[h][j] = 0.f;
-          }
-          for (int t = 0; t < st.n_terms; ++t) {
-            const gemnet_chain_term& tm = st.term[t];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int64_t rr = r0 + prow[h];
-              const int col = pg[h] * 8;
-              if (rr >= M || col >= K) continue;
+              for (int j = 0; j < 8; ++j) v[h][j] = 0.f;
+            }
+            for (int t = 0; t < st.n_terms; ++t) {
+              const gemnet_chain_term& tm = st.term[t];
+              float4 a0[PG], a1[PG];
               if (tm.kind == 0) {
-                const int64_t sr = tm.idx ? (int64_t)__ldg(tm.idx + rr) : rr;
-                float4 a0 = ldg4(tm.src + sr * K + col), a1 = ldg4(tm.src + sr * K + col + 4);
-                if (tm.mul) {
-                  const float4 m0 = ldg4(tm.mul + rr * K + col), m1 = ldg4(tm.mul + rr * K + col + 4);
-                  a0.x *= m0.x; a0.y *= m0.y; a0.z *= m0.z; a0.w *= m0.w;
-                  a1.x *= m1.x; a1.y *= m1.y; a1.z *= m1.z; a1.w *= m1.w;
+#pragma unroll
+                for (int h = 0; h < PG; ++h) {
+                  // out-of-range pieces read a clamped (valid) address and are zeroed below: no divergent branches
+                  const int64_t rr = min(r0 + prow[h], M - 1);
+                  const int col = min(pgr[h] * 8, K - 8);
+                  const int64_t sr = tm.idx ? (int64_t)__ldg(tm.idx + rr) : rr;
+                  a0[h] = ldg4(tm.src + sr * K + col);
+                  a1[h] = ldg4(tm.src + sr * K + col + 4);
                 }
-                v[h][0] = fmaf(tm.scale, a0.x, v[h][0]); v[h][1] = fmaf(tm.scale, a0.y, v[h][1]);
-                v[h][2] = fmaf(tm.scale, a0.z, v[h][2]); v[h][3] = fmaf(tm.scale, a0.w, v[h][3]);
-                v[h][4] = fmaf(tm.scale, a1.x, v[h][4]); v[h][5] = fmaf(tm.scale, a1.y, v[h][5]);
-                v[h][6] = fmaf(tm.scale, a1.z, v[h][6]); v[h][7] = fmaf(tm.scale, a1.w, v[h][7]);
+                if (tm.mul) {
+#pragma unroll
+                  for (int h = 0; h < PG; ++h) {
+                    const int64_t rr = min(r0 + prow[h], M - 1);
+                    const int col = min(pgr[h] * 8, K - 8);
+                    const float4 m0 = ldg4(tm.mul + rr * K + col), m1 = ldg4(tm.mul + rr * K + col + 4);
+                    a0[h].x *= m0.x; a0[h].y *= m0.y; a0[h].z *= m0.z; a0[h].w *= m0.w;
+                    a1[h].x *= m1.x; a1[h].y *= m1.y; a1[h].z *= m1.z; a1[h].w *= m1.w;
+                  }
+                }
               } else {  // outer product src[row] * mul[col]
-                const float a = __ldg(tm.src + rr) * tm.scale;
-                const float4 m0 = ldg4(tm.mul + col), m1 = ldg4(tm.mul + col + 4);
-                v[h][0] = fmaf(a, m0.x, v[h][0]); v[h][1] = fmaf(a, m0.y, v[h][1]);
-                v[h][2] = fmaf(a, m0.z, v[h][2]); v[h][3] = fmaf(a, m0.w, v[h][3]);
-                v[h][4] = fmaf(a, m1.x, v[h][4]); v[h][5] = fmaf(a, m1.y, v[h][5]);
-                v[h][6] = fmaf(a, m1.z, v[h][6]); v[h][7] = fmaf(a, m1.w, v[h][7]);
+#pragma unroll
+                for (int h = 0; h < PG; ++h) {
+                  const int64_t rr = min(r0 + prow[h], M - 1);
+                  const int col = min(pgr[h] * 8, K - 8);
+                  const float a = __ldg(tm.src + rr);
+                  const float4 m0 = ldg4(tm.mul + col), m1 = ldg4(tm.mul + col + 4);
+                  a0[h] = make_float4(a * m0.x, a * m0.y, a * m0.z, a * m0.w);
+                  a1[h] = make_float4(a * m1.x, a * m1.y, a * m1.z, a * m1.w);
+                }
+              }
+              const float sc = tm.scale;
+#pragma unroll
+              for (int h = 0; h < PG; ++h) {
+                v[h][0] = fmaf(sc, a0[h].x, v[h][0]); v[h][1] = fmaf(sc, a0[h].y, v[h][1]);
+                v[h][2] = fmaf(sc, a0[h].z, v[h][2]); v[h][3] = fmaf(sc, a0[h].w, v[h][3]);
+                v[h][4] = fmaf(sc, a1[h].x, v[h][4]); v[h][5] = fmaf(sc, a1[h].y, v[h][5]);
+                v[h][6] = fmaf(sc, a1[h].z, v[h][6]); v[h][7] = fmaf(sc, a1[h].w, v[h][7]);
               }
             }
-          }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int64_t rr = r0 + prow[h];
-            const int col = pg[h] * 8;
-            if (fold_amul && rr < M && col < K) {
-              const float4 m0 = ldg4(st.amul + rr * K + col), m1 = ldg4(st.amul + rr * K + col + 4);
-              v[h][0] *= m0.x; v[h][1] *= m0.y; v[h][2] *= m0.z; v[h][3] *= m0.w;
-              v[h][4] *= m1.x; v[h][5] *= m1.y; v[h][6] *= m1.z; v[h][7] *= m1.w;
+            for (int h = 0; h < PG; ++h) {
+              if (fold_amul) {
+                const int64_t rr = min(r0 + prow[h], M - 1);
+                const int col = min(pgr[h] * 8, K - 8);
+                const float4 m0 = ldg4(st.amul + rr * K + col), m1 = ldg4(st.amul + rr * K + col + 4);
+                v[h][0] *= m0.x; v[h][1] *= m0.y; v[h][2] *= m0.z; v[h][3] *= m0.w;
+                v[h][4] *= m1.x; v[h][5] *= m1.y; v[h][6] *= m1.z; v[h][7] *= m1.w;
+              }
+              const bool valid = r0 + prow[h] < M && pgr[h] * 8 < K;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[h][j] = valid ? v[h][j] : 0.f;
+              store_granule(A, prow[h], pgr[h], v[h]);
             }
-            store_granule(A, prow[h], pg[h], v[h]);
           }
-        }
+        };
+        const bool simple = st.n_terms == 1 && st.term[0].mul == nullptr && !fold_amul && NKB == 2;
+        if (simple) fill(std::integral_constant<int, 4>{});
+        else fill(std::integral_constant<int, 2>{});
         if (st.load_set_carry) {
           // the skip value is wanted in the epilogue's thread mapping: read it back from the (exact) operand split
           __syncthreads();
           const int Wd = K > 64 ? 32 : 16;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (u * 8 >= Wd) break;
-            float v[8];
-            load_granule(A, row, (Wd * cg + u * 8) >> 3, v);
+          for (int h = 0; h < 2; ++h) {
+            if (h * 16 >= Wd) break;
+            float c[16], lo[8], hi[8];
+            load_granule(A, row, (Wd * cg + h * 16) >> 3, lo);
+            load_granule(A, row, ((Wd * cg + h * 16) >> 3) + 1, hi);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) carry[u * 8 + j] = v[j];
+            for (int j = 0; j < 8; ++j) {
+              c[j] = lo[j];
+              c[8 + j] = hi[j];
+            }
+            carry_st(Wd * cg + h * 16, c);
           }
-          if (st.amul) write_patch(carry, K, 1.0f, st.amul, r, rv);
+          if (st.amul) patch_from_carry(K, 1.0f, st.amul, rv ? r : M - 1, rv);
         }
       }
-
+      stamp();  // step: operand written by this thread
       // ------------------------------------------------------------------ GEMM: operand complete -> thread 0 issues
       fence_proxy_async();   // generic-proxy writes of A -> visible to the tensor-core (async) proxy
       tc_fence_before();     // this thread's tcgen05.ld of the previous accumulators are done
       __syncthreads();
+      stamp();  // step: all threads' operand parts visible
       if (tid == 0) {
         tc_fence_after();
         const int Npad = N > 64 ? 128 : 64;
@@ -236,6 +298,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
           uint32_t& use = kb ? wuse1 : wuse0;
           mbar_wait(w_full(kb), use & 1u);
           ++use;
+          stamp();  // step: weight chunk kb resident
           tc_fence_after();
           const uint32_t sa = a_base + kb * CHUNK_BYTES;
           const uint64_t a_h = make_desc(sa), a_m = make_desc(sa + SPLIT_BYTES), a_l = make_desc(sa + 2 * SPLIT_BYTES);
@@ -254,9 +317,11 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
           }
         }
         umma_commit(acc_full);
+        stamp();  // step: MMAs issued
       }
       __syncwarp();
       mbar_wait(acc_full, gemm & 1u);
+      stamp();  // step: accumulators complete
       ++gemm;
       tc_fence_after();
       const bool last = s + 1 == n_steps;
@@ -271,19 +336,28 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       const int Knext = last ? 0 : prog.step[s + 1].K;
       const float c0f = kShrinkPerStep * (float)min(4, (K + 15) / 16);
       const float c1f = kShrinkPerStep * (float)max(0, min(4, (K - 64 + 15) / 16));
-      const int64_t pr0 = (st.pre0 && rv) ? (st.pre0_idx ? (int64_t)__ldg(st.pre0_idx + r) : r) : 0;
-      const int64_t pr1 = (st.pre1 && rv) ? (st.pre1_idx ? (int64_t)__ldg(st.pre1_idx + r) : r) : 0;
-      const int64_t orow = (st.out && rv) ? (st.out_idx ? (int64_t)__ldg(st.out_idx + r) : r) : 0;
+      const int64_t rc = rv ? r : M - 1;   // loads of rows past the end read the last row (and are discarded)
+      const float* const pre0 = st.pre0; const float* const pre1 = st.pre1;
+      const float* const mul_early = st.mul_early; const float* const mul_late = st.mul_late;
+      const float* const post0 = st.post0; const float* const post1 = st.post1;
+      const float s_acc = st.s_acc, s_carry = st.s_carry;
+      const int64_t pr0 = pre0 ? (st.pre0_idx ? (int64_t)__ldg(st.pre0_idx + rc) : rc) : 0;
+      const int64_t pr1 = pre1 ? (st.pre1_idx ? (int64_t)__ldg(st.pre1_idx + rc) : rc) : 0;
+      const int64_t orow = st.out ? (st.out_idx ? (int64_t)__ldg(st.out_idx + rc) : rc) : 0;
       float dot = 0.f;
       if (st.dot_w) {
         if (cg == 0) dotbuf[row] = 0.f;
         __syncthreads();
       }
+      const bool need_d = st.dact != nullptr;
 #pragma unroll
       for (int piece = 0; piece < 2; ++piece) {
         if (piece * 16 >= Wd) break;
+        // The pointwise program runs STAGE BY STAGE over the 16 values of the piece (feature tests outside the element
+        // loops): 16 independent dependency chains per stage keep the FMA / MUFU pipes busy with only 4 warps per
+        // scheduler, and a disabled feature costs one uniform branch instead of one per float4.
         const int c0 = Wd * cg + piece * 16;            // first column of this 16-column piece
-        float z[16];
+        float v[16], d[16];
         {
           uint32_t a0[16], a1[16], cc[16];
           const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -301,106 +375,147 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
               corr = fmaf(__uint_as_float(a1[j]), c1f, corr);
               mainv += __uint_as_float(a1[j]);
             }
-            z[j] = mainv + corr;
+            v[j] = mainv + corr;
           }
         }
-        const bool cv = rv && c0 < N;
+        bool ok[4];
+        int cl[4];                                      // clamped column for loads (N is a multiple of 8)
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-          const int col = c0 + 4 * f;
-          const bool ok = cv && col < N;               // N is a multiple of 8: a float4 is never split
-          float v[4], d[4];
+          ok[f] = rv && c0 + 4 * f < N;
+          cl[f] = min(c0 + 4 * f, N - 4);
+        }
+        if (pre0) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = z[4 * f + u];
-          if (ok && st.pre0) {
-            const float4 t = ld4(st.pre0 + pr0 * N + col);
-            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+          for (int f = 0; f < 4; ++f) {
+            const float4 t = ld4(pre0 + pr0 * N + cl[f]);
+            v[4 * f] += t.x; v[4 * f + 1] += t.y; v[4 * f + 2] += t.z; v[4 * f + 3] += t.w;
           }
-          if (ok && st.pre1) {
-            const float4 t = ld4(st.pre1 + pr1 * N + col);
-            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-          }
-          if (flags & GEMNET_CHAIN_ACT) {
+        }
+        if (pre1) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) scaled_silu(v[u], v[u], d[u]);
+          for (int f = 0; f < 4; ++f) {
+            const float4 t = ld4(pre1 + pr1 * N + cl[f]);
+            v[4 * f] += t.x; v[4 * f + 1] += t.y; v[4 * f + 2] += t.z; v[4 * f + 3] += t.w;
+          }
+        }
+        if (flags & GEMNET_CHAIN_ACT) {
+          if (need_d) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) scaled_silu(v[j], v[j], d[j]);
           } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) d[u] = 1.f;
+            for (int j = 0; j < 16; ++j) v[j] = scaled_silu_value(v[j]);
           }
-          if (st.mul_early) {
-            float4 t = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (ok) t = ldg4(st.mul_early + r * N + col);
-            if (ok && st.aux)
-              *reinterpret_cast<float4*>(st.aux + r * N + col) =
-                  make_float4(v[0] * st.s_acc, v[1] * st.s_acc, v[2] * st.s_acc, v[3] * st.s_acc);
-            v[0] *= t.x; v[1] *= t.y; v[2] *= t.z; v[3] *= t.w;
-            d[0] *= t.x; d[1] *= t.y; d[2] *= t.z; d[3] *= t.w;
-          }
+        } else if (need_d) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            v[u] *= st.s_acc;
-            d[u] *= st.s_acc;
-          }
-          if (flags & GEMNET_CHAIN_CARRY_ADD) {
+          for (int j = 0; j < 16; ++j) d[j] = 1.f;
+        }
+        if (mul_early) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = fmaf(carry[piece * 16 + 4 * f + u], st.s_carry, v[u]);
+          for (int f = 0; f < 4; ++f) {
+            const float4 t = ldg4(mul_early + rc * N + cl[f]);
+            if (st.aux && ok[f])
+              *reinterpret_cast<float4*>(st.aux + r * N + c0 + 4 * f) =
+                  make_float4(v[4 * f] * s_acc, v[4 * f + 1] * s_acc, v[4 * f + 2] * s_acc, v[4 * f + 3] * s_acc);
+            v[4 * f] *= t.x; v[4 * f + 1] *= t.y; v[4 * f + 2] *= t.z; v[4 * f + 3] *= t.w;
+            if (need_d) {
+              d[4 * f] *= t.x; d[4 * f + 1] *= t.y; d[4 * f + 2] *= t.z; d[4 * f + 3] *= t.w;
+            }
           }
-          if (ok && st.post0) {
-            const float4 t = ld4(st.post0 + r * N + col);
-            v[0] = fmaf(t.x, st.s_post0, v[0]); v[1] = fmaf(t.y, st.s_post0, v[1]);
-            v[2] = fmaf(t.z, st.s_post0, v[2]); v[3] = fmaf(t.w, st.s_post0, v[3]);
-          }
-          if (ok && st.post1) {
-            const float4 t = ld4(st.post1 + r * N + col);
-            v[0] = fmaf(t.x, st.s_post1, v[0]); v[1] = fmaf(t.y, st.s_post1, v[1]);
-            v[2] = fmaf(t.z, st.s_post1, v[2]); v[3] = fmaf(t.w, st.s_post1, v[3]);
-          }
-          if (ok && st.mul_late) {
-            const float4 t = ldg4(st.mul_late + r * N + col);
-            v[0] *= t.x; v[1] *= t.y; v[2] *= t.z; v[3] *= t.w;
-          }
-          if (!ok) {
+        }
+        if (need_d) {  // stored here: the derivative's registers are free for the rest of the program
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = 0.f;
+          for (int f = 0; f < 4; ++f)
+            if (ok[f])
+              *reinterpret_cast<float4*>(st.dact + r * N + c0 + 4 * f) =
+                  make_float4(d[4 * f] * s_acc, d[4 * f + 1] * s_acc, d[4 * f + 2] * s_acc, d[4 * f + 3] * s_acc);
+        }
+        if (flags & GEMNET_CHAIN_CARRY_ADD) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= s_acc;
+          float c[16];
+          carry_ld(c0, c);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(c[j], s_carry, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= s_acc;
+        }
+        if (post0) {
+          const float sp = st.s_post0;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const float4 t = ld4(post0 + rc * N + cl[f]);
+            v[4 * f] = fmaf(t.x, sp, v[4 * f]); v[4 * f + 1] = fmaf(t.y, sp, v[4 * f + 1]);
+            v[4 * f + 2] = fmaf(t.z, sp, v[4 * f + 2]); v[4 * f + 3] = fmaf(t.w, sp, v[4 * f + 3]);
           }
-          if (ok && st.dact) *reinterpret_cast<float4*>(st.dact + r * N + col) = make_float4(d[0], d[1], d[2], d[3]);
-          if (ok && st.out) {
-            float4 o = make_float4(v[0] * st.s_store, v[1] * st.s_store, v[2] * st.s_store, v[3] * st.s_store);
+        }
+        if (post1) {
+          const float sp = st.s_post1;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const float4 t = ld4(post1 + rc * N + cl[f]);
+            v[4 * f] = fmaf(t.x, sp, v[4 * f]); v[4 * f + 1] = fmaf(t.y, sp, v[4 * f + 1]);
+            v[4 * f + 2] = fmaf(t.z, sp, v[4 * f + 2]); v[4 * f + 3] = fmaf(t.w, sp, v[4 * f + 3]);
+          }
+        }
+        if (mul_late) {
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const float4 t = ldg4(mul_late + rc * N + cl[f]);
+            v[4 * f] *= t.x; v[4 * f + 1] *= t.y; v[4 * f + 2] *= t.z; v[4 * f + 3] *= t.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = ok[j >> 2] ? v[j] : 0.f;
+        if (st.out) {
+          const float ss = st.s_store;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            float4 o = make_float4(v[4 * f] * ss, v[4 * f + 1] * ss, v[4 * f + 2] * ss, v[4 * f + 3] * ss);
             if (st.smul) {
-              const float4 t = ldg4(st.smul + r * N + col);
+              const float4 t = ldg4(st.smul + rc * N + cl[f]);
               o.x *= t.x; o.y *= t.y; o.z *= t.z; o.w *= t.w;
             }
-            *reinterpret_cast<float4*>(st.out + orow * N + col) = o;
+            if (ok[f]) *reinterpret_cast<float4*>(st.out + orow * N + c0 + 4 * f) = o;
           }
-          if (ok && st.dot_w) {
-            const float4 t = ldg4(st.dot_w + col);
-            dot = fmaf(v[0], t.x, fmaf(v[1], t.y, fmaf(v[2], t.z, fmaf(v[3], t.w, dot))));
-          }
+        }
+        if (st.dot_w) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) z[4 * f + u] = v[u];   // final values of the piece (for the next operand)
-          if (flags & GEMNET_CHAIN_SET_CARRY) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) carry[piece * 16 + 4 * f + u] = v[u] * st.s_set_carry;
+          for (int f = 0; f < 4; ++f) {
+            const float4 t = ldg4(st.dot_w + cl[f]);
+            dot = fmaf(v[4 * f], t.x, fmaf(v[4 * f + 1], t.y, fmaf(v[4 * f + 2], t.z, fmaf(v[4 * f + 3], t.w, dot))));
           }
+        }
+        if (flags & GEMNET_CHAIN_SET_CARRY) {
+          const float sc = st.s_set_carry;
+          float c[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) c[j] = v[j] * sc;
+          carry_st(c0, c);
         }
         if ((flags & GEMNET_CHAIN_TO_A) && !last) {
           // two granules of the next operand; its width equals this step's (Kpad_next == Npad)
 #pragma unroll
           for (int g2 = 0; g2 < 2; ++g2) {
             const int col = c0 + 8 * g2;
-            float v[8];
+            const bool gv = rv && col < Knext;
+            float w[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (rv && col < Knext) ? z[8 * g2 + j] * st.s_a : 0.f;
-            if (st.next_amul && rv && col < Knext) {
-              const float4 m0 = ldg4(st.next_amul + r * Knext + col), m1 = ldg4(st.next_amul + r * Knext + col + 4);
-              v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w;
-              v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+            for (int j = 0; j < 8; ++j) w[j] = gv ? v[8 * g2 + j] * st.s_a : 0.f;
+            if (st.next_amul) {
+              const int cn = min(col, Knext - 8);
+              const float4 m0 = ldg4(st.next_amul + rc * Knext + cn), m1 = ldg4(st.next_amul + rc * Knext + cn + 4);
+              w[0] *= m0.x; w[1] *= m0.y; w[2] *= m0.z; w[3] *= m0.w;
+              w[4] *= m1.x; w[5] *= m1.y; w[6] *= m1.z; w[7] *= m1.w;
             }
-            store_granule(A, row, col >> 3, v);
+            store_granule(A, row, col >> 3, w);
           }
         }
       }
-      if ((flags & GEMNET_CHAIN_A_FROM_CARRY) && !last) write_patch(carry, Knext, st.s_a, st.next_amul, r, rv);
+      if ((flags & GEMNET_CHAIN_A_FROM_CARRY) && !last) patch_from_carry(Knext, st.s_a, st.next_amul, rc, rv);
+      stamp();  // step: epilogue of this thread done
       if (st.dot_w) {
         atomicAdd(&dotbuf[row], dot);
         __syncthreads();
@@ -421,6 +536,11 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 }  // namespace gemnet
 
 using namespace gemnet;
+
+static long long* g_chain_prof = nullptr;
+GEMNET_API void gemnet_chain_set_profile_buffer(void* device_int64_x256) {
+  g_chain_prof = static_cast<long long*>(device_int64_x256);
+}
 
 GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t flags, void* stream) {
   GEMNET_REQUIRE(program_host, "null program");
@@ -469,7 +589,7 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const int settled = (flags & GEMNET_DENSE_WEIGHTS_SETTLED) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel, p, n_tiles, settled);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel, p, n_tiles, settled, g_chain_prof);
   if (e != cudaSuccess) {
     set_error("gemnet_chain_tc: launch failed: %s", cudaGetErrorString(e));
     return 1;

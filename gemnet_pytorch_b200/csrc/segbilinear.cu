@@ -400,7 +400,9 @@ __global__ void __launch_bounds__(256) segbil_bwd_kernel(const float* __restrict
 //   backward:  segsum (A)  ->  segbil_bwd_edges_kernel (dB, dA -> workspace, g_rbf_W1)  ->  segbil_bwd_units_kernel
 constexpr int kSplitWarps = 4;
 
-template <typename Cfg>
+// kCS8: output layout (E, C, 8) — the S values of one column contiguous (padded to 8) — for the tcgen05 backward kernel,
+// whose edge-per-thread roles read / write whole columns with 128-bit accesses; default (E, S, C).
+template <typename Cfg, bool kCS8 = false>
 __global__ void __launch_bounds__(kSplitWarps * 32) segsum_kernel(const float* __restrict__ x,
                                                                    const int32_t* __restrict__ expand,
                                                                    const int32_t* __restrict__ rowptr,
@@ -413,11 +415,24 @@ __global__ void __launch_bounds__(kSplitWarps * 32) segsum_kernel(const float* _
   if (e >= n_edges) return;
   float A[Cfg::S][Cfg::CC];
   segment_sum<Cfg>(x, expand, sph, rowptr[e], rowptr[e + 1], lane, stage[warp], A);
-  float* dst = A_out + e * (Cfg::S * Cfg::C) + lane;
+  if constexpr (kCS8) {
+    static_assert(!kCS8 || Cfg::S <= 8, "the (E, C, 8) layout holds up to 8 basis values per column");
 #pragma unroll
-  for (int s = 0; s < Cfg::S; ++s)
+    for (int cc = 0; cc < Cfg::CC; ++cc) {
+      float v[8];
 #pragma unroll
-    for (int cc = 0; cc < Cfg::CC; ++cc) dst[s * Cfg::C + 32 * cc] = A[s][cc];
+      for (int s = 0; s < 8; ++s) v[s] = s < Cfg::S ? A[s < Cfg::S ? s : 0][cc] : 0.f;
+      float4* dst = reinterpret_cast<float4*>(A_out + (e * Cfg::C + lane + 32 * cc) * 8);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  } else {
+    float* dst = A_out + e * (Cfg::S * Cfg::C) + lane;
+#pragma unroll
+    for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+      for (int cc = 0; cc < Cfg::CC; ++cc) dst[s * Cfg::C + 32 * cc] = A[s][cc];
+  }
 }
 
 // rows of an (S, C) per-edge matrix with lanes over s: lane L holds row L (and row 32 + L when S > 32), all C columns
@@ -573,7 +588,7 @@ __global__ void __launch_bounds__(256) segbil_bwd_edges_kernel(const float* __re
 }
 
 // backward, unit part (one warp per edge): g_sph[t,s] = sum_c dA[s,c] x[exp,c];  g_x[exp,c] += sum_s sph[t,s] dA[s,c]
-template <typename Cfg>
+template <typename Cfg, bool kCS8 = false>
 __global__ void __launch_bounds__(kSplitWarps * 32) segbil_bwd_units_kernel(const float* __restrict__ x,
                                                                              const int32_t* __restrict__ expand,
                                                                              const int32_t* __restrict__ rowptr,
@@ -592,12 +607,23 @@ __global__ void __launch_bounds__(kSplitWarps * 32) segbil_bwd_units_kernel(cons
   const int32_t beg = rowptr[e], end = rowptr[e + 1];
   if (beg >= end) return;
   float* st = stage[warp];
-  const float* dAe = dA_in + e * (Cfg::S * Cfg::C);
+  const float* dAe = dA_in + e * (kCS8 ? Cfg::C * 8 : Cfg::S * Cfg::C);
   float dA[Cfg::S][Cfg::CC];
+  if constexpr (kCS8) {  // (E, C, 8) layout written by the tcgen05 edge kernel
 #pragma unroll
-  for (int s = 0; s < Cfg::S; ++s)
+    for (int cc = 0; cc < Cfg::CC; ++cc) {
+      const float4* src = reinterpret_cast<const float4*>(dAe + (lane + 32 * cc) * 8);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int cc = 0; cc < Cfg::CC; ++cc) dA[s][cc] = __ldg(dAe + s * Cfg::C + lane + 32 * cc);
+      for (int s = 0; s < Cfg::S; ++s) dA[s][cc] = v[s < 8 ? s : 0];
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < Cfg::S; ++s)
+#pragma unroll
+      for (int cc = 0; cc < Cfg::CC; ++cc) dA[s][cc] = __ldg(dAe + s * Cfg::C + lane + 32 * cc);
+  }
   float dAs[kBySLane ? (Cfg::S + 31) / 32 : 1][kBySLane ? Cfg::C : 1];
   if constexpr (kBySLane) load_rows_by_lane<Cfg>(dAe, lane, dAs);
   constexpr int RSP = Cfg::S <= 8 ? 8 : 16;
@@ -766,23 +792,45 @@ int launch_segbil_fwd_tc(const float* x, const int32_t* expand, const int32_t* r
                          const float* rbf_W1, const float* W, float scale, int64_t n_edges, float* out,
                          void* workspace, cudaStream_t st);
 
+// tcgen05 backward, edge part (segbilinear_bwd_tc.cu)
+int64_t segbil_bwd_tc_pack_bytes();
+int launch_segbil_bwd_pack_tc(const float* W, void* packed, cudaStream_t st);
+int launch_segbil_bwd_edges_tc(const float* rbf_W1, const void* packed, float scale, int64_t n_edges, const float* g_out,
+                               const float* A_in, float* dA_out, float* g_rbf_W1, cudaStream_t st);
+int launch_segbil_fwd_pack_tc(const float* W, void* packed, cudaStream_t st);
+int launch_segbil_fwd_tc_packed(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                                const float* rbf_W1, const void* packed, float scale, int64_t n_edges, float* out,
+                                cudaStream_t st);
+
 using TripCfg = SegCfg<7, 64, 16, 64, 16>;
 using QuadCfg = SegCfg<49, 32, 32, 32, 32>;
+
+// backward of the triplet shape with the dB GEMM on tensor cores: segsum (A, layout (E,C,8)) -> tcgen05 edge kernel
+// (dA, g_rbf_W1) -> unit kernel (g_x, g_sph).  ws: A and dA, E*C*8 floats each.
+static int launch_bwd_tc(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                         const float* rbf_W1, const void* packed, float scale, int64_t n_edges, const float* g_out,
+                         float* g_x, float* g_sph, float* g_rbf_W1, float* ws, cudaStream_t st) {
+  using Cfg = TripCfg;
+  const unsigned wgrid = (unsigned)ceil_div(n_edges, kSplitWarps);
+  float* A = ws;
+  float* dA = ws + n_edges * (Cfg::C * 8);
+  if (g_rbf_W1)
+    launch_pdl(segsum_kernel<Cfg, true>, wgrid, kSplitWarps * 32, 0, st, x, expand, rowptr, sph, n_edges, A);
+  if (launch_segbil_bwd_edges_tc(rbf_W1, packed, scale, n_edges, g_out, A, dA, g_rbf_W1, st)) return 1;
+  if (g_x || g_sph)
+    launch_pdl(segbil_bwd_units_kernel<Cfg, true>, wgrid, kSplitWarps * 32, 0, st, x, expand, rowptr, sph, n_edges, dA,
+               g_x, g_sph);
+  return check_launch("gemnet_segbilinear_bwd(tcgen05)");
+}
 
 }  // namespace gemnet
 
 using namespace gemnet;
 
-static bool split_enabled();
-
-GEMNET_API int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O,
-                                                      int32_t algo, int32_t backward) {
-  if (algo == 1 && !backward && S == 7 && C == 64 && I == 16 && O == 64) return segbil_tc_workspace_bytes();
-  if (!split_enabled()) return 0;
-  // split pipeline of the fp32 kernels: A (E,S,C) for the forward, A and dA for the backward.  The narrow triplet
-  // forward stays fused (measured: 83 us fused vs 140 us split at batch 64; its segments are short and balanced).
-  if (!backward && S <= 16) return 0;
-  return (int64_t)sizeof(float) * n_edges * S * C * (backward ? 2 : 1);
+static int shape_id(int32_t S, int32_t C, int32_t I, int32_t O) {
+  if (S == 7 && C == 64 && I == 16 && O == 64) return 1;
+  if (S == 49 && C == 32 && I == 32 && O == 32) return 2;
+  return 0;
 }
 
 static bool split_enabled() {
@@ -793,10 +841,31 @@ static bool split_enabled() {
   return on;
 }
 
-static int shape_id(int32_t S, int32_t C, int32_t I, int32_t O) {
-  if (S == 7 && C == 64 && I == 16 && O == 64) return 1;
-  if (S == 49 && C == 32 && I == 32 && O == 32) return 2;
-  return 0;
+GEMNET_API int64_t gemnet_segbilinear_pack_bytes(int32_t S, int32_t C, int32_t I, int32_t O, int32_t backward) {
+  if (shape_id(S, C, I, O) != 1) return 0;
+  return backward ? segbil_bwd_tc_pack_bytes() : segbil_tc_workspace_bytes();
+}
+
+GEMNET_API int gemnet_segbilinear_pack(const float* W, int32_t S, int32_t C, int32_t I, int32_t O, int32_t backward,
+                                       void* packed, void* stream) {
+  GEMNET_REQUIRE(shape_id(S, C, I, O) == 1, "the tcgen05 kernels are built for the triplet shape (7,64,16,64) only");
+  GEMNET_REQUIRE(W && packed && ((uintptr_t)packed % 16) == 0, "null / misaligned pointer");
+  return backward ? launch_segbil_bwd_pack_tc(W, packed, as_stream(stream)) : launch_segbil_fwd_pack_tc(W, packed, as_stream(stream));
+}
+
+GEMNET_API int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O,
+                                                      int32_t algo, int32_t backward) {
+  const bool tc = (algo & GEMNET_SEGBIL_TC) && shape_id(S, C, I, O) == 1;
+  const bool prepacked = (algo & GEMNET_SEGBIL_PREPACKED) != 0;
+  if (tc && !backward) return prepacked ? 0 : segbil_tc_workspace_bytes();
+  // tcgen05 backward: [packed image unless prepacked][A (E,C,8)][dA (E,C,8)]
+  if (tc && backward)
+    return (prepacked ? 0 : segbil_bwd_tc_pack_bytes()) + (int64_t)sizeof(float) * n_edges * C * 8 * 2;
+  if (!split_enabled()) return 0;
+  // split pipeline of the fp32 kernels: A (E,S,C) for the forward, A and dA for the backward.  The narrow triplet
+  // forward stays fused (measured: 83 us fused vs 140 us split at batch 64; its segments are short and balanced).
+  if (!backward && S <= 16) return 0;
+  return (int64_t)sizeof(float) * n_edges * S * C * (backward ? 2 : 1);
 }
 
 GEMNET_API int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
@@ -804,7 +873,7 @@ GEMNET_API int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, con
                                       int64_t n_units, int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo,
                                       float* out, void* workspace, void* stream) {
   GEMNET_REQUIRE(n_edges >= 0 && n_units >= 0, "negative size");
-  GEMNET_REQUIRE(algo == 0 || algo == 1, "algo must be 0 (fp32 CUDA cores) or 1 (tcgen05)");
+  GEMNET_REQUIRE(algo >= 0 && algo <= 3 && algo != 2, "algo: 0 fp32 CUDA cores, 1 tcgen05, 3 tcgen05 with a pre-packed weight image");
   const int sid = shape_id(S, C, I, O);
   GEMNET_REQUIRE(sid != 0, "unsupported (S,C,I,O): built for (7,64,16,64) and (49,32,32,32)");
   GEMNET_REQUIRE(algo == 0 || sid == 1, "algo 1 (tcgen05) is built for the triplet shape (7,64,16,64) only");
@@ -812,6 +881,7 @@ GEMNET_API int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, con
   GEMNET_REQUIRE(rowptr && rbf_W1 && W && out && (n_units == 0 || (x && expand && sph)), "null pointer");
   GEMNET_REQUIRE(((uintptr_t)W | (uintptr_t)out) % 16 == 0, "W/out must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
+  if (algo == 3) return launch_segbil_fwd_tc_packed(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, st);
   if (algo == 1) return launch_segbil_fwd_tc(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, workspace, st);
   float* ws = split_enabled() ? static_cast<float*>(workspace) : nullptr;
   if (sid == 1) return launch_fwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, out, nullptr, st);
@@ -823,8 +893,8 @@ GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, con
                                       int64_t n_units, int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo,
                                       const float* g_out, float* g_x, float* g_sph, float* g_rbf_W1, float* g_W,
                                       void* workspace, void* stream) {
-  (void)algo;  // the backward runs on the fp32 CUDA-core kernel for every algo in this library version
   GEMNET_REQUIRE(n_edges >= 0 && n_units >= 0, "negative size");
+  GEMNET_REQUIRE(algo >= 0 && algo <= 3 && algo != 2, "algo: 0 fp32 CUDA cores, 1 tcgen05, 3 tcgen05 with a pre-packed weight image");
   GEMNET_REQUIRE(g_W == nullptr, "g_W is computed by the host wrapper in this library version; pass NULL");
   const int sid = shape_id(S, C, I, O);
   GEMNET_REQUIRE(sid != 0, "unsupported (S,C,I,O): built for (7,64,16,64) and (49,32,32,32)");
@@ -832,6 +902,19 @@ GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, con
   GEMNET_REQUIRE(rowptr && rbf_W1 && W && g_out && (n_units == 0 || (x && expand && sph)), "null pointer");
   GEMNET_REQUIRE(((uintptr_t)W) % 16 == 0, "W must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
+  if ((algo & GEMNET_SEGBIL_TC) && sid == 1) {
+    // tensor-core backward (triplet shape): dB = g W'^T on tcgen05; the other shapes keep the fp32 kernels
+    GEMNET_REQUIRE(workspace && ((uintptr_t)workspace % 16) == 0, "workspace of gemnet_segbilinear_workspace_bytes() bytes required");
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const void* packed = W;
+    if (!(algo & GEMNET_SEGBIL_PREPACKED)) {
+      if (launch_segbil_bwd_pack_tc(W, ws, st)) return 1;
+      packed = ws;
+      ws += segbil_bwd_tc_pack_bytes();
+    }
+    return launch_bwd_tc(x, expand, rowptr, sph, rbf_W1, packed, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1,
+                         reinterpret_cast<float*>(ws), st);
+  }
   float* ws = split_enabled() ? static_cast<float*>(workspace) : nullptr;
   if (sid == 1)
     return launch_bwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, ws, st);

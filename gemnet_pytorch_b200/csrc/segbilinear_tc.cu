@@ -405,12 +405,18 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
 
 int64_t segbil_tc_workspace_bytes() { return tc::WPACK_BYTES; }
 
-int launch_segbil_fwd_tc(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
-                         const float* rbf_W1, const float* W, float scale, int64_t n_edges, float* out,
-                         void* workspace, cudaStream_t st) {
+int launch_segbil_fwd_pack_tc(const float* W, void* packed, cudaStream_t st) {
   using namespace tc;
-  if (!workspace || ((uintptr_t)workspace % 16) != 0) {
-    set_error("gemnet_segbilinear_fwd(algo=1): workspace of gemnet_segbilinear_workspace_bytes() bytes required");
+  pack_weight_kernel<<<(NCHUNK * O * KC + 255) / 256, 256, 0, st>>>(W, reinterpret_cast<__nv_bfloat16*>(packed));
+  return check_launch("gemnet_segbilinear_pack(fwd)");
+}
+
+int launch_segbil_fwd_tc_packed(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                                const float* rbf_W1, const void* packed, float scale, int64_t n_edges, float* out,
+                                cudaStream_t st) {
+  using namespace tc;
+  if (!packed || ((uintptr_t)packed % 16) != 0) {
+    set_error("gemnet_segbilinear_fwd(tcgen05): packed weight image missing / misaligned");
     return 1;
   }
   static bool configured = false;
@@ -422,15 +428,24 @@ int launch_segbil_fwd_tc(const float* x, const int32_t* expand, const int32_t* r
     }
     configured = true;
   }
-  __nv_bfloat16* Wp = reinterpret_cast<__nv_bfloat16*>(workspace);
-  pack_weight_kernel<<<(NCHUNK * O * KC + 255) / 256, 256, 0, st>>>(W, Wp);
   const int n_tiles = (int)ceil_div(n_edges, TILE_M);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  launch_pdl(segbil_fwd_tc_kernel, grid, THREADS, SMEM_BYTES, st, x, expand, rowptr, sph, rbf_W1, Wp, scale, n_edges, n_tiles,
-                                                         out);
+  launch_pdl(segbil_fwd_tc_kernel, grid, THREADS, SMEM_BYTES, st, x, expand, rowptr, sph, rbf_W1,
+             reinterpret_cast<const __nv_bfloat16*>(packed), scale, n_edges, n_tiles, out);
   return check_launch("gemnet_segbilinear_fwd(algo=1)");
+}
+
+int launch_segbil_fwd_tc(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                         const float* rbf_W1, const float* W, float scale, int64_t n_edges, float* out,
+                         void* workspace, cudaStream_t st) {
+  if (!workspace || ((uintptr_t)workspace % 16) != 0) {
+    set_error("gemnet_segbilinear_fwd(algo=1): workspace of gemnet_segbilinear_workspace_bytes() bytes required");
+    return 1;
+  }
+  if (launch_segbil_fwd_pack_tc(W, workspace, st)) return 1;
+  return launch_segbil_fwd_tc_packed(x, expand, rowptr, sph, rbf_W1, workspace, scale, n_edges, out, st);
 }
 
 }  // namespace gemnet

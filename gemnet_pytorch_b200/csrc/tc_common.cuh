@@ -84,6 +84,16 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// registers -> 16 consecutive fp32 columns of this thread's TMEM lane (complete when it returns)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // exact three-way bf16 split of two fp32 values: v = h + m + l (each packed as bf16x2, low half = first value)
@@ -108,11 +118,17 @@ constexpr float kShrinkPerStep = 1.25e-8f;  // mean relative toward-zero roundin
 
 // silu(z)/0.6 and its derivative; sigmoid and 1 - sigmoid from exp(-|z|): no overflow / cancellation
 __device__ __forceinline__ void scaled_silu(float z, float& v, float& d) {
-  const float t = expf(-fabsf(z));
-  const float rr = 1.0f / (1.0f + t);
+  const float t = __expf(-fabsf(z));            // ex2.approx: 2 ulp, no slow path
+  const float rr = __fdividef(1.0f, 1.0f + t);  // rcp.approx (1 + t in (1, 2])
   const float sg = z >= 0.f ? rr : t * rr, oms = z >= 0.f ? t * rr : rr;
   v = z * sg * kSiluScale;
   d = sg * fmaf(z, oms, 1.0f) * kSiluScale;
+}
+
+__device__ __forceinline__ float scaled_silu_value(float z) {
+  const float t = __expf(-fabsf(z));
+  const float rr = __fdividef(1.0f, 1.0f + t);
+  return z * (z >= 0.f ? rr : t * rr) * kSiluScale;
 }
 
 }  // namespace tcx

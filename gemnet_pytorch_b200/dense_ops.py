@@ -53,6 +53,8 @@ PACKER = [None]
 def invalidate():
     """Drop every packed weight image (they are rebuilt on next use)."""
     _packs.clear()
+    from . import ops
+    ops._segbil_packs.clear()
 
 
 _fn = []

@@ -12,7 +12,7 @@ fp64, scatters are CSR segment sums without atomics, and scale factors are folde
 """
 import torch
 
-from . import _lib, engine, graph, layers, ops
+from . import _lib, dense_ops, engine, graph, layers, ops
 from .layers import (AtomEmbedding, BesselBasisLayer, Dense, EdgeEmbedding, EfficientInteractionDownProjection,
                      InteractionBlock, InteractionBlockTripletsOnly, OutputBlock, SphericalBasisLayer,
                      TensorBasisLayer)
@@ -111,6 +111,35 @@ class GemNet(torch.nn.Module):
         self.out_blocks = torch.nn.ModuleList(out_blocks)
         self.int_blocks = torch.nn.ModuleList(int_blocks)
 
+    # ------------------------------------------------------------------------------------------ weight caches
+    def invalidate_caches(self):
+        """Drop the packed (bf16-split) weight images of the tcgen05 kernels.  They are keyed on the tensors' version
+        counters, which optimizer steps / copy_ / load_state_dict move but in-place writes through `.data` do not
+        (ExponentialMovingAverage.copy_to / restore, ema_decay.py:110,145).  train()/eval() mode changes,
+        load_state_dict and .to()/.cuda() call this, which covers the reference Trainer's cycle
+        (load_averaged_variables -> eval -> restore_variable_backups -> train); call it yourself after any other `.data`
+        write."""
+        dense_ops.invalidate()
+        for mod in self.modules():
+            if isinstance(mod, layers.ScalingFactor):
+                mod._cached = None
+        self._fuse_ok = None
+
+    def train(self, mode=True):
+        if mode != self.training:
+            self.invalidate_caches()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_caches()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_caches()
+        return out
+
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs):
         if self.use_engine and not self.training:
@@ -128,6 +157,13 @@ class GemNet(torch.nn.Module):
         dev = R.device
 
         if not self.direct_forces:
+            if self.training and torch.is_grad_enabled():
+                # the reference differentiates the force THROUGH the force (create_graph=True, gemnet.py:598-613); the
+                # kernels' backward passes are first-order only, so the force loss would silently contribute no weight
+                # gradient: refuse instead of training on the energy alone
+                raise NotImplementedError(
+                    "training a direct_forces=False GemNet needs a double backward (SURVEY 8f N3), which the B200 "
+                    "kernels do not provide: train with direct_forces=True, or evaluate with model.eval()")
             inputs["R"].requires_grad = True
 
         # H1: distances and unit vectors

@@ -351,6 +351,30 @@ def _segbilinear_weight_grad(x, expand, rowptr, sph, rbf_W1, g_out_scaled):
     return torch.einsum("eci,eo->cio", B, g_out_scaled)
 
 
+_segbil_packs = {}
+
+
+def segbil_packed(W, backward):
+    """bf16 hi/lo image of the bilinear weight for the tcgen05 kernels (gemnet_segbilinear_pack), packed once per
+    weight version (see dense_ops.packed_weight for the `.data` caveat; dense_ops.invalidate() clears this cache too)."""
+    C, I, O = W.shape
+    key = (W.data_ptr(), (C, I, O), bool(backward))
+    hit = _segbil_packs.get(key)
+    if hit is not None and hit[2] == W._version:
+        return hit[0]
+    S = 7
+    n = _L().gemnet_segbilinear_pack_bytes(S, C, I, O, int(backward))
+    buf = hit[0] if hit is not None else torch.empty(n, dtype=torch.uint8, device=W.device)
+    _check(_L().gemnet_segbilinear_pack(_p(_f32(W)), S, C, I, O, int(backward), _p(buf), _stream()),
+           "gemnet_segbilinear_pack")
+    _segbil_packs[key] = (buf, W, W._version)
+    return buf
+
+
+def _tc_shape(S, C, I, O):
+    return (S, C, I, O) == (7, 64, 16, 64)
+
+
 class _SegBilinear(Function):
     @staticmethod
     def forward(ctx, x, sph, rbf_W1, W, expand, rowptr, scale, algo):
@@ -359,11 +383,18 @@ class _SegBilinear(Function):
         C, _, O = W.shape
         U = expand.numel()
         out = torch.empty(E, O, dtype=torch.float32, device=x.device)
-        nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, algo, 0)
-        ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
-        _check(_L().gemnet_segbilinear_fwd(_p(x), _p(_i32(expand)), _p(_i32(rowptr)), _p(sph), _p(rbf_W1), _p(W),
-                                           scale, E, U, S, C, I, O, algo, _p(out), _p(ws), _stream()),
-               "gemnet_segbilinear_fwd", kernels=1 if (algo == 0 and ws is None) else 2)
+        if algo and _tc_shape(S, C, I, O):
+            # tcgen05 kernel with the weight image packed once per weight version (algo 3 = TC | PREPACKED)
+            _check(_L().gemnet_segbilinear_fwd(_p(x), _p(_i32(expand)), _p(_i32(rowptr)), _p(sph), _p(rbf_W1),
+                                               _p(segbil_packed(W, False)), scale, E, U, S, C, I, O, 3, _p(out), None,
+                                               _stream()), "gemnet_segbilinear_fwd")
+        else:
+            algo = 0
+            nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, algo, 0)
+            ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
+            _check(_L().gemnet_segbilinear_fwd(_p(x), _p(_i32(expand)), _p(_i32(rowptr)), _p(sph), _p(rbf_W1), _p(W),
+                                               scale, E, U, S, C, I, O, algo, _p(out), _p(ws), _stream()),
+                   "gemnet_segbilinear_fwd", kernels=1 if ws is None else 2)
         ctx.save_for_backward(x, sph, rbf_W1, W, expand, rowptr)
         ctx.cfg = (scale, algo)
         return out
@@ -381,13 +412,21 @@ class _SegBilinear(Function):
         g_sph = torch.empty_like(sph) if ctx.needs_input_grad[1] else None
         g_rw = torch.empty_like(rbf_W1) if ctx.needs_input_grad[2] else None
         if g_x is not None or g_sph is not None or g_rw is not None:
-            nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, algo, 1)
+            tc = bool(algo) and _tc_shape(S, C, I, O) and BWD_TC[0]
+            a = 3 if tc else 0
+            nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, a, 1)
             ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
-            _check(_L().gemnet_segbilinear_bwd(_p(x), _p(expand), _p(rowptr), _p(sph), _p(rbf_W1), _p(W), scale, E, U,
-                                               S, C, I, O, algo, _p(g), _p(g_x), _p(g_sph), _p(g_rw), None, _p(ws),
+            Wk = segbil_packed(W, True) if tc else W
+            _check(_L().gemnet_segbilinear_bwd(_p(x), _p(expand), _p(rowptr), _p(sph), _p(rbf_W1), _p(Wk), scale, E, U,
+                                               S, C, I, O, a, _p(g), _p(g_x), _p(g_sph), _p(g_rw), None, _p(ws),
                                                _stream()), "gemnet_segbilinear_bwd", kernels=3 if ws is not None else 1)
         g_W = _segbilinear_weight_grad(x, expand, rowptr, sph, rbf_W1, g * scale) if ctx.needs_input_grad[3] else None
         return g_x, g_sph, g_rw, g_W, None, None, None, None
+
+
+import os as _os
+
+BWD_TC = [_os.environ.get("GEMNET_B200_H7_BWD_TC", "1") != "0"]  # dB = g W'^T of the triplet shape on tcgen05
 
 
 def segmented_bilinear(x, sph, rbf_W1, W, expand, rowptr, scale=1.0, algo=0):

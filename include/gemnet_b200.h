@@ -155,13 +155,23 @@ int gemnet_downproj_bwd(const float* rad, const float* Wd, const int32_t* l_of_s
  * A ragged (CSR) segmented GEMM: no (E,Kmax,.) padding, no gathered (T,C) tensor in HBM.
  * Supported shapes (S,C,I,O): (7,64,16,64) triplets and (49,32,32,32) quadruplets of the published
  * configuration, plus the generic fallback kernel for any S<=64, C in {16,32,64,128}, I<=64, O<=128.
- * `algo`: 0 = fp32 CUDA-core reference kernel, 1 = tcgen05 (tensor-core) kernel when available for the shape.
+ * `algo`: 0 = fp32 CUDA-core kernels; GEMNET_SEGBIL_TC (1) = tcgen05 kernels where built — the triplet shape: the
+ * forward's (E x 1024) @ (1024 x 64) stage and the backward's dB = g W'^T stage (the quadruplet shape and `algo` 1 fall
+ * back to the fp32 kernels in the backward of other shapes); | GEMNET_SEGBIL_PREPACKED (2): `W` points to the image
+ * written by gemnet_segbilinear_pack (forward image for _fwd, backward image for _bwd) instead of the raw weight, so
+ * that the per-call pack kernel disappears (weights are packed once per version by the caller).
  * bwd: g_x (n_x, C) accumulated (atomics); g_sph (U,S), g_rbf_W1 (E,I,S) overwritten;
  *      g_W (C,I,O) accumulated (may be NULL: inference / force evaluation does not need it).
  * workspace: gemnet_segbilinear_workspace_bytes() bytes (may return 0).
  * ---------------------------------------------------------------------------------------------- */
+#define GEMNET_SEGBIL_TC 1
+#define GEMNET_SEGBIL_PREPACKED 2
 int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo,
                                            int32_t backward);
+/* packed bf16 hi/lo weight images of the tcgen05 kernels (0 bytes = no tensor-core kernel for the shape) */
+int64_t gemnet_segbilinear_pack_bytes(int32_t S, int32_t C, int32_t I, int32_t O, int32_t backward);
+int gemnet_segbilinear_pack(const float* W, int32_t S, int32_t C, int32_t I, int32_t O, int32_t backward, void* packed,
+                            void* stream);
 int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
                            const float* rbf_W1, const float* W, float scale, int64_t n_edges, int64_t n_units,
                            int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo, float* out, void* workspace,
@@ -330,6 +340,9 @@ typedef struct {
 } gemnet_chain_program;
 
 int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t flags, void* stream);
+/* diagnostics: when non-NULL, thread 0 of CTA 0 of every following gemnet_chain_tc launch writes clock64() stamps of its
+ * phase boundaries (<= 250 int64) to this device buffer; NULL (default) switches it off. */
+void gemnet_chain_set_profile_buffer(void* device_int64_x256);
 
 /* ------------------------------------------------------------------------------------------------
  * H0  host index builder: DataContainer.__getitem__ / get_triplets / get_quadruplets

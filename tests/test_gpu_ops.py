@@ -426,6 +426,31 @@ def test_segmented_bilinear_tcgen05_matches_fp32_kernel_and_oracle(ops, dev, ids
     assert torch.equal(out1, out1b)
 
 
+@pytest.mark.parametrize("ids", [[1, 4, 7, 9, 16], list(range(64)), list(range(256))])
+def test_segmented_bilinear_tcgen05_backward(ops, dev, ids):
+    """algo 1 backward: dB = g W'^T on tcgen05 (segbilinear_bwd_tc.cu) + the (E,C,8)-layout segsum / unit kernels,
+    against the oracle's autograd gradients and the fp32 kernels; ragged tile (E % 128 != 0) and multi-tile cases."""
+    torch.manual_seed(5)
+    cpu, gpu = batch(ids, True, dev)
+    nE, U = len(cpu["id_c"]), len(cpu["id3_reduce_ca"])
+    x = torch.randn(nE, 64, device=dev)
+    sph = torch.randn(U, 7, device=dev)
+    rbf_W1 = torch.randn(nE, 16, 7, device=dev) * 0.3
+    W = torch.randn(64, 16, 64, device=dev) / 32
+    expand = gpu["id3_expand_ba"]
+    rowptr, _ = ops.csr_from_sorted(gpu["id3_reduce_ca"], nE)
+    g = torch.randn(nE, 64, device=dev)
+    got1 = kernel_grads(lambda a, b, c: ops.segmented_bilinear(a, b, c, W, expand, rowptr, 0.9, algo=1), [x, sph, rbf_W1], g)
+    got0 = kernel_grads(lambda a, b, c: ops.segmented_bilinear(a, b, c, W, expand, rowptr, 0.9, algo=0), [x, sph, rbf_W1], g)
+    ref = oracle_grads(lambda a, b, c: _bilinear_oracle(a, b, c, W.double().cpu(), cpu["id3_expand_ba"],
+                                                        cpu["id3_reduce_ca"], cpu["Kidx3"], 0.9), [x, sph, rbf_W1], g)
+    for name, a1, a0, b in zip(("g_x", "g_sph", "g_rbf_W1"), got1, got0, ref):
+        e1, e0 = relerr(a1, b), relerr(a0, b)
+        print(f"E={nE} {name}: tcgen05 {e1:.2e}  fp32 {e0:.2e}")
+        assert e1 < 2e-5, name   # bf16x3 split: ~2^-16 per product
+        assert e0 < 2e-5, name
+
+
 # ----------------------------------------------------------------------------- N1: fused dense on tcgen05 (bf16x3 split)
 @pytest.mark.parametrize("M,K,N", [(1, 128, 128), (300, 16, 128), (8186, 128, 128), (5000, 128, 64), (777, 64, 128),
                                    (20000, 128, 128), (130, 128, 16)])
