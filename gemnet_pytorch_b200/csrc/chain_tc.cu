@@ -1,24 +1,31 @@
 // N1 chain fusion: a whole stack of dense layers with the pointwise work between them in ONE tcgen05 kernel
 // (include/gemnet_b200.h, gemnet_chain_tc).  Batch-64 GemNet is latency bound: ~25 dependent launches per
-// interaction block in each direction, every one a 128x128 GEMM that finishes in microseconds.  Here a 128-row tile of
-// the activation stays on chip for the whole chain:
+// interaction block in each direction, every one a 128x128 GEMM that finishes in microseconds.  Here a 64-row tile of
+// the activation stays on chip for the whole chain.
 //
-//   operand A      shared memory, exact three-way bf16 split (h + m + l == fp32 value), K-major SWIZZLE_128B, 96 KB
-//   weights        streamed through a 2-slot ring (one 64-k chunk = 48 KB per slot) by cp.async.bulk, one thread;
-//                  the next layer's weights arrive while the current layer's epilogue runs
+// The GEMM is issued TRANSPOSED: D^T (features x rows) = W (features x K) @ X^T, i.e. the packed weight image is the
+// M-side operand (M = 128 output features = the 128 TMEM lanes) and the activation tile is the N-side operand (N = 64
+// rows).  With the accumulator in that orientation a warp's 32 lanes are 32 consecutive FEATURES of one row, so
+//   * every global access of the epilogue (stores of the activation derivative and of the outputs, loads of skip /
+//     Hadamard / gathered terms) is a fully coalesced 128-byte line per warp instruction,
+//   * a 64-row tile keeps all 512 threads busy with 16 values each (a row-per-lane layout would idle half the lanes),
+//     so batch 64 (8186 edges) runs on 128 CTAs instead of 64, and the MMA of a step costs 32 instead of 64 cycles per
+//     K16 instruction.
+//
+//   operand X      shared memory, exact three-way bf16 split (h + m + l == fp32 value), K-major SWIZZLE_128B, 48 KB
+//   weights        two 48 KB chunk slots filled by cp.async.bulk; the next layer's image streams in while the current
+//                  layer's epilogue runs
 //   accumulators   TMEM: one main accumulator per K chunk + one correction accumulator (dense_tc.cu's numerics:
 //                  six significant products, the toward-zero rounding of the accumulator compensated)
-//   skip value     "carry": the last 128 TMEM columns (tcgen05.st / tcgen05.ld of the thread's row x 32-column patch):
-//                  it costs no registers and no shared memory
+//   skip value     "carry": 64 more TMEM columns (tcgen05.st / tcgen05.ld): no registers, no shared memory
 //
-// 512 threads (16 warps: 128 registers per thread), one CTA per SM, persistent over row tiles.  Every thread is a
-// worker: operand fill from global memory (coalesced; gathers and several summed terms allowed) and the epilogue of
-// every step — tcgen05.ld of the thread's (row, 32 columns) patch, the pointwise program (activation, Hadamard
-// products, skip connections, scales), the stores the backward pass needs, and the next layer's operand written back
-// into shared memory (so the GEMM chain never touches HBM).  Thread 0 additionally issues the tcgen05.mma of each
-// step (6 products per K16 step) once the operand is complete (one __syncthreads per GEMM) and, as soon as a GEMM
-// has completed (mbarrier acc_full), the cp.async.bulk of the NEXT GEMM's packed weight image into the two chunk
-// slots — the weights stream in while the epilogue runs.  The step program is a kernel parameter (__grid_constant__).
+// 512 threads, one CTA per SM, persistent over row tiles.  Every thread is a worker: operand fill from global memory
+// (coalesced; gathers and several summed terms allowed) and the epilogue of every step — thread (feature f = 32 q +
+// lane, rows 16 cg .. 16 cg + 15) reads its 16 accumulator values with one tcgen05.ld per accumulator, runs the
+// pointwise program stage by stage over them, stores what the backward pass needs and writes the next layer's operand
+// back into shared memory.  Thread 0 additionally issues the tcgen05.mma of each step once the operand is complete
+// (one __syncthreads per GEMM) and, as soon as a GEMM has completed (mbarrier acc_full), the cp.async.bulk of the NEXT
+// GEMM's weight image.  The step program is a kernel parameter (__grid_constant__).
 #include <cuda_bf16.h>
 
 #include <type_traits>
@@ -31,41 +38,54 @@ namespace chain {
 
 using namespace tcx;
 
-constexpr int TM = 128;
-constexpr int SPLIT_BYTES = TM * 128;          // one bf16 split of one 64-k chunk: 128 rows x 128 B
-constexpr int CHUNK_BYTES = 3 * SPLIT_BYTES;   // 49152
-constexpr int A_BYTES = 2 * CHUNK_BYTES;       // 98304
+constexpr int TR = 64;                         // rows per tile (the N side of the MMA)
+constexpr int SPLIT_BYTES = TR * 128;          // one bf16 split of one 64-k chunk of the operand: 64 rows x 128 B
+constexpr int CHUNK_BYTES = 3 * SPLIT_BYTES;   // 24576
+constexpr int X_BYTES = 2 * CHUNK_BYTES;       // 49152
 constexpr int WSLOT_BYTES = 3 * 128 * 128;     // 49152: one 64-k chunk of a (<=128)-row weight image, three splits
 constexpr int W_SLOTS = 2;
 constexpr int THREADS = 512;
 constexpr int MISC_BYTES = 1024;               // barriers, TMEM slot, dot buffer
-constexpr int SMEM_BYTES = 1024 + A_BYTES + W_SLOTS * WSLOT_BYTES + MISC_BYTES;
-constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t ACC_STRIDE = 128, CORR_COL = 256, CARRY_COL = 384;
+constexpr int SMEM_BYTES = 1024 + X_BYTES + W_SLOTS * WSLOT_BYTES + MISC_BYTES;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t ACC_STRIDE = 64, CORR_COL = 128, CARRY_COL = 192;
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-// coherent load: for tensors that an earlier step of the SAME kernel (the same thread) may have written
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-__device__ __forceinline__ void store_granule(uint8_t* A, int row, int g, const float (&v)[8]) {
-  // granule g (8 k-values) of operand row `row`: chunk g / 8, 16-byte slot (g % 8) XOR-swizzled by the row
+// byte offset (inside one split) of element (row, k) of the K-major SWIZZLE_128B operand: chunk k / 64, 16-byte granule
+// (k % 64) / 8 XOR-swizzled by the row
+__device__ __forceinline__ uint32_t x_offset(int row, int k) {
+  return (uint32_t)((k >> 6) * CHUNK_BYTES + row * 128 + (((((k & 63) >> 3)) ^ (row & 7)) << 4) + (k & 7) * 2);
+}
+__device__ __forceinline__ void store_granule(uint8_t* X, int row, int g, const float (&v)[8]) {
   uint32_t h[4], m[4], l[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) split3(v[2 * u], v[2 * u + 1], h[u], m[u], l[u]);
-  uint8_t* p = A + (g >> 3) * CHUNK_BYTES + row * 128 + (((g & 7) ^ (row & 7)) << 4);
+  uint8_t* p = X + (g >> 3) * CHUNK_BYTES + row * 128 + (((g & 7) ^ (row & 7)) << 4);
   *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(p + SPLIT_BYTES) = make_uint4(m[0], m[1], m[2], m[3]);
   *reinterpret_cast<uint4*>(p + 2 * SPLIT_BYTES) = make_uint4(l[0], l[1], l[2], l[3]);
 }
-__device__ __forceinline__ void load_granule(const uint8_t* A, int row, int g, float (&v)[8]) {
-  const uint8_t* p = A + (g >> 3) * CHUNK_BYTES + row * 128 + (((g & 7) ^ (row & 7)) << 4);
-  const uint4 h = *reinterpret_cast<const uint4*>(p);
-  const uint4 m = *reinterpret_cast<const uint4*>(p + SPLIT_BYTES);
-  const uint4 l = *reinterpret_cast<const uint4*>(p + 2 * SPLIT_BYTES);
-  join3(h.x, m.x, l.x, v[0], v[1]);
-  join3(h.y, m.y, l.y, v[2], v[3]);
-  join3(h.z, m.z, l.z, v[4], v[5]);
-  join3(h.w, m.w, l.w, v[6], v[7]);
+// two values of ONE feature k for two consecutive rows -> the three split tiles (2-byte stores; a warp writes 64
+// contiguous bytes per instruction: conflict free)
+__device__ __forceinline__ void store_pair(uint8_t* X, int row, int k, float v0, float v1) {
+  uint32_t h, m, l;
+  split3(v0, v1, h, m, l);
+  uint8_t* p0 = X + x_offset(row, k);
+  uint8_t* p1 = X + x_offset(row + 1, k);
+  *reinterpret_cast<uint16_t*>(p0) = (uint16_t)h;
+  *reinterpret_cast<uint16_t*>(p1) = (uint16_t)(h >> 16);
+  *reinterpret_cast<uint16_t*>(p0 + SPLIT_BYTES) = (uint16_t)m;
+  *reinterpret_cast<uint16_t*>(p1 + SPLIT_BYTES) = (uint16_t)(m >> 16);
+  *reinterpret_cast<uint16_t*>(p0 + 2 * SPLIT_BYTES) = (uint16_t)l;
+  *reinterpret_cast<uint16_t*>(p1 + 2 * SPLIT_BYTES) = (uint16_t)(l >> 16);
+}
+__device__ __forceinline__ float load_elem(const uint8_t* X, int row, int k) {
+  const uint8_t* p = X + x_offset(row, k);
+  const uint32_t h = *reinterpret_cast<const uint16_t*>(p);
+  const uint32_t m = *reinterpret_cast<const uint16_t*>(p + SPLIT_BYTES);
+  const uint32_t l = *reinterpret_cast<const uint16_t*>(p + 2 * SPLIT_BYTES);
+  return (__uint_as_float(h << 16) + __uint_as_float(m << 16)) + __uint_as_float(l << 16);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -74,15 +94,15 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* A = sm;                                      // operand: [chunk][split][row][128 B]
-  const uint32_t a_base = base;
-  const uint32_t w_base = base + A_BYTES;               // weight slots: [chunk][split][n][128 B]
+  uint8_t* X = sm;                                      // operand: [chunk][split][row][128 B]
+  const uint32_t x_base = base;
+  const uint32_t w_base = base + X_BYTES;               // weight slots: [chunk][split][n][128 B]
   const uint32_t bar_base = w_base + W_SLOTS * WSLOT_BYTES;
   const uint32_t acc_full = bar_base;
   auto w_full = [&](int s) { return bar_base + 8u + 8u * s; };
   const uint32_t tmem_slot = bar_base + 32;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + A_BYTES + W_SLOTS * WSLOT_BYTES + 32);
-  float* dotbuf = reinterpret_cast<float*>(sm + A_BYTES + W_SLOTS * WSLOT_BYTES + 64);  // 128 floats
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + X_BYTES + W_SLOTS * WSLOT_BYTES + 32);
+  float* dotbuf = reinterpret_cast<float*>(sm + X_BYTES + W_SLOTS * WSLOT_BYTES + 64);  // TR floats
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // diagnostics (gemnet_chain_set_profile_buffer): thread 0 of CTA 0 records clock64() at the phase boundaries
@@ -119,62 +139,69 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       for (int sp = 0; sp < 3; ++sp) bulk_g2s(w_base + kb * WSLOT_BYTES + sp * blk, src + (size_t)sp * blk, blk, w_full(kb));
     }
   };
-  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+  if (tid == 0) {
     if (!weights_settled) griddep_wait();  // the packed images may come from the kernel launched just before
     fetch_weights(prog.step[0]);
   }
   griddep_wait();
   stamp();  // 2: predecessor complete
 
-  const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (rows 32q..32q+31), column group
-  const int row = q * 32 + lane;                // epilogue row of this thread inside the tile
-  // carry: 16 columns of this thread's row at TMEM column CARRY_COL + col
-  auto carry_ld = [&](int col, float (&c)[16]) {
+  const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (features 32q..32q+31), row group (16 rows)
+  const int f = q * 32 + lane;                  // feature (accumulator row = TMEM lane) of this thread
+  const int e_loc = cg * 16;                    // first tile row of this thread's 16 values
+  const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)e_loc;
+  uint32_t gemm = 0;                            // GEMMs issued by this CTA (parity of acc_full)
+  uint32_t wuse0 = 0, wuse1 = 0;                // fills of weight slot 0 / 1 consumed so far (thread 0)
+
+  auto carry_ld = [&](float (&c)[16]) {
     uint32_t raw[16];
-    tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + CARRY_COL + (uint32_t)col, raw);
+    tmem_ld16_nowait(t_lane + CARRY_COL, raw);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) c[j] = __uint_as_float(raw[j]);
   };
-  auto carry_st = [&](int col, const float (&c)[16]) {
+  auto carry_st = [&](const float (&c)[16]) {
     uint32_t raw[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) raw[j] = __float_as_uint(c[j]);
-    tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + CARRY_COL + (uint32_t)col, raw);
-  };
-  uint32_t gemm = 0;                            // GEMMs issued by this CTA (parity of acc_full)
-  uint32_t wuse0 = 0, wuse1 = 0;                // fills of weight slot 0 / 1 consumed so far (thread 0)
-
-  // the thread's epilogue patch of the NEXT operand (width W = Kpad / 4 columns starting at W * cg) from the carry
-  auto patch_from_carry = [&](int Knext, float s_a, const float* amul, int64_t rcl, bool rv) {
-    const int Wd = Knext > 64 ? 32 : 16;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h * 16 >= Wd) break;
-      float c[16];
-      carry_ld(Wd * cg + h * 16, c);
-#pragma unroll
-      for (int g2 = 0; g2 < 2; ++g2) {
-        const int col = Wd * cg + h * 16 + g2 * 8;
-        const bool gv = rv && col < Knext;
-        float w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = gv ? c[g2 * 8 + j] * s_a : 0.f;
-        if (amul) {
-          const int cn = min(col, Knext - 8);
-          const float4 m0 = ldg4(amul + rcl * Knext + cn), m1 = ldg4(amul + rcl * Knext + cn + 4);
-          w[0] *= m0.x; w[1] *= m0.y; w[2] *= m0.z; w[3] *= m0.w;
-          w[4] *= m1.x; w[5] *= m1.y; w[6] *= m1.z; w[7] *= m1.w;
-        }
-        store_granule(A, row, col >> 3, w);
-      }
-    }
+    tmem_st16(t_lane + CARRY_COL, raw);
   };
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t r0 = (int64_t)tile * TM;
-    const int64_t r = r0 + row;
-    const bool rv = r < M;
+    const int64_t r0 = (int64_t)tile * TR;
+    const int64_t rb = r0 + e_loc;                          // first row of this thread's 16 values
+    const int nv = (int)max((int64_t)0, min((int64_t)16, M - rb));   // valid rows among them
+    const int64_t rbc = nv > 0 ? rb : M - 1;                // clamped row base / index for loads (always in range)
+    const int jmax = max(nv, 1) - 1;
+
+    // values of feature f for rows rb .. rb+15 -> the next operand (element (row, k = f)); zero beyond Knext / M
+    auto operand_from = [&](const float (&vals)[16], int Knext, float s_a, const float* amul, bool full) {
+      const bool kv = f < Knext;
+      const int fc = min(f, Knext - 1);
+      float w[16];
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = vals[j] * s_a;
+        if (amul) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] *= __ldg(amul + (rb + j) * Knext + fc);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = kv ? w[j] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = (kv && j < nv) ? vals[j] * s_a : 0.f;
+        if (amul) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] *= __ldg(amul + (rbc + min(j, jmax)) * Knext + fc);
+        }
+      }
+      if (f < (Knext > 64 ? 128 : 64)) {                    // inside the padded operand width
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) store_pair(X, e_loc + j, f, w[j], w[j + 1]);
+      }
+    };
+
 #pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
       const gemnet_chain_step& st = prog.step[s];
@@ -184,115 +211,101 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       if (st.n_terms > 0) {
         const int gpr = 8 * NKB;                                   // granules (8 columns) per operand row
         const bool fold_amul = st.amul != nullptr && !st.load_set_carry;
-        // PG (row, granule) pieces per thread and pass: all loads of a pass are in flight together.  The common fill
-        // (one plain or gathered term) takes its 4 pieces in ONE pass; fills with Hadamard factors or several terms
-        // take 2 per pass (registers).
+        // PG (row, granule) pieces per thread: 64 rows x 8|16 granules = 512|1024 pieces, all loads in flight together
         auto fill = [&](auto pg_tag) {
           constexpr int PG = decltype(pg_tag)::value;
-#pragma unroll 1
-          for (int p0 = tid; p0 < TM * gpr; p0 += PG * THREADS) {
-            float v[PG][8];
-            int prow[PG], pgr[PG];
+          float v[PG][8];
+          int prow[PG], pgr[PG];
 #pragma unroll
-            for (int h = 0; h < PG; ++h) {
-              const int p = p0 + h * THREADS;
-              prow[h] = p / gpr;
-              pgr[h] = p % gpr;
+          for (int h = 0; h < PG; ++h) {
+            const int p = tid + h * THREADS;
+            prow[h] = p / gpr;
+            pgr[h] = p % gpr;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[h][j] = 0.f;
-            }
-            for (int t = 0; t < st.n_terms; ++t) {
-              const gemnet_chain_term& tm = st.term[t];
-              float4 a0[PG], a1[PG];
-              if (tm.kind == 0) {
-#pragma unroll
-                for (int h = 0; h < PG; ++h) {
-                  // out-of-range pieces read a clamped (valid) address and are zeroed below: no divergent branches
-                  const int64_t rr = min(r0 + prow[h], M - 1);
-                  const int col = min(pgr[h] * 8, K - 8);
-                  const int64_t sr = tm.idx ? (int64_t)__ldg(tm.idx + rr) : rr;
-                  a0[h] = ldg4(tm.src + sr * K + col);
-                  a1[h] = ldg4(tm.src + sr * K + col + 4);
-                }
-                if (tm.mul) {
-#pragma unroll
-                  for (int h = 0; h < PG; ++h) {
-                    const int64_t rr = min(r0 + prow[h], M - 1);
-                    const int col = min(pgr[h] * 8, K - 8);
-                    const float4 m0 = ldg4(tm.mul + rr * K + col), m1 = ldg4(tm.mul + rr * K + col + 4);
-                    a0[h].x *= m0.x; a0[h].y *= m0.y; a0[h].z *= m0.z; a0[h].w *= m0.w;
-                    a1[h].x *= m1.x; a1[h].y *= m1.y; a1[h].z *= m1.z; a1[h].w *= m1.w;
-                  }
-                }
-              } else {  // outer product src[row] * mul[col]
-#pragma unroll
-                for (int h = 0; h < PG; ++h) {
-                  const int64_t rr = min(r0 + prow[h], M - 1);
-                  const int col = min(pgr[h] * 8, K - 8);
-                  const float a = __ldg(tm.src + rr);
-                  const float4 m0 = ldg4(tm.mul + col), m1 = ldg4(tm.mul + col + 4);
-                  a0[h] = make_float4(a * m0.x, a * m0.y, a * m0.z, a * m0.w);
-                  a1[h] = make_float4(a * m1.x, a * m1.y, a * m1.z, a * m1.w);
-                }
-              }
-              const float sc = tm.scale;
+            for (int j = 0; j < 8; ++j) v[h][j] = 0.f;
+          }
+          for (int t = 0; t < st.n_terms; ++t) {
+            const gemnet_chain_term& tm = st.term[t];
+            float4 a0[PG], a1[PG];
+            if (tm.kind == 0) {
 #pragma unroll
               for (int h = 0; h < PG; ++h) {
-                v[h][0] = fmaf(sc, a0[h].x, v[h][0]); v[h][1] = fmaf(sc, a0[h].y, v[h][1]);
-                v[h][2] = fmaf(sc, a0[h].z, v[h][2]); v[h][3] = fmaf(sc, a0[h].w, v[h][3]);
-                v[h][4] = fmaf(sc, a1[h].x, v[h][4]); v[h][5] = fmaf(sc, a1[h].y, v[h][5]);
-                v[h][6] = fmaf(sc, a1[h].z, v[h][6]); v[h][7] = fmaf(sc, a1[h].w, v[h][7]);
-              }
-            }
-#pragma unroll
-            for (int h = 0; h < PG; ++h) {
-              if (fold_amul) {
+                // out-of-range pieces read a clamped (valid) address and are zeroed below: no divergent branches
                 const int64_t rr = min(r0 + prow[h], M - 1);
                 const int col = min(pgr[h] * 8, K - 8);
-                const float4 m0 = ldg4(st.amul + rr * K + col), m1 = ldg4(st.amul + rr * K + col + 4);
-                v[h][0] *= m0.x; v[h][1] *= m0.y; v[h][2] *= m0.z; v[h][3] *= m0.w;
-                v[h][4] *= m1.x; v[h][5] *= m1.y; v[h][6] *= m1.z; v[h][7] *= m1.w;
+                const int64_t sr = tm.idx ? (int64_t)__ldg(tm.idx + rr) : rr;
+                a0[h] = ldg4(tm.src + sr * K + col);
+                a1[h] = ldg4(tm.src + sr * K + col + 4);
               }
-              const bool valid = r0 + prow[h] < M && pgr[h] * 8 < K;
+              if (tm.mul) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[h][j] = valid ? v[h][j] : 0.f;
-              store_granule(A, prow[h], pgr[h], v[h]);
+                for (int h = 0; h < PG; ++h) {
+                  const int64_t rr = min(r0 + prow[h], M - 1);
+                  const int col = min(pgr[h] * 8, K - 8);
+                  const float4 m0 = ldg4(tm.mul + rr * K + col), m1 = ldg4(tm.mul + rr * K + col + 4);
+                  a0[h].x *= m0.x; a0[h].y *= m0.y; a0[h].z *= m0.z; a0[h].w *= m0.w;
+                  a1[h].x *= m1.x; a1[h].y *= m1.y; a1[h].z *= m1.z; a1[h].w *= m1.w;
+                }
+              }
+            } else {  // outer product src[row] * mul[col]
+#pragma unroll
+              for (int h = 0; h < PG; ++h) {
+                const int64_t rr = min(r0 + prow[h], M - 1);
+                const int col = min(pgr[h] * 8, K - 8);
+                const float a = __ldg(tm.src + rr);
+                const float4 m0 = ldg4(tm.mul + col), m1 = ldg4(tm.mul + col + 4);
+                a0[h] = make_float4(a * m0.x, a * m0.y, a * m0.z, a * m0.w);
+                a1[h] = make_float4(a * m1.x, a * m1.y, a * m1.z, a * m1.w);
+              }
+            }
+            const float sc = tm.scale;
+#pragma unroll
+            for (int h = 0; h < PG; ++h) {
+              v[h][0] = fmaf(sc, a0[h].x, v[h][0]); v[h][1] = fmaf(sc, a0[h].y, v[h][1]);
+              v[h][2] = fmaf(sc, a0[h].z, v[h][2]); v[h][3] = fmaf(sc, a0[h].w, v[h][3]);
+              v[h][4] = fmaf(sc, a1[h].x, v[h][4]); v[h][5] = fmaf(sc, a1[h].y, v[h][5]);
+              v[h][6] = fmaf(sc, a1[h].z, v[h][6]); v[h][7] = fmaf(sc, a1[h].w, v[h][7]);
             }
           }
+#pragma unroll
+          for (int h = 0; h < PG; ++h) {
+            if (fold_amul) {
+              const int64_t rr = min(r0 + prow[h], M - 1);
+              const int col = min(pgr[h] * 8, K - 8);
+              const float4 m0 = ldg4(st.amul + rr * K + col), m1 = ldg4(st.amul + rr * K + col + 4);
+              v[h][0] *= m0.x; v[h][1] *= m0.y; v[h][2] *= m0.z; v[h][3] *= m0.w;
+              v[h][4] *= m1.x; v[h][5] *= m1.y; v[h][6] *= m1.z; v[h][7] *= m1.w;
+            }
+            const bool valid = r0 + prow[h] < M && pgr[h] * 8 < K;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[h][j] = valid ? v[h][j] : 0.f;
+            store_granule(X, prow[h], pgr[h], v[h]);
+          }
         };
-        const bool simple = st.n_terms == 1 && st.term[0].mul == nullptr && !fold_amul && NKB == 2;
-        if (simple) fill(std::integral_constant<int, 4>{});
-        else fill(std::integral_constant<int, 2>{});
+        if (NKB == 2) fill(std::integral_constant<int, 2>{});
+        else fill(std::integral_constant<int, 1>{});
         if (st.load_set_carry) {
           // the skip value is wanted in the epilogue's thread mapping: read it back from the (exact) operand split
           __syncthreads();
-          const int Wd = K > 64 ? 32 : 16;
+          float c[16];
+          const bool kin = f < 64 * NKB;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h * 16 >= Wd) break;
-            float c[16], lo[8], hi[8];
-            load_granule(A, row, (Wd * cg + h * 16) >> 3, lo);
-            load_granule(A, row, ((Wd * cg + h * 16) >> 3) + 1, hi);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              c[j] = lo[j];
-              c[8 + j] = hi[j];
-            }
-            carry_st(Wd * cg + h * 16, c);
-          }
-          if (st.amul) patch_from_carry(K, 1.0f, st.amul, rv ? r : M - 1, rv);
+          for (int j = 0; j < 16; ++j) c[j] = kin ? load_elem(X, e_loc + j, min(f, 64 * NKB - 1)) : 0.f;
+          carry_st(c);
+          if (st.amul) operand_from(c, K, 1.0f, st.amul, false);   // (each thread rewrites exactly the elements it read)
         }
       }
       stamp();  // step: operand written by this thread
+
       // ------------------------------------------------------------------ GEMM: operand complete -> thread 0 issues
-      fence_proxy_async();   // generic-proxy writes of A -> visible to the tensor-core (async) proxy
-      tc_fence_before();     // this thread's tcgen05.ld of the previous accumulators are done
+      fence_proxy_async();   // generic-proxy writes of X -> visible to the tensor-core (async) proxy
+      tc_fence_before();     // this thread's tcgen05.ld / st of the previous step are done
       __syncthreads();
       stamp();  // step: all threads' operand parts visible
       if (tid == 0) {
         tc_fence_after();
         const int Npad = N > 64 ? 128 : 64;
-        const uint32_t idesc = make_idesc(TM, Npad);
+        const uint32_t idesc = make_idesc(128, TR);     // D^T tile: 128 features x 64 rows
         const uint32_t d_corr = tmem_base + CORR_COL;
         for (int kb = 0; kb < NKB; ++kb) {
           uint32_t& use = kb ? wuse1 : wuse0;
@@ -300,20 +313,20 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
           ++use;
           stamp();  // step: weight chunk kb resident
           tc_fence_after();
-          const uint32_t sa = a_base + kb * CHUNK_BYTES;
-          const uint64_t a_h = make_desc(sa), a_m = make_desc(sa + SPLIT_BYTES), a_l = make_desc(sa + 2 * SPLIT_BYTES);
+          const uint32_t xa = x_base + kb * CHUNK_BYTES;
+          const uint64_t x_h = make_desc(xa), x_m = make_desc(xa + SPLIT_BYTES), x_l = make_desc(xa + 2 * SPLIT_BYTES);
           const uint32_t wb = w_base + kb * WSLOT_BYTES;
           const uint64_t w_h = make_desc(wb), w_m = make_desc(wb + Npad * 128), w_l = make_desc(wb + 2 * Npad * 128);
           const uint32_t d_main = tmem_base + kb * ACC_STRIDE;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle atom
-            umma_bf16(d_main, a_h + adv, w_h + adv, idesc, kk != 0);
-            umma_bf16(d_corr, a_h + adv, w_m + adv, idesc, (kb | kk) != 0);
-            umma_bf16(d_corr, a_m + adv, w_h + adv, idesc, 1u);
-            umma_bf16(d_corr, a_m + adv, w_m + adv, idesc, 1u);
-            umma_bf16(d_corr, a_h + adv, w_l + adv, idesc, 1u);
-            umma_bf16(d_corr, a_l + adv, w_h + adv, idesc, 1u);
+            umma_bf16(d_main, w_h + adv, x_h + adv, idesc, kk != 0);
+            umma_bf16(d_corr, w_h + adv, x_m + adv, idesc, (kb | kk) != 0);
+            umma_bf16(d_corr, w_m + adv, x_h + adv, idesc, 1u);
+            umma_bf16(d_corr, w_m + adv, x_m + adv, idesc, 1u);
+            umma_bf16(d_corr, w_h + adv, x_l + adv, idesc, 1u);
+            umma_bf16(d_corr, w_l + adv, x_h + adv, idesc, 1u);
           }
         }
         umma_commit(acc_full);
@@ -321,9 +334,9 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       }
       __syncwarp();
       mbar_wait(acc_full, gemm & 1u);
-      stamp();  // step: accumulators complete
       ++gemm;
       tc_fence_after();
+      stamp();  // step: accumulators complete
       const bool last = s + 1 == n_steps;
       if (tid == 0) {  // both weight slots are free now: stream the next GEMM's image in while the epilogue runs
         if (!last) fetch_weights(prog.step[s + 1]);
@@ -331,41 +344,39 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       }
 
       // ------------------------------------------------------------------ epilogue of this step's GEMM
-      const int Wd = N > 64 ? 32 : 16;                  // columns of this thread's patch
+      // thread = feature f, rows rb .. rb+15.  The pointwise program runs STAGE BY STAGE over the 16 values (feature
+      // tests outside the element loops): 16 independent dependency chains per stage, one uniform branch per
+      // disabled feature, and every global access is a coalesced line per warp (lanes = consecutive features).
       const int flags = st.flags;
       const int Knext = last ? 0 : prog.step[s + 1].K;
       const float c0f = kShrinkPerStep * (float)min(4, (K + 15) / 16);
       const float c1f = kShrinkPerStep * (float)max(0, min(4, (K - 64 + 15) / 16));
-      const int64_t rc = rv ? r : M - 1;   // loads of rows past the end read the last row (and are discarded)
-      const float* const pre0 = st.pre0; const float* const pre1 = st.pre1;
-      const float* const mul_early = st.mul_early; const float* const mul_late = st.mul_late;
-      const float* const post0 = st.post0; const float* const post1 = st.post1;
-      const float s_acc = st.s_acc, s_carry = st.s_carry;
-      const int64_t pr0 = pre0 ? (st.pre0_idx ? (int64_t)__ldg(st.pre0_idx + rc) : rc) : 0;
-      const int64_t pr1 = pre1 ? (st.pre1_idx ? (int64_t)__ldg(st.pre1_idx + rc) : rc) : 0;
-      const int64_t orow = st.out ? (st.out_idx ? (int64_t)__ldg(st.out_idx + rc) : rc) : 0;
-      float dot = 0.f;
+      const float s_acc = st.s_acc;
+      const bool need_d = st.dact != nullptr;
       if (st.dot_w) {
-        if (cg == 0) dotbuf[row] = 0.f;
+        if (tid < TR) dotbuf[tid] = 0.f;
         __syncthreads();
       }
-      const bool need_d = st.dact != nullptr;
-#pragma unroll
-      for (int piece = 0; piece < 2; ++piece) {
-        if (piece * 16 >= Wd) break;
-        // The pointwise program runs STAGE BY STAGE over the 16 values of the piece (feature tests outside the element
-        // loops): 16 independent dependency chains per stage keep the FMA / MUFU pipes busy with only 4 warps per
-        // scheduler, and a disabled feature costs one uniform branch instead of one per float4.
-        const int c0 = Wd * cg + piece * 16;            // first column of this 16-column piece
+      // a warp whose 32 features lie beyond this step's output AND the next operand has nothing to do
+      const bool warp_idle = 32 * q >= N && (last || 32 * q >= (Knext > 64 ? 128 : 64));
+      // FULL (warp-uniform): all 16 rows and all 32 features of the warp are in range -> no clamps, no predicates
+      auto epilogue = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const bool fv = FULL || f < N;
+        const int fc = FULL ? f : min(f, N - 1);
+        const int64_t RB = FULL ? rb : rbc;
+        const int64_t off0 = RB * N + fc;                  // element j at off0 + JJ(j) * N
+        auto OKJ = [&](int j) { return FULL || (fv && j < nv); };
+        auto JJ = [&](int j) { return FULL ? j : min(j, jmax); };
+
         float v[16], d[16];
         {
           uint32_t a0[16], a1[16], cc[16];
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-          tmem_ld16_nowait(ta, a0);
-          tmem_ld16_nowait(ta + CORR_COL, cc);
-          if (NKB == 2) tmem_ld16_nowait(ta + ACC_STRIDE, a1);
+          tmem_ld16_nowait(t_lane, a0);
+          tmem_ld16_nowait(t_lane + CORR_COL, cc);
+          if (NKB == 2) tmem_ld16_nowait(t_lane + ACC_STRIDE, a1);
           tmem_wait_ld();
-#pragma unroll
+  #pragma unroll
           for (int j = 0; j < 16; ++j) {
             // compensated sum (dense_tc.cu): the mean truncation loss of the main chains goes through the small
             // correction sum, then ONE round-to-nearest add per accumulator
@@ -378,148 +389,119 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
             v[j] = mainv + corr;
           }
         }
-        bool ok[4];
-        int cl[4];                                      // clamped column for loads (N is a multiple of 8)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          ok[f] = rv && c0 + 4 * f < N;
-          cl[f] = min(c0 + 4 * f, N - 4);
-        }
-        if (pre0) {
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const float4 t = ld4(pre0 + pr0 * N + cl[f]);
-            v[4 * f] += t.x; v[4 * f + 1] += t.y; v[4 * f + 2] += t.z; v[4 * f + 3] += t.w;
+        if (st.pre0) {
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int64_t rr = RB + JJ(j);
+            const int64_t pr = st.pre0_idx ? (int64_t)__ldg(st.pre0_idx + rr) : rr;
+            v[j] += st.pre0[pr * N + fc];
           }
         }
-        if (pre1) {
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const float4 t = ld4(pre1 + pr1 * N + cl[f]);
-            v[4 * f] += t.x; v[4 * f + 1] += t.y; v[4 * f + 2] += t.z; v[4 * f + 3] += t.w;
+        if (st.pre1) {
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int64_t rr = RB + JJ(j);
+            const int64_t pr = st.pre1_idx ? (int64_t)__ldg(st.pre1_idx + rr) : rr;
+            v[j] += st.pre1[pr * N + fc];
           }
         }
         if (flags & GEMNET_CHAIN_ACT) {
           if (need_d) {
-#pragma unroll
+  #pragma unroll
             for (int j = 0; j < 16; ++j) scaled_silu(v[j], v[j], d[j]);
           } else {
-#pragma unroll
+  #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = scaled_silu_value(v[j]);
           }
         } else if (need_d) {
-#pragma unroll
+  #pragma unroll
           for (int j = 0; j < 16; ++j) d[j] = 1.f;
         }
-        if (mul_early) {
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const float4 t = ldg4(mul_early + rc * N + cl[f]);
-            if (st.aux && ok[f])
-              *reinterpret_cast<float4*>(st.aux + r * N + c0 + 4 * f) =
-                  make_float4(v[4 * f] * s_acc, v[4 * f + 1] * s_acc, v[4 * f + 2] * s_acc, v[4 * f + 3] * s_acc);
-            v[4 * f] *= t.x; v[4 * f + 1] *= t.y; v[4 * f + 2] *= t.z; v[4 * f + 3] *= t.w;
-            if (need_d) {
-              d[4 * f] *= t.x; d[4 * f + 1] *= t.y; d[4 * f + 2] *= t.z; d[4 * f + 3] *= t.w;
-            }
+        if (st.mul_early) {
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float t = __ldg(st.mul_early + off0 + (int64_t)JJ(j) * N);
+            if (st.aux && OKJ(j)) st.aux[(rb + j) * N + f] = v[j] * s_acc;
+            v[j] *= t;
+            if (need_d) d[j] *= t;
           }
         }
         if (need_d) {  // stored here: the derivative's registers are free for the rest of the program
-#pragma unroll
-          for (int f = 0; f < 4; ++f)
-            if (ok[f])
-              *reinterpret_cast<float4*>(st.dact + r * N + c0 + 4 * f) =
-                  make_float4(d[4 * f] * s_acc, d[4 * f + 1] * s_acc, d[4 * f + 2] * s_acc, d[4 * f + 3] * s_acc);
+  #pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (OKJ(j)) st.dact[(rb + j) * N + f] = d[j] * s_acc;
         }
         if (flags & GEMNET_CHAIN_CARRY_ADD) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= s_acc;
           float c[16];
-          carry_ld(c0, c);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(c[j], s_carry, v[j]);
+          carry_ld(c);
+          const float sc = st.s_carry;
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_acc, c[j] * sc);
         } else {
-#pragma unroll
+  #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] *= s_acc;
         }
-        if (post0) {
+        if (st.post0) {
           const float sp = st.s_post0;
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const float4 t = ld4(post0 + rc * N + cl[f]);
-            v[4 * f] = fmaf(t.x, sp, v[4 * f]); v[4 * f + 1] = fmaf(t.y, sp, v[4 * f + 1]);
-            v[4 * f + 2] = fmaf(t.z, sp, v[4 * f + 2]); v[4 * f + 3] = fmaf(t.w, sp, v[4 * f + 3]);
-          }
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(st.post0[off0 + (int64_t)JJ(j) * N], sp, v[j]);
         }
-        if (post1) {
+        if (st.post1) {
           const float sp = st.s_post1;
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const float4 t = ld4(post1 + rc * N + cl[f]);
-            v[4 * f] = fmaf(t.x, sp, v[4 * f]); v[4 * f + 1] = fmaf(t.y, sp, v[4 * f + 1]);
-            v[4 * f + 2] = fmaf(t.z, sp, v[4 * f + 2]); v[4 * f + 3] = fmaf(t.w, sp, v[4 * f + 3]);
-          }
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(st.post1[off0 + (int64_t)JJ(j) * N], sp, v[j]);
         }
-        if (mul_late) {
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const float4 t = ldg4(mul_late + rc * N + cl[f]);
-            v[4 * f] *= t.x; v[4 * f + 1] *= t.y; v[4 * f + 2] *= t.z; v[4 * f + 3] *= t.w;
-          }
+        if (st.mul_late) {
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= __ldg(st.mul_late + off0 + (int64_t)JJ(j) * N);
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = ok[j >> 2] ? v[j] : 0.f;
+  #pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (OKJ(j)) ? v[j] : 0.f;
         if (st.out) {
           const float ss = st.s_store;
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            float4 o = make_float4(v[4 * f] * ss, v[4 * f + 1] * ss, v[4 * f + 2] * ss, v[4 * f + 3] * ss);
-            if (st.smul) {
-              const float4 t = ldg4(st.smul + rc * N + cl[f]);
-              o.x *= t.x; o.y *= t.y; o.z *= t.z; o.w *= t.w;
-            }
-            if (ok[f]) *reinterpret_cast<float4*>(st.out + orow * N + c0 + 4 * f) = o;
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float o = v[j] * ss;
+            if (st.smul) o *= __ldg(st.smul + off0 + (int64_t)JJ(j) * N);
+            const int64_t orow = st.out_idx ? (int64_t)__ldg(st.out_idx + RB + JJ(j)) : rb + j;
+            if (OKJ(j)) st.out[orow * N + f] = o;
           }
         }
         if (st.dot_w) {
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const float4 t = ldg4(st.dot_w + cl[f]);
-            dot = fmaf(v[4 * f], t.x, fmaf(v[4 * f + 1], t.y, fmaf(v[4 * f + 2], t.z, fmaf(v[4 * f + 3], t.w, dot))));
+          const float wv = __ldg(st.dot_w + fc);
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float p = v[j] * wv;                       // (0 for invalid features / rows)
+  #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            if (lane == 0) atomicAdd(&dotbuf[e_loc + j], p);
           }
         }
         if (flags & GEMNET_CHAIN_SET_CARRY) {
           const float sc = st.s_set_carry;
           float c[16];
-#pragma unroll
+  #pragma unroll
           for (int j = 0; j < 16; ++j) c[j] = v[j] * sc;
-          carry_st(c0, c);
+          carry_st(c);
         }
-        if ((flags & GEMNET_CHAIN_TO_A) && !last) {
-          // two granules of the next operand; its width equals this step's (Kpad_next == Npad)
-#pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            const int col = c0 + 8 * g2;
-            const bool gv = rv && col < Knext;
-            float w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = gv ? v[8 * g2 + j] * st.s_a : 0.f;
-            if (st.next_amul) {
-              const int cn = min(col, Knext - 8);
-              const float4 m0 = ldg4(st.next_amul + rc * Knext + cn), m1 = ldg4(st.next_amul + rc * Knext + cn + 4);
-              w[0] *= m0.x; w[1] *= m0.y; w[2] *= m0.z; w[3] *= m0.w;
-              w[4] *= m1.x; w[5] *= m1.y; w[6] *= m1.z; w[7] *= m1.w;
-            }
-            store_granule(A, row, col >> 3, w);
+        if (!last) {
+          if (flags & GEMNET_CHAIN_TO_A) {
+            operand_from(v, Knext, st.s_a, st.next_amul, FULL);
+          } else if (flags & GEMNET_CHAIN_A_FROM_CARRY) {
+            float c[16];
+            carry_ld(c);
+            operand_from(c, Knext, st.s_a, st.next_amul, FULL);
           }
         }
+      };
+      if (!warp_idle) {
+        if (nv == 16 && 32 * q + 32 <= N) epilogue(std::true_type{});
+        else epilogue(std::false_type{});
       }
-      if ((flags & GEMNET_CHAIN_A_FROM_CARRY) && !last) patch_from_carry(Knext, st.s_a, st.next_amul, rc, rv);
       stamp();  // step: epilogue of this thread done
       if (st.dot_w) {
-        atomicAdd(&dotbuf[row], dot);
         __syncthreads();
-        if (cg == 0 && rv) st.dot_out[r] = dotbuf[row] + (st.dot_in ? st.dot_in[r] : 0.f);
+        if (tid < TR && r0 + tid < M) st.dot_out[r0 + tid] = dotbuf[tid] + (st.dot_in ? st.dot_in[r0 + tid] : 0.f);
       }
     }
   }
@@ -557,12 +539,6 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
     GEMNET_REQUIRE(st.n_terms >= 0 && st.n_terms <= GEMNET_CHAIN_MAX_TERMS, "chain: too many operand terms");
     for (int t = 0; t < st.n_terms; ++t)
       GEMNET_REQUIRE(st.term[t].src && (st.term[t].kind == 0 || st.term[t].mul), "chain: operand term without source");
-    if (s + 1 < p.n_steps && p.step[s + 1].n_terms == 0 &&
-        (st.flags & (GEMNET_CHAIN_TO_A | GEMNET_CHAIN_A_FROM_CARRY))) {
-      const int kn = p.step[s + 1].K;
-      GEMNET_REQUIRE((st.flags & GEMNET_CHAIN_A_FROM_CARRY) || (kn > 64) == (st.N > 64),
-                     "chain: TO_A needs the next step's K to pad like this step's N");
-    }
     GEMNET_REQUIRE(!st.dot_w || st.dot_out, "chain: dot_w without dot_out");
   }
   static bool configured = false;
@@ -575,7 +551,7 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
     }
     configured = true;
   }
-  const int n_tiles = (int)ceil_div(p.M, chain::TM);
+  const int n_tiles = (int)ceil_div(p.M, chain::TR);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   cudaLaunchConfig_t cfg = {};

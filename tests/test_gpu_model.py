@@ -206,9 +206,11 @@ def test_engine_matches_autograd_path(name, dev):
     E1, F1 = model(inputs)
     E2, F2 = model.forward_autograd(inputs)
     assert inputs["R"].requires_grad is False
-    # engine = fused tcgen05 dense layers (unbiased, fp32-grade), autograd path = cuBLAS fp32 GEMMs
-    assert (E1 - E2).abs().max() <= 3e-6 * E2.abs().max()
-    assert (F1 - F2).abs().max() <= 5e-6 * F2.abs().max()
+    # engine = chain-fused tcgen05 dense stacks (exact operand split, compensated accumulation; ScaledSiLU through
+    # ex2.approx / rcp.approx, ~3e-7 per activation), autograd path = cuBLAS fp32 GEMMs + expf kernels
+    dE, dF = (E1 - E2).abs().max() / E2.abs().max(), (F1 - F2).abs().max() / F2.abs().max()
+    print(f"[{name}] engine vs autograd path: dE {dE:.2e} dF {dF:.2e}")
+    assert dE <= 1e-5 and dF <= 1.5e-5
     model.dense_algo = 0  # same engine on the cuBLAS GEMMs: only the gradient-accumulation order differs
     E3, F3 = model(inputs)
     model.dense_algo = 1
