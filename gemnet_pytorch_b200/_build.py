@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libgemnet_b200.so")
-SOURCES = ["prep.cu", "geometry.cu", "basis.cu", "scatter.cu", "segbilinear.cu", "segbilinear_tc.cu", "segbilinear_bwd_tc.cu", "dense_tc.cu", "chain_tc.cu", "quad.cu", "pointwise.cu", "graph_host.cpp"]
+SOURCES = ["prep.cu", "geometry.cu", "basis.cu", "scatter.cu", "segbilinear.cu", "segbilinear_tc.cu", "segbilinear_bwd_tc.cu", "dense_tc.cu", "chain_tc.cu", "rbf_fan.cu", "quad.cu", "pointwise.cu", "graph_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "--fmad=true", "-shared"]
 

@@ -255,34 +255,57 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
       const int64_t e0 = (int64_t)tile * TILE_M;
       asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");  // As of the previous tile is no longer read
 
-      // ---------------- phase 1: one warp per edge, lanes over the 64 columns (c = lane, lane + 32)
-      for (int r = warp; r < TILE_M; r += PRODUCER_WARPS) {
+      // ---------------- phase 1: one HALF-warp per edge (two independent segments per warp), 4 columns per lane.
+      // The gather indices of up to 16 triplets are fetched with one coalesced load per half-warp and broadcast by
+      // shuffles, so the row gathers do not wait for an index load, and they are issued four triplets at a time:
+      // 8 independent 128-bit requests in flight per warp instead of one dependent pair (the long-scoreboard stall of
+      // the round-1 kernel, profiles/ncu_r01_final_segbil_fwd_tc_large.txt).
+      for (int rp = warp * 2; rp < TILE_M; rp += PRODUCER_WARPS * 2) {
+        const int hl = lane & 15, half = lane >> 4;
+        const int r = rp + half;
         const int64_t e = e0 + r;
-        float A0[S], A1[S];
+        float A[S][4];
 #pragma unroll
-        for (int s = 0; s < S; ++s) A0[s] = A1[s] = 0.f;
+        for (int s = 0; s < S; ++s) A[s][0] = A[s][1] = A[s][2] = A[s][3] = 0.f;
+        int32_t beg = 0, end = 0;
         if (e < n_edges) {
-          const int32_t beg = __ldg(rowptr + e), end = __ldg(rowptr + e + 1);
-          int32_t idx_next = beg < end ? __ldg(expand + beg) : 0;
-          for (int32_t t = beg; t < end; ++t) {
-            const float* xr = x + (int64_t)idx_next * C + lane;
-            if (t + 1 < end) idx_next = __ldg(expand + t + 1);
-            const float x0 = __ldg(xr), x1 = __ldg(xr + 32);
-            const float* sp = sph + (int64_t)t * S;
+          beg = __ldg(rowptr + e);
+          end = __ldg(rowptr + e + 1);
+        }
+        // both halves run the same number of 16-triplet chunks (the longer segment decides): shuffles stay convergent
+        const int len = end - beg;
+        const int len_max = max(len, __shfl_xor_sync(0xffffffffu, len, 16));
+        for (int base = 0; base < len_max; base += 16) {
+          const int n = min(16, len - base);                       // triplets of this half in the chunk (may be <= 0)
+          const int32_t my_idx = hl < n ? __ldg(expand + beg + base + hl) : 0;
+          const int n_max = min(16, len_max - base);
+          for (int k0 = 0; k0 < n_max; k0 += 4) {
+            float4 xv[4];
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float w = __ldg(sp + s);
-              A0[s] = fmaf(w, x0, A0[s]);
-              A1[s] = fmaf(w, x1, A1[s]);
+            for (int u = 0; u < 4; ++u) {
+              const int32_t ix = __shfl_sync(0xffffffffu, my_idx, (half << 4) + ((k0 + u) & 15));
+              xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k0 + u < n) xv[u] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)ix * C) + hl);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (k0 + u < n) {
+                const float* sp = sph + (int64_t)(beg + base + k0 + u) * S;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                  const float w = __ldg(sp + s);
+                  A[s][0] = fmaf(w, xv[u].x, A[s][0]);
+                  A[s][1] = fmaf(w, xv[u].y, A[s][1]);
+                  A[s][2] = fmaf(w, xv[u].z, A[s][2]);
+                  A[s][3] = fmaf(w, xv[u].w, A[s][3]);
+                }
+              }
             }
           }
         }
-        float* arow = As + r * AS_LD + lane;
+        float* arow = As + r * AS_LD + 4 * hl;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          arow[s * C] = A0[s];
-          arow[s * C + 32] = A1[s];
-        }
+        for (int s = 0; s < S; ++s) *reinterpret_cast<float4*>(arow + s * C) = make_float4(A[s][0], A[s][1], A[s][2], A[s][3]);
       }
 
       // rbf_W1 block of this thread: rows i = 8*ih .. 8*ih+7, all 7 s  (56 contiguous floats, 16-byte aligned)

@@ -219,6 +219,7 @@ class _Run:
         # chain-fused blocks (fused.py): one launch per dense stack instead of one per layer
         self.fuse = self.tc and getattr(model, "chain_fusion", True) and fuse_ok(model)
         self.fuse_out = self.fuse and model.num_targets == 1
+        self.fan_out = {}   # id(level-2 rbf layer) -> its precomputed output (fused.RbfFan)
 
     # -- primitives
     def _tc_ok(self, W, x):
@@ -338,9 +339,14 @@ class _Run:
         return self.add_scale(layers.INV_SQRT_2, x_ca, x_ac)
 
     # -- chain-fused blocks (fused.py)
+    def rlin(self, dense, x):
+        """a projection of the radial basis: precomputed by the fan kernel, or a dense layer of its own"""
+        hit = self.fan_out.get(id(dense))
+        return hit if hit is not None else self.linear(dense, x)
+
     def quad_path_fused(self, qi, m, basis, algo):
         p = self.p
-        r4 = self.linear(qi.mlp_rbf, basis["rbf4"])
+        r4 = self.rlin(qi.mlp_rbf, basis["rbf4"])
         x = self.t.apply(fused.TripPrologue, m, r4, qi.dense_db, qi.down_projection, qi.scale_rbf.value())
         x = self.gather(x, p.id4_expand_intm_db, p.intm_db_perm, p.intm_db_rowptr)
         x = self.mul_scale(x, self.linear(qi.mlp_cbf, basis["cbf4"]), qi.scale_cbf.value())
@@ -357,7 +363,7 @@ class _Run:
         if not blk.triplets_only:
             # the quadruplet branch fills the GPU; the triplet branch (small, latency-bound launches) hides next to it
             x4 = t.on_side(lambda: self.quad_path_fused(blk.quad_interaction, m, basis, algo), lane=2)
-        r3 = self.linear(ti.mlp_rbf, basis["rbf3"])
+        r3 = self.rlin(ti.mlp_rbf, basis["rbf3"])
         x = A(fused.TripPrologue, m, r3, ti.dense_ba, ti.down_projection, ti.scale_rbf.value())
         x3 = self.bilinear(ti.mlp_cbf, basis["rbf_W1_3"], basis["sph3"], x, p.id3_expand, p.rowptr3,
                            ti.scale_cbf_sum.value(), algo)
@@ -366,7 +372,7 @@ class _Run:
             t.keep.append(x4)
         m2 = A(fused.Post, m, x3, x4, blk, p)
         au = blk.atom_update
-        rh = self.linear(au.dense_rbf, basis["rbf_h"])
+        rh = self.rlin(au.dense_rbf, basis["rbf_h"])
         x0 = A(fused.EdgeToAtomLazy, m2, rh, p.id_a, p.atom_perm, p.atom_rowptr, au.scale_sum.value(), None)
         h2, p_c, p_a = A(fused.AtomChain, x0, h, blk)
         m3 = A(fused.EdgeEmb, m2, p_c, p_a, blk, p)
@@ -375,7 +381,7 @@ class _Run:
     def output_block_fused(self, blk, m, rbf_out, E_prev, F_prev):
         """OutputBlock.forward (atom_update_block.py:157-193) accumulated onto the previous blocks' sums."""
         p, A = self.p, self.t.apply
-        ro = self.linear(blk.dense_rbf, rbf_out)
+        ro = self.rlin(blk.dense_rbf, rbf_out)
         if blk.direct_forces:
             x_E, x_F = A(fused.EdgeToAtomLazy, m, ro, p.id_a, p.atom_perm, p.atom_rowptr, blk.scale_sum.value(),
                          blk.scale_rbf.value())
@@ -510,14 +516,19 @@ def energy_and_forces(model, inputs):
 
         h = model.atom_emb(Z)
         m = run.edge_embedding(model.edge_emb, h, rbf)
+        use_fan = run.fuse and run.fuse_out and fused.rbf_fan_ok(model)
+        if use_fan:  # every projection of the radial basis in one launch (13 / 17 K=16 GEMMs per direction otherwise)
+            level1, uses = fused.fan_layout(model)
+            outs = A(fused.RbfFan, rbf, level1, uses)
+            run.fan_out = {id(d): o for (_, d), o in zip(uses, outs)}
         if not model.triplets_only:
-            basis["rbf4"] = run.linear(model.mlp_rbf4, rbf)
+            basis["rbf4"] = None if use_fan else run.linear(model.mlp_rbf4, rbf)
             basis["cbf4"] = run.linear(model.mlp_cbf4, cbf4)
             basis["rbf_W1_4"] = A(ops._DownProj, rad, model.mlp_sbf4.weight.detach(), layers.l_of_s_tensor(S, True, dev))
-        basis["rbf3"] = run.linear(model.mlp_rbf3, rbf)
+        basis["rbf3"] = None if use_fan else run.linear(model.mlp_rbf3, rbf)
         basis["rbf_W1_3"] = A(ops._DownProj, rad, model.mlp_cbf3.weight.detach(), layers.l_of_s_tensor(S, False, dev))
-        basis["rbf_h"] = run.linear(model.mlp_rbf_h, rbf)
-        rbf_out = run.linear(model.mlp_rbf_out, rbf)
+        basis["rbf_h"] = None if use_fan else run.linear(model.mlp_rbf_h, rbf)
+        rbf_out = None if use_fan else run.linear(model.mlp_rbf_out, rbf)
 
         # The output blocks (mostly atom-level layers: a dozen CTAs per launch) only feed the final sums, so they run
         # on the side lane, next to the following interaction block — forward and backward.

@@ -350,3 +350,61 @@ class EdgeToAtomLazy:
                                           None if g_had is None else g_had[0],
                                           0.0 if g_had is None else had_scale * g_had[1])
         return (g_m if ctx.needs_input_grad[0] else None), g_r, None, None, None, None, None
+
+
+class RbfFan:
+    """Every projection of the Bessel basis in one launch (rbf_fan.cu): level 1 = the shared mlp_rbf* layers
+    (gemnet.py:206-247), level 2 = the per-consumer layers (interaction_block.py:458-463,601-606;
+    atom_update_block.py:36-41,128).  Returns one (E, H) tensor per `uses` entry."""
+    fused = True
+
+    @staticmethod
+    def forward(ctx, rbf, level1, uses):
+        W1s = [d.linear.weight for d in level1]
+        W2s = [d.linear.weight for _, d in uses]
+        groups = [g for g, _ in uses]
+        out = ops.rbf_fan_fwd(rbf, W1s, W2s, groups)
+        ctx.save = (rbf.shape[0], rbf.shape[1], W1s, W2s, groups)
+        return tuple(out[j] for j in range(len(uses)))
+
+    @staticmethod
+    def backward_terms(ctx, tape, terms):
+        E, R, W1s, W2s, groups = ctx.save
+        gs = []
+        for t in terms:
+            if not t:
+                gs.append(None)
+                continue
+            g, sc, _, _ = tape.reduce_terms(t, 1, plain=True)[0]
+            gs.append(g if sc == 1.0 else ops.lincomb([(g, sc)]))
+        if all(g is None for g in gs):
+            return None, None, None
+        return ops.rbf_fan_bwd(E, R, W1s, W2s, groups, gs), None, None
+
+
+def rbf_fan_ok(model):
+    """the fan kernel covers emb_size_rbf = 16, equal consumer widths (multiple of 32, <= 512), <= 24 consumers"""
+    try:
+        uses = fan_layout(model)[1]
+        H = {d.linear.weight.shape[0] for _, d in uses}
+        return (model.mlp_rbf3.linear.weight.shape[0] == 16 and len(H) == 1 and next(iter(H)) % 32 == 0
+                and next(iter(H)) <= 512 and len(uses) <= 24 and model.mlp_rbf3.linear.weight.shape[1] <= 64
+                and all(d.linear.bias is None and not _is_silu(d) for _, d in uses))
+    except AttributeError:
+        return False
+
+
+def fan_layout(model):
+    """(level-1 layers, [(group, level-2 layer)]) of a GemNet: groups 0 rbf3, 1 rbf_h, 2 rbf_out, 3 rbf4"""
+    level1 = [model.mlp_rbf3, model.mlp_rbf_h, model.mlp_rbf_out]
+    if not model.triplets_only:
+        level1.append(model.mlp_rbf4)
+    uses = []
+    for blk in model.int_blocks:
+        uses.append((0, blk.trip_interaction.mlp_rbf))
+        uses.append((1, blk.atom_update.dense_rbf))
+        if not blk.triplets_only:
+            uses.append((3, blk.quad_interaction.mlp_rbf))
+    for ob in model.out_blocks:
+        uses.append((2, ob.dense_rbf))
+    return level1, uses

@@ -734,3 +734,35 @@ def materialize_term(g, idx, mul, scale):
         _check(_L().gemnet_gather_rows(_p(g), _p(_i32(idx)), n, F, _p(out), _stream()), "gemnet_gather_rows")
         return out if scale == 1.0 else lincomb([(out, scale)])
     return g if scale == 1.0 else lincomb([(g, scale)])
+
+
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def rbf_fan_fwd(rbf, W1s, W2s, groups):
+    """out (J, E, H): out[j] = (rbf W1s[groups[j]]^T) W2s[j]^T  (gemnet_rbf_fan_fwd)."""
+    import ctypes
+    rbf = _f32(rbf)
+    E, R = rbf.shape
+    J, H = len(W2s), W2s[0].shape[0]
+    W1s, W2s = [_f32(w) for w in W1s], [_f32(w) for w in W2s]
+    out = torch.empty(J, E, H, dtype=torch.float32, device=rbf.device)
+    _check(_L().gemnet_rbf_fan_fwd(_p(rbf), E, R, _ptr_array(W1s), len(W1s), _ptr_array(W2s),
+                                   (ctypes.c_int32 * J)(*groups), J, H, _p(out), _stream()), "gemnet_rbf_fan_fwd")
+    return out
+
+
+def rbf_fan_bwd(E, R, W1s, W2s, groups, g_outs):
+    """g_rbf (E, R) = sum_j (g_outs[j] W2s[j]) W1s[groups[j]]; g_outs[j] may be None (gemnet_rbf_fan_bwd)."""
+    import ctypes
+    J, H = len(W2s), W2s[0].shape[0]
+    W1s, W2s = [_f32(w) for w in W1s], [_f32(w) for w in W2s]
+    g_outs = [_f32(g) for g in g_outs]
+    dev = W2s[0].device
+    ws = torch.empty(J * E * 16, dtype=torch.float32, device=dev)
+    g_rbf = torch.empty(E, R, dtype=torch.float32, device=dev)
+    _check(_L().gemnet_rbf_fan_bwd(E, R, _ptr_array(W1s), len(W1s), _ptr_array(W2s), (ctypes.c_int32 * J)(*groups), J, H,
+                                   _ptr_array(g_outs), _p(ws), _p(g_rbf), _stream()), "gemnet_rbf_fan_bwd", kernels=2)
+    return g_rbf

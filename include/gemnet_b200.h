@@ -345,6 +345,26 @@ int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t flags, voi
 void gemnet_chain_set_profile_buffer(void* device_int64_x256);
 
 /* ------------------------------------------------------------------------------------------------
+ * N1: every projection of the radial basis in one launch.  GemNet maps rbf (E, num_radial) through a two-level
+ * bias-free linear fan: level 1 (shared) mlp_rbf3 / mlp_rbf_h / mlp_rbf_out [/ mlp_rbf4] (gemnet.py:206-247, 16 wide),
+ * level 2 (one per consumer) TripletInteraction.mlp_rbf / QuadrupletInteraction.mlp_rbf (interaction_block.py:458-463,
+ * 601-606), AtomUpdateBlock.dense_rbf / OutputBlock.dense_rbf (atom_update_block.py:36-41,128):
+ *     out[j] (E, H) = (rbf W1[group[j]]^T) W2[j]^T          j < n_out,  W1[g] (16, num_radial),  W2[j] (H, 16)
+ * `out` is one (n_out, E, H) buffer.  W1_host / W2_host / group_host are HOST arrays (of device pointers / ints); the
+ * backward takes the output gradients as a HOST array of n_out device pointers (NULL = no gradient for that output):
+ *     g_rbf (E, num_radial) = sum_j (g_out[j] W2[j]) W1[group[j]]     deterministic (fixed order over j)
+ * workspace: n_out * E * 16 floats.
+ * ---------------------------------------------------------------------------------------------- */
+#define GEMNET_RBF_FAN_MAX_OUT 24
+#define GEMNET_RBF_FAN_MAX_GROUPS 4
+int gemnet_rbf_fan_fwd(const float* rbf, int64_t n_edges, int32_t num_radial, const float* const* W1_host,
+                       int32_t n_groups, const float* const* W2_host, const int32_t* group_host, int32_t n_out, int32_t H,
+                       float* out, void* stream);
+int gemnet_rbf_fan_bwd(int64_t n_edges, int32_t num_radial, const float* const* W1_host, int32_t n_groups,
+                       const float* const* W2_host, const int32_t* group_host, int32_t n_out, int32_t H,
+                       const float* const* g_out_host, float* workspace, float* g_rbf, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * H0  host index builder: DataContainer.__getitem__ / get_triplets / get_quadruplets
  *     (gemnet/training/data_container.py:156-408, 411-489).  HOST function, native C++.
  * Input: molecules concatenated, R_host float64 (n_atoms,3), n_per_mol int32[n_mol].

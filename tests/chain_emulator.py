@@ -222,12 +222,26 @@ class _AddScaleCPU:
         return out * s
 
 
+def _rbf_fan_fwd(rbf, W1s, W2s, groups):
+    return torch.stack([(rbf @ W1s[g].t()) @ W2.t() for g, W2 in zip(groups, W2s)])
+
+
+def _rbf_fan_bwd(E, R, W1s, W2s, groups, g_outs):
+    tot = torch.zeros(E, R, dtype=W2s[0].dtype)
+    for g, W2, go in zip(groups, W2s, g_outs):
+        if go is not None:
+            tot = tot + (go @ W2) @ W1s[g]
+    return tot
+
+
 @contextlib.contextmanager
 def patched(dtype=None):
     """Run the fused engine's host logic on CPU tensors: every kernel launch it makes goes to a torch stand-in."""
     saved = (chain.RUNNER[0], dense_ops.PACKER[0], dense_ops.dense_tc, ops._SegBilinear, ops._EdgeToAtom.forward,
              ops.edge_to_atom_grad_r, ops.materialize_term, ops.segment_sum_rows, ops.lincomb, ops._GatherRows,
              ops._MulScale, ops._f32)
+    saved_fan = (ops.rbf_fan_fwd, ops.rbf_fan_bwd)
+    ops.rbf_fan_fwd, ops.rbf_fan_bwd = _rbf_fan_fwd, _rbf_fan_bwd
     chain.RUNNER[0] = lambda prog, settled: emulate(prog, settled, dtype)
     dense_ops.PACKER[0] = "emulated"
     dense_ops.dense_tc = _dense_tc
@@ -245,5 +259,6 @@ def patched(dtype=None):
         (chain.RUNNER[0], dense_ops.PACKER[0], dense_ops.dense_tc, ops._SegBilinear, fwd, ops.edge_to_atom_grad_r,
          ops.materialize_term, ops.segment_sum_rows, ops.lincomb, ops._GatherRows, ops._MulScale, ops._f32) = saved
         ops._EdgeToAtom.forward = staticmethod(fwd) if not isinstance(fwd, staticmethod) else fwd
+        ops.rbf_fan_fwd, ops.rbf_fan_bwd = saved_fan
         dense_ops._f32 = ops._f32
         dense_ops.invalidate()

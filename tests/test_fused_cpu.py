@@ -124,6 +124,38 @@ def test_fused_blocks_match_oracle_blocks(name):
             assert err < 1e-9, f"gradient {k}: {err:.2e}"
 
 
+@pytest.mark.parametrize("name", ["T", "Q"])
+def test_rbf_fan_layout_and_gradient(name):
+    """fused.RbfFan on the tape: every level-2 projection of the radial basis equals layer(level1(rbf)), and the
+    summed gradient w.r.t. rbf equals torch autograd's (including consumers without a gradient)."""
+    from gemnet_pytorch_b200 import engine, fused
+    kw, model, oracle, inp = setup(name, [1, 4], seed=5)
+    assert fused.rbf_fan_ok(model)
+    E = int(inp["id_c"].numel())
+    g = torch.Generator().manual_seed(1)
+    rbf = torch.randn(E, kw["num_radial"], generator=g, dtype=torch.float64)
+    level1, uses = fused.fan_layout(model)
+    ref_in = rbf.clone().requires_grad_(True)
+    ref = [torch.nn.functional.linear(torch.nn.functional.linear(ref_in, level1[gi].linear.weight), d.linear.weight)
+           for gi, d in uses]
+    Gs = [torch.randn(E, 128, generator=g, dtype=torch.float64) if j % 3 else None for j in range(len(uses))]
+    loss = sum((r * G).sum() for r, G in zip(ref, Gs) if G is not None)
+    g_ref = torch.autograd.grad(loss, ref_in)[0]
+    with ce.patched(), torch.no_grad():
+        tape = engine.Tape(enabled=True)
+        x = rbf.clone()
+        tape.require(x)
+        outs = tape.apply(fused.RbfFan, x, level1, uses)
+        for o, r in zip(outs, ref):
+            assert (o - r).abs().max() < 1e-12
+        for o, G in zip(outs, Gs):
+            if G is not None:
+                tape.add_grad(o, G, 0.5)
+                tape.add_grad(o, G, 0.5)
+        tape.backward()
+        assert (tape._take(id(x)) - g_ref).abs().max() / g_ref.abs().max() < 1e-12
+
+
 def test_fuse_ok_rejects_other_structures():
     from gemnet_pytorch_b200 import GemNet, engine
     kw = H.model_kwargs(H.load_npz("model_T.npz"))
