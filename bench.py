@@ -12,7 +12,10 @@ JSON line keys follow the driver contract; in addition
   roofline      the triplet segmented-bilinear kernel (row H7) at the bench batch: algorithmic bytes (SURVEY §8d
                 formula) / CUDA-event time of isolated launches vs MEASURED_PEAKS.json hbm_gbs
   roofline_large same kernel on a 2048-molecule batch (the batch-64 launch is latency-bound)
-  cpu_baseline  the oracle port (torch CPU restatement of the reference, all host threads) on the same batch
+  roofline_chain / roofline_h7_bwd  the chain-fused dense stack kernel and the tcgen05 backward of H7
+  cpu_baseline  the reference's own forward on the host cores: the UNMODIFIED reference (oracle/_ref, staged by
+                oracle/build_ref.sh, kind "reference") when present, else the oracle port (kind "port")
+  e2e           host molecules -> (E, F) on the host through GemNet.make_molecule_server, index construction INCLUDED
 `--impl reference` times that CPU path on rank 0 only.
 """
 import argparse
@@ -158,6 +161,63 @@ def time_dense(M, dev, flush, reps):
     return float(np.mean(times)), 4 * M * 128 * 3 + 6 * 128 * 128, 2 * M * 128 * 128
 
 
+def time_h7_backward(plan, dev, flush, reps):
+    """CUDA-event time of the tcgen05 backward of the triplet bilinear layer (segsum -> dB GEMM on tensor cores + dA /
+    g_rbf_W1 -> unit kernel); algorithmic bytes: every operand and every gradient once."""
+    from gemnet_pytorch_b200 import ops
+    E, T = plan.n_edges, plan.n_triplets
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(E, 64, generator=g).to(dev).requires_grad_(True)
+    sph = torch.randn(T, 7, generator=g).to(dev).requires_grad_(True)
+    rw = torch.randn(E, 16, 7, generator=g).to(dev).requires_grad_(True)
+    W = (torch.randn(64, 16, 64, generator=g) / 32).to(dev)
+    go_ = torch.randn(E, 64, generator=g).to(dev)
+    times = []
+    for it in range(reps + 3):
+        out = ops.segmented_bilinear(x, sph, rw, W, plan.id3_expand, plan.rowptr3, 1.0, 1)
+        flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        torch.autograd.grad(out, [x, sph, rw], go_)
+        e.record()
+        e.synchronize()
+        if it >= 3:
+            times.append(s.elapsed_time(e) * 1e-3)
+    bts = 4 * (E * 64 + E * 64 + T * 7 + E * 112 + 64 * 16 * 64) + 4 * (E * 64 + T * 7 + E * 112) + 4 * (T + E + 1)
+    return float(np.mean(times)), bts
+
+
+def time_chain(M, dev, flush, reps):
+    """CUDA-event time of one chain-fused launch in the shape of fused.Post's forward (3 operand fills, 7 GEMM steps of
+    128 -> 128 with ScaledSiLU, every step storing its activation derivative); algorithmic bytes: the three inputs, the
+    seven derivative tensors, the output, the seven packed weight images."""
+    from gemnet_pytorch_b200 import chain, dense_ops
+    from gemnet_pytorch_b200.chain import ACT, CARRY_ADD, SET_CARRY, TO_A, Program, Step, Term
+    g = torch.Generator(device="cpu").manual_seed(0)
+    xs = [torch.randn(M, 128, generator=g).to(dev) for _ in range(3)]
+    pw = [dense_ops.packed_weight((torch.randn(128, 128, generator=g) / 11).to(dev), False) for _ in range(7)]
+    bufs = [torch.empty(M, 128, device=dev) for _ in range(8)]
+    steps = [Step(pw[0], terms=[Term(xs[0])], flags=ACT | SET_CARRY, dact=bufs[1]),
+             Step(pw[1], terms=[Term(xs[1])], flags=ACT | CARRY_ADD | SET_CARRY, dact=bufs[2]),
+             Step(pw[2], terms=[Term(xs[2])], flags=ACT | CARRY_ADD | SET_CARRY | TO_A, dact=bufs[3])]
+    for j in range(3, 7):
+        steps.append(Step(pw[j], flags=ACT | CARRY_ADD | SET_CARRY | TO_A, dact=bufs[1 + j]))
+    steps[-1].out = bufs[0]
+    prog = Program(M, steps)
+    for _ in range(3):
+        chain.run(prog)
+    times = []
+    for _ in range(reps):
+        flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        chain.run(prog)
+        e.record()
+        e.synchronize()
+        times.append(s.elapsed_time(e) * 1e-3)
+    return float(np.mean(times)), 4 * M * 128 * (3 + 7 + 1) + 7 * 6 * 128 * 128, 7 * 2 * M * 128 * 128
+
+
 def ncu_traffic_large(n_mol):
     """dram__bytes_read.sum + dram__bytes_write.sum of the H7 tcgen05 kernel on the 2048-molecule batch, from the
     committed `ncu --set full` capture of the same launch (profiles/final_run.sh); None for any other size."""
@@ -191,8 +251,24 @@ def pick_cpu_threads(fn):
     return best, avail
 
 
+def reference_cpu_model(kw, sd):
+    """(predict_fn, kind): the UNMODIFIED reference's GemNet on CPU through oracle/ref_shims.py when it is staged
+    (oracle/_ref, oracle/build_ref.sh) or present (/root/reference) — kind "reference" — else the oracle port."""
+    from oracle import gemnet_oracle as go
+    from oracle import ref_shims
+    if ref_shims.reference_available():
+        RefGemNet, _ = ref_shims.load_reference()
+        kw_ref = dict(kw, scale_file=os.path.join(ref_shims.REFERENCE_ROOT, "pretrained", "scaling_factors.json"))
+        model = RefGemNet(**kw_ref)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        return (lambda inp: model.predict(dict(inp))), "reference"
+    orc = go.OracleGemNet(kw, sd)
+    return orc.predict, "port"
+
+
 def run_reference(args, kw, rank, world):
-    """CPU arm: the oracle port of the reference forward (torch CPU, all host threads) on rank 0 only."""
+    """CPU arm: the reference's own forward (energy + autograd forces) on the host cores, rank 0 only."""
     if rank != 0:
         return
     from oracle import gemnet_oracle as go
@@ -201,23 +277,25 @@ def run_reference(args, kw, rank, world):
     t0 = time.perf_counter()
     inputs = gr.to_torch_inputs(gr.build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]))
     t_index = time.perf_counter() - t0
-    model = go.OracleGemNet(kw, go.synthetic_state_dict(kw, seed=1234))
-    threads, avail = pick_cpu_threads(lambda: model.predict(inputs))
+    predict, kind = reference_cpu_model(kw, go.synthetic_state_dict(kw, seed=1234))
+    threads, avail = pick_cpu_threads(lambda: predict(inputs))
     for _ in range(args.warmup):
-        model.predict(inputs)
+        predict(inputs)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        model.predict(inputs)
+        predict(inputs)
     dt = time.perf_counter() - t0
     val = args.batch * args.steps / dt
+    what = ("the unmodified reference GemNet.predict (oracle/_ref via oracle/ref_shims.py)" if kind == "reference"
+            else "oracle/gemnet_oracle.py (torch CPU restatement of the reference)")
     line = {
         "impl": "reference", "metric": "molecules_per_sec", "value": val, "unit": "molecules/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, kw, "cpu"),
-        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": threads, "host_cores": avail, "kind": "port",
-                         "sample": f"{args.steps} energy+force evaluations of the same {args.batch}-molecule batch "
-                                   f"(oracle/gemnet_oracle.py, torch CPU fp32; index build {t_index * 1e3:.0f} ms excluded)"},
+        "config": workload_config(args, kw),
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": threads, "host_cores": avail, "kind": kind,
+                         "sample": f"{args.steps} energy+force evaluations of the same {args.batch}-molecule batch with "
+                                   f"{what}, torch CPU fp32; index build {t_index * 1e3:.0f} ms excluded"},
         "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -285,12 +363,12 @@ def run_train(args, kw, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def workload_config(args, kw, where):
+def workload_config(args, kw):
     name = "GemNet-T" if kw["triplets_only"] else "GemNet-Q"
     return {"workload": f"{name} energy+force inference (forces = -dE/dR), COLL-shaped synthetic batch={args.batch} "
                         f"molecules/GPU, emb_size=128, cutoff 5 A",
             "batch_per_gpu": args.batch, "l2": "flushed (256 MiB write) between timed iterations",
-            "weights": "seeded synthetic (random-init architecture weights)", "device": where}
+            "weights": "seeded synthetic (random-init architecture weights)"}
 
 
 def main():
@@ -389,60 +467,65 @@ def main():
     t_eager = timed(lambda: model(inputs)) if use_graph else t_dev
     launches = launches_per_step * args.steps
 
-    # ---------------- end-to-end timing: pinned host dict -> device -> index plan -> forward -> E,F back on the host.
-    # Four DIFFERENT batches are cycled so that no per-topology state (index plan, packed buffers) carries over.
-    host_batches = [host_inputs]
-    for j in range(1, 4):
-        Rj, Zj = synthetic_molecules(args.batch, 1234 + rank + 1000 * j)
-        host_batches.append(build_batch(Rj, Zj, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"], pin_memory=True))
-    h2d = sum(sum(v.numel() * v.element_size() for v in hb.values()) for hb in host_batches) / len(host_batches)
-    d2h = 0
-    # The public call for that is GemNet.make_serving(capacity): ONE captured graph (H2D from pinned staging, index
-    # plan, E+F, D2H) serving every batch that fits the capacity; the batch is padded on the host with inert entries
-    # (graph.pad_batch).  Quadruplet models have no static-shape path yet: eager predict().
-    serving = None
-    if kw["triplets_only"]:
-        # capacity buckets on a geometric ladder (12% steps), one captured graph per bucket, captured on first use
-        # (during the warm-up below); nothing is fitted to these four batches except the atom capacity
-        serving = model.make_serving_pool(args.batch, max(int(hb["Z"].shape[0]) for hb in host_batches) + 64)
+    # ---------------- end-to-end timing through the public call a user makes (GemNet.make_molecule_server):
+    #   host molecules (R, Z lists) -> index construction (row H0, native builder, worker threads) -> padding into pinned
+    #   staging -> ONE graph launch (H2D, index plan, E+F, D2H) -> (E, F) on the host.
+    # Eight DIFFERENT batches are cycled (no per-topology state carries over).  Timed with the HOST clock between
+    # synchronisations (perf_counter); the L2 flush kernel of every step runs INSIDE the timed region (conservative).
+    #   e2e.value       pipelined throughput: stream() overlaps the index construction of the next batches with the GPU
+    #   e2e.latency_ms  one batch at a time, index construction inline (what an MD step pays)
+    mol_batches = [(Rl, Zl)] + [synthetic_molecules(args.batch, 1234 + rank + 1000 * j) for j in range(1, 8)]
+    max_atoms = max(sum(len(z) for z in Zb) for _, Zb in mol_batches) + 64
+    server = model.make_molecule_server(args.batch, max_atoms, workers=3)
+    for Rb, Zb in mol_batches:               # warm-up: captures the graph of every capacity bucket these batches need
+        server(Rb, Zb)
+    for _ in server.stream(mol_batches[:4]):
+        pass
+    h2d, d2h = server.h2d_bytes, server.d2h_bytes
+    if server.pool is None:
+        hb = server.build(Rl, Zl)
+        h2d = sum(v.numel() * v.element_size() for v in hb.values())
 
-    def e2e_step(hb):
-        if serving is not None:
-            return serving(hb)  # host pad -> graph replay -> stream sync -> (E, F) on the host
-        return model.predict({k: v.to(dev, non_blocking=True) for k, v in hb.items()})
-
-    for j in range(max(4, args.warmup)):
-        e2e_step(host_batches[j % 4])
-    if serving is not None:
-        h2d, d2h = serving.h2d_bytes, serving.d2h_bytes
-    barrier()
-    ev2 = []
-    for j in range(args.steps):
-        flush()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        E_h, F_h = e2e_step(host_batches[j % 4])
-        e.record()
-        ev2.append((s, e))
-        if serving is None:
-            d2h = E_h.numel() * 4 + F_h.numel() * 4
-    barrier()
-    t_e2e = sum(s.elapsed_time(e) for s, e in ev2) * 1e-3
-
-    # the same four batches through the eager public call (per-batch device plan, ~480 launches from Python)
-    t_e2e_eager = None
-    if serving is not None:
-        ev3 = []
-        for j in range(max(4, args.warmup) + args.steps):
+    def flushed(batches):
+        for b in batches:
             flush()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
+            yield b
+
+    barrier()
+    t0 = time.perf_counter()
+    n_done = 0
+    for E_h, F_h in server.stream(flushed(mol_batches[j % 8] for j in range(args.steps))):
+        n_done += 1
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if server.pool is None:
+        d2h = E_h.numel() * 4 + F_h.numel() * 4
+    lat = []
+    for j in range(min(args.steps, 10)):
+        flush()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        server(*mol_batches[j % 8])
+        lat.append(time.perf_counter() - t0)
+    t_lat = float(np.median(lat))
+    # the reference-format host batch (indices already built) through the serving pool alone, and through eager predict
+    host_batches = [server.build(*mb) for mb in mol_batches[:4]]
+    t_serv = t_e2e_eager = None
+    if server.pool is not None:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for j in range(args.steps):
+            flush()
+            server.pool(host_batches[j % 4])
+        t_serv = time.perf_counter() - t0
+        for j in range(4):
             model.predict({k: v.to(dev, non_blocking=True) for k, v in host_batches[j % 4].items()})
-            e.record()
-            if j >= max(4, args.warmup):
-                ev3.append((s, e))
-        barrier()
-        t_e2e_eager = sum(s.elapsed_time(e) for s, e in ev3) * 1e-3
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for j in range(args.steps):
+            flush()
+            model.predict({k: v.to(dev, non_blocking=True) for k, v in host_batches[j % 4].items()})
+        t_e2e_eager = time.perf_counter() - t0
 
     if world > 1:
         tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
@@ -460,14 +543,17 @@ def main():
         "metric": "molecules_per_sec", "value": mols / t_dev, "unit": "molecules/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, kw, torch.cuda.get_device_name(dev)),
+        "config": workload_config(args, kw), "device": torch.cuda.get_device_name(dev),
         "clocks": clocks,
         "e2e": {"value": mols / t_e2e, "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3,
-                "host_index_build_ms": t_index * 1e3,
-                "path": ("GemNet.make_serving_pool: static-shape CUDA graphs incl. H2D/plan/D2H, host-side padding to "
-                         f"capacity buckets (edges, triplets) = {sorted(serving.runners)}")
-                if serving is not None else "GemNet.predict (eager)",
+                "latency_ms": t_lat * 1e3, "host_index_build_ms": t_index * 1e3,
+                "index_construction": "INCLUDED (row H0, native builder on 3 worker threads, pipelined by stream())",
+                "clock": "host perf_counter between synchronisations; the per-step L2 flush kernel is inside the region",
+                "path": ("GemNet.make_molecule_server: host (R, Z) lists -> H0 -> static-shape CUDA graph pool (H2D, "
+                         f"index plan, E+F, D2H), capacity buckets (edges, triplets) = {sorted(server.pool.runners)}")
+                if server.pool is not None else "GemNet.make_molecule_server: H0 -> GemNet.predict (eager)",
+                "serving_pool_only_ms_per_step": None if t_serv is None else t_serv / args.steps * 1e3,
                 "eager_ms_per_step": None if t_e2e_eager is None else t_e2e_eager / args.steps * 1e3},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": launches_per_step,
@@ -493,6 +579,18 @@ def main():
                               "rows": plan.n_edges, "bound": "hbm", "achieved": b_d / t_d / 1e9, "peak": hbm_peak,
                               "unit": "GB/s", "frac": b_d / t_d / 1e9 / hbm_peak, "us_per_launch": t_d * 1e6,
                               "bytes_per_launch": b_d, "fp32_tflops": f_d / t_d / 1e12, "traffic": None}
+    t_c, b_c, f_c = time_chain(plan.n_edges, dev, flush, 20)
+    line["roofline_chain"] = {"kernel": "chain_tc_kernel (7 fused dense layers: 3 operand fills, ScaledSiLU + derivative "
+                                        "stores, skip connections; tcgen05 bf16x3x3, transposed tiles)",
+                              "rows": plan.n_edges, "bound": "hbm", "achieved": b_c / t_c / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": b_c / t_c / 1e9 / hbm_peak, "us_per_launch": t_c * 1e6,
+                              "bytes_per_launch": b_c, "fp32_tflops": f_c / t_c / 1e12, "traffic": None,
+                              "note": "latency-bound at batch 64 (128 tiles, 7 dependent GEMM steps per tile)"}
+    t_b, b_b = time_h7_backward(plan, dev, flush, 20)
+    line["roofline_h7_bwd"] = {"kernel": "segsum + segbil_bwd_edges_tc_kernel (dB = g W'^T on tcgen05) + segbil_bwd_units",
+                               "bound": "hbm", "achieved": b_b / t_b / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": b_b / t_b / 1e9 / hbm_peak, "us_per_call": t_b * 1e6, "bytes_per_call": b_b,
+                               "traffic": None}
     if args.large_batch and world == 1:
         Rb, Zb = synthetic_molecules(args.large_batch, 4321)
         big = {k: v.to(dev) for k, v in build_batch(Rb, Zb, kw["cutoff"], kw["int_cutoff"], True).items()}
@@ -506,6 +604,14 @@ def main():
                                   "tensor_frac_of_bf16_peak": 3 * 2 * bplan.n_edges * 1024 * 64 / t_k / 1e12 / tc_peak,
                                   "fp32_cuda_core_kernel_us": t_k0 * 1e6,
                                   "bytes_per_launch": bts, "traffic": ncu_traffic_large(args.large_batch)}
+        t_c, b_c, f_c = time_chain(bplan.n_edges, dev, flush, 5)
+        line["roofline_chain_large"] = {"rows": bplan.n_edges, "bound": "hbm", "achieved": b_c / t_c / 1e9, "peak": hbm_peak,
+                                        "unit": "GB/s", "frac": b_c / t_c / 1e9 / hbm_peak, "us_per_launch": t_c * 1e6,
+                                        "bytes_per_launch": b_c, "fp32_tflops": f_c / t_c / 1e12,
+                                        "tensor_frac_of_bf16_peak": 6 * f_c / t_c / 1e12 / tc_peak}
+        t_b, b_b = time_h7_backward(bplan, dev, flush, 5)
+        line["roofline_h7_bwd_large"] = {"bound": "hbm", "achieved": b_b / t_b / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": b_b / t_b / 1e9 / hbm_peak, "us_per_call": t_b * 1e6, "bytes_per_call": b_b}
         t_d, b_d, f_d = time_dense(bplan.n_edges, dev, flush, 10)
         line["roofline_dense_large"] = {"rows": bplan.n_edges, "bound": "hbm", "achieved": b_d / t_d / 1e9,
                                         "peak": hbm_peak, "unit": "GB/s", "frac": b_d / t_d / 1e9 / hbm_peak,
@@ -513,22 +619,23 @@ def main():
                                         "fp32_tflops": f_d / t_d / 1e12}
         del big, bplan
 
-    # ---------------- CPU baseline beside it (oracle port of the reference path, bounded sample)
+    # ---------------- CPU baseline beside it: the reference's own forward on the host cores (bounded sample)
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import gemnet_oracle as go  # the checker / CPU baseline: the only use of oracle/ in this arm
-        from oracle import graph_oracle as gr
+        from oracle import graph_oracle as gr  # the checker / CPU baseline: the only use of oracle/ in this arm
         cpu_inputs = gr.to_torch_inputs(gr.build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]))
-        orc = go.OracleGemNet(kw, sd)
-        threads, avail = pick_cpu_threads(lambda: orc.predict(cpu_inputs))
+        predict, kind = reference_cpu_model(kw, sd)
+        threads, avail = pick_cpu_threads(lambda: predict(cpu_inputs))
         n_rep, t0 = 0, time.perf_counter()
         while n_rep < 5 or (time.perf_counter() - t0 < 10 and n_rep < 40):
-            E_c, F_c = orc.predict(cpu_inputs)
+            E_c, F_c = predict(cpu_inputs)
             n_rep += 1
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": args.batch * n_rep / dt, "unit": "molecules/s",
-                                "cores": threads, "host_cores": avail, "kind": "port",
-                                "sample": f"{n_rep} energy+force evaluations of the same {args.batch}-molecule batch "
-                                          "with oracle/gemnet_oracle.py (torch CPU fp32 restatement of the reference)"}
+                                "cores": threads, "host_cores": avail, "kind": kind,
+                                "sample": f"{n_rep} energy+force evaluations of the same {args.batch}-molecule batch with "
+                                          + ("the unmodified reference GemNet.predict (oracle/_ref, torch CPU fp32)"
+                                             if kind == "reference" else
+                                             "oracle/gemnet_oracle.py (torch CPU fp32 restatement of the reference)")}
         # parity of the timed GPU result against the CPU result of the same batch
         E_g, F_g = model.predict(inputs)
         line["parity_vs_cpu"] = {"rel_dE": float((E_g - E_c).abs().max() / E_c.abs().max()),

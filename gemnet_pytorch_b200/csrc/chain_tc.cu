@@ -45,7 +45,7 @@ constexpr int X_BYTES = 2 * CHUNK_BYTES;       // 49152
 constexpr int WSLOT_BYTES = 3 * 128 * 128;     // 49152: one 64-k chunk of a (<=128)-row weight image, three splits
 constexpr int W_SLOTS = 2;
 constexpr int THREADS = 512;
-constexpr int MISC_BYTES = 1024;               // barriers, TMEM slot, dot buffer
+constexpr int MISC_BYTES = 2048;               // barriers, TMEM slot, dot buffer (4 quadrants x TR floats)
 constexpr int SMEM_BYTES = 1024 + X_BYTES + W_SLOTS * WSLOT_BYTES + MISC_BYTES;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t ACC_STRIDE = 64, CORR_COL = 128, CARRY_COL = 192;
@@ -102,7 +102,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   auto w_full = [&](int s) { return bar_base + 8u + 8u * s; };
   const uint32_t tmem_slot = bar_base + 32;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + X_BYTES + W_SLOTS * WSLOT_BYTES + 32);
-  float* dotbuf = reinterpret_cast<float*>(sm + X_BYTES + W_SLOTS * WSLOT_BYTES + 64);  // TR floats
+  float* dotbuf = reinterpret_cast<float*>(sm + X_BYTES + W_SLOTS * WSLOT_BYTES + 64);  // [4 quadrants][TR] floats
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // diagnostics (gemnet_chain_set_profile_buffer): thread 0 of CTA 0 records clock64() at the phase boundaries
@@ -353,8 +353,8 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       const float c1f = kShrinkPerStep * (float)max(0, min(4, (K - 64 + 15) / 16));
       const float s_acc = st.s_acc;
       const bool need_d = st.dact != nullptr;
-      if (st.dot_w) {
-        if (tid < TR) dotbuf[tid] = 0.f;
+      if (st.dot_w) {   // idle / partial warps must not leave stale partial sums
+        if (tid < 4 * TR) dotbuf[tid] = 0.f;
         __syncthreads();
       }
       // a warp whose 32 features lie beyond this step's output AND the next operand has nothing to do
@@ -474,7 +474,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
             float p = v[j] * wv;                       // (0 for invalid features / rows)
   #pragma unroll
             for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-            if (lane == 0) atomicAdd(&dotbuf[e_loc + j], p);
+            if (lane == 0) dotbuf[q * TR + e_loc + j] = p;   // one writer per (quadrant, row): deterministic
           }
         }
         if (flags & GEMNET_CHAIN_SET_CARRY) {
@@ -501,7 +501,9 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       stamp();  // step: epilogue of this thread done
       if (st.dot_w) {
         __syncthreads();
-        if (tid < TR && r0 + tid < M) st.dot_out[r0 + tid] = dotbuf[tid] + (st.dot_in ? st.dot_in[r0 + tid] : 0.f);
+        if (tid < TR && r0 + tid < M)
+          st.dot_out[r0 + tid] = ((dotbuf[tid] + dotbuf[TR + tid]) + (dotbuf[2 * TR + tid] + dotbuf[3 * TR + tid])) +
+                                 (st.dot_in ? st.dot_in[r0 + tid] : 0.f);
       }
     }
   }

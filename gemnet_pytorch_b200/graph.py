@@ -19,6 +19,7 @@ from . import _lib, ops
 
 _PLAN_KEY = "_gemnet_b200_plan"
 _VALIDATED_KEY = "_gemnet_b200_indices_validated"  # set by pad_batch: the host already checked the index order
+_REBUILD_KEY = "_gemnet_b200_rebuild_plan"  # serving: the static device buffers get new contents, rebuild the plan
 _CHECK_SORTED = os.environ.get("GEMNET_B200_CHECK_INDICES", "1") != "0"
 
 TRIPLET_KEYS = ("id_undir", "id_swap", "id_c", "id_a", "id3_expand_ba", "id3_reduce_ca", "Kidx3")
@@ -145,15 +146,26 @@ class GraphPlan:
                     "(batch_seg, id3_reduce_ca, id4_reduce_ca must be non-decreasing and in range)")
 
 
+_plans = {}  # (pointers, sizes, model kind) -> (weakref of the id_c tensor, plan); a few entries, least recent out
+
+
 def get_plan(inputs, triplets_only):
-    plan = inputs.get(_PLAN_KEY)
-    key = (inputs["id_c"].data_ptr(), inputs["id3_reduce_ca"].data_ptr(), int(inputs["id_c"].numel()),
-           int(inputs["id3_reduce_ca"].numel()), triplets_only)
-    if plan is None or plan[0] != key:
-        check = _CHECK_SORTED and not inputs.get(_VALIDATED_KEY, False)  # the device check ends in a host sync
-        plan = (key, GraphPlan(inputs, triplets_only, check=check))
-        inputs[_PLAN_KEY] = plan
-    return plan[1]
+    """The device plan of a batch, cached per index-tensor identity.  The cache is NOT kept in the caller's dict: the
+    reference's Trainer.dict2device (trainer.py:312-318) calls `.to(device)` on every value of it."""
+    import weakref
+    id_c, red = inputs["id_c"], inputs["id3_reduce_ca"]
+    key = (id_c.data_ptr(), red.data_ptr(), int(id_c.numel()), int(red.numel()), triplets_only)
+    hit = None if inputs.get(_REBUILD_KEY, False) else _plans.get(key)
+    if hit is not None and hit[0]() is id_c:       # same tensor object (not merely a recycled address)
+        _plans[key] = _plans.pop(key)              # most recent last
+        return hit[1]
+    check = _CHECK_SORTED and not inputs.get(_VALIDATED_KEY, False)  # the device check ends in a host sync
+    plan = GraphPlan(inputs, triplets_only, check=check)
+    _plans.pop(key, None)
+    while len(_plans) >= 4:
+        _plans.pop(next(iter(_plans)))
+    _plans[key] = (weakref.ref(id_c), plan)
+    return plan
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ class GemNet(torch.nn.Module):
         self.direct_forces = direct_forces
         self.triplets_only = triplets_only
         self.num_spherical, self.num_radial = num_spherical, num_radial
+        self.cutoff, self.int_cutoff = float(cutoff), float(int_cutoff)
         # 1 = tcgen05 forward kernel where built (published triplet shape), 0 = fp32 CUDA-core kernels everywhere
         self.bilinear_algo = int(kwargs.get("bilinear_algo", 1))
         # 1 = fused tcgen05 dense layers in the engine (dense_tc.cu: exact 3-way bf16 split, short accumulation
@@ -254,6 +255,14 @@ class GemNet(torch.nn.Module):
         graph per bucket, captured on first use.  Returns a ServingPool (same call convention as ServingGemNet)."""
         return ServingPool(self, molecules, max_atoms, growth, max_graphs, warmup)
 
+    def make_molecule_server(self, molecules, max_atoms, workers=2, **pool_kwargs):
+        """Serving from raw molecules: (R_list, Z_list) on the host -> (E, F) on the host.  The index construction
+        (row H0: the native builder behind graph.build_batch, data_container.py:156-489) runs on `workers` host threads
+        and is pipelined with the GPU evaluation by MoleculeServer.stream(); the evaluation is the static-shape CUDA
+        graph pool of make_serving_pool.  This is what ase_calculator.py:148-170 does per MD step (rebuild indices,
+        predict) as one call."""
+        return MoleculeServer(self, molecules, max_atoms, workers, **pool_kwargs)
+
     def load_weights(self, path):
         self.load_state_dict(torch.load(path))
 
@@ -314,8 +323,10 @@ class ServingGemNet:
                 self.dev[k].copy_(h, non_blocking=True)
             inputs = dict(self.dev)  # a fresh dict: the index plan is rebuilt (inside the graph) for every batch
             inputs[graph._VALIDATED_KEY] = True
+            inputs[graph._REBUILD_KEY] = True   # same device buffers, new contents: the plan kernels are part of the graph
             E, F = model(inputs)
-            flags = torch.cat(inputs[graph._PLAN_KEY][1].flags)  # device-side order/range check of the index lists
+            inputs[graph._REBUILD_KEY] = False
+            flags = torch.cat(graph.get_plan(inputs, model.triplets_only).flags)  # device-side order/range check of the index lists
             if self.E_host is None:
                 self.E_host = torch.empty(E.shape, dtype=E.dtype).pin_memory()
                 self.F_host = torch.empty(F.shape, dtype=F.dtype).pin_memory()
@@ -388,3 +399,59 @@ class ServingPool:
     @property
     def d2h_bytes(self):
         return max((r.d2h_bytes for r in self.runners.values()), default=0)
+
+
+class MoleculeServer:
+    """Host molecules in, energies and forces out: H0 (index construction) on worker threads + ServingPool on the GPU.
+
+    __call__(R_list, Z_list)       one batch, H0 inline (latency path)
+    stream(batches)                generator over an iterable of (R_list, Z_list): the index construction of the next
+                                   `workers` batches overlaps the GPU evaluation of the current one (the native builder
+                                   releases the GIL), results are yielded in order"""
+
+    def __init__(self, model, molecules, max_atoms, workers=2, **pool_kwargs):
+        from concurrent.futures import ThreadPoolExecutor
+        self.model = model
+        if model.triplets_only:
+            self.pool = ServingPool(model, molecules, max_atoms, **pool_kwargs)
+        else:
+            self.pool = None  # quadruplet models: eager evaluation of the built batch
+        self.workers = max(1, int(workers))
+        self.exec = ThreadPoolExecutor(max_workers=self.workers)
+        self.dev = next(model.parameters()).device
+
+    def build(self, R_list, Z_list):
+        m = self.model
+        return graph.build_batch(R_list, Z_list, m.cutoff, m.int_cutoff, m.triplets_only)
+
+    def evaluate(self, host_batch):
+        if self.pool is not None:
+            return self.pool(host_batch)
+        return self.model.predict({k: v.to(self.dev, non_blocking=True) for k, v in host_batch.items()})
+
+    def __call__(self, R_list, Z_list):
+        return self.evaluate(self.build(R_list, Z_list))
+
+    def stream(self, batches):
+        import collections
+        pending = collections.deque()
+        it = iter(batches)
+        for _ in range(self.workers + 1):
+            nxt = next(it, None)
+            if nxt is None:
+                break
+            pending.append(self.exec.submit(self.build, *nxt))
+        while pending:
+            hb = pending.popleft().result()
+            nxt = next(it, None)
+            if nxt is not None:
+                pending.append(self.exec.submit(self.build, *nxt))
+            yield self.evaluate(hb)
+
+    @property
+    def h2d_bytes(self):
+        return 0 if self.pool is None else self.pool.h2d_bytes
+
+    @property
+    def d2h_bytes(self):
+        return 0 if self.pool is None else self.pool.d2h_bytes

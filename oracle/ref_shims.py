@@ -20,7 +20,9 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("GEMNET_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/build_ref.sh (travels to the GPU box)
+REFERENCE_ROOT = os.environ.get("GEMNET_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/gemnet/model") else _STAGED)
 
 
 def reference_available() -> bool:
