@@ -35,6 +35,7 @@ _SIGNATURES = {
     "gemnet_segbilinear_workspace_bytes": [_I64, _I32, _I32, _I32, _I32, _I32, _I32],
     "gemnet_segbilinear_pack_bytes": [_I32, _I32, _I32, _I32, _I32],
     "gemnet_segbilinear_pack": [_P, _I32, _I32, _I32, _I32, _I32, _P, _P],
+    "gemnet_segbilinear_segsum": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P],
     "gemnet_segbilinear_fwd": [_P, _P, _P, _P, _P, _P, _F, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P],
     "gemnet_segbilinear_bwd": [_P, _P, _P, _P, _P, _P, _F, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P,
                                _P, _P, _P, _P],

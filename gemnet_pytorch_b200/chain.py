@@ -36,7 +36,7 @@ class CStep(ctypes.Structure):
                 ("s_post1", ctypes.c_float), ("s_store", ctypes.c_float), ("s_set_carry", ctypes.c_float),
                 ("s_a", ctypes.c_float), ("s_pad", ctypes.c_float),
                 ("aux", _P), ("dact", _P), ("out", _P), ("smul", _P), ("out_idx", _P), ("next_amul", _P),
-                ("dot_w", _P), ("dot_out", _P), ("dot_in", _P)]
+                ("dot_w", _P), ("dot_out", _P), ("dot_in", _P), ("save_x", _P)]
 
 
 class CProgram(ctypes.Structure):
@@ -55,7 +55,7 @@ class Term:
 class Step:
     """One GEMM step.  `weight` is a packed image record of dense_ops.packed_weight (list [buf, N, K, ...])."""
     _TENSORS = ("amul", "pre0", "pre0_idx", "pre1", "pre1_idx", "mul_early", "mul_late", "post0", "post1", "aux",
-                "dact", "out", "smul", "out_idx", "next_amul", "dot_w", "dot_out", "dot_in")
+                "dact", "out", "smul", "out_idx", "next_amul", "dot_w", "dot_out", "dot_in", "save_x")
 
     def __init__(self, weight, terms=(), load_set_carry=False, flags=0, s_acc=1.0, s_carry=1.0, s_post0=1.0,
                  s_post1=1.0, s_store=1.0, s_set_carry=1.0, s_a=1.0, **tensors):

@@ -175,7 +175,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
     const int jmax = max(nv, 1) - 1;
 
     // values of feature f for rows rb .. rb+15 -> the next operand (element (row, k = f)); zero beyond Knext / M
-    auto operand_from = [&](const float (&vals)[16], int Knext, float s_a, const float* amul, bool full) {
+    auto operand_from = [&](const float (&vals)[16], int Knext, float s_a, const float* amul, bool full, float* save) {
       const bool kv = f < Knext;
       const int fc = min(f, Knext - 1);
       float w[16];
@@ -200,6 +200,11 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 #pragma unroll
         for (int j = 0; j < 16; j += 2) store_pair(X, e_loc + j, f, w[j], w[j + 1]);
       }
+      if (save != nullptr && kv) {                          // training: the operand itself (coalesced over f)
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) save[(rb + j) * Knext + f] = w[j];
+      }
     };
 
 #pragma unroll 1
@@ -211,6 +216,8 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       if (st.n_terms > 0) {
         const int gpr = 8 * NKB;                                   // granules (8 columns) per operand row
         const bool fold_amul = st.amul != nullptr && !st.load_set_carry;
+        // the fill IS the operand unless a carry read-back multiplies it afterwards (then operand_from stores it)
+        const bool save_here = st.save_x != nullptr && !(st.load_set_carry && st.amul != nullptr);
         // PG (row, granule) pieces per thread: 64 rows x 8|16 granules = 512|1024 pieces, all loads in flight together
         auto fill = [&](auto pg_tag) {
           constexpr int PG = decltype(pg_tag)::value;
@@ -280,6 +287,11 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[h][j] = valid ? v[h][j] : 0.f;
             store_granule(X, prow[h], pgr[h], v[h]);
+            if (save_here && valid) {
+              float4* dst = reinterpret_cast<float4*>(st.save_x + (r0 + prow[h]) * K + pgr[h] * 8);
+              dst[0] = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
+              dst[1] = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
+            }
           }
         };
         if (NKB == 2) fill(std::integral_constant<int, 2>{});
@@ -292,7 +304,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 #pragma unroll
           for (int j = 0; j < 16; ++j) c[j] = kin ? load_elem(X, e_loc + j, min(f, 64 * NKB - 1)) : 0.f;
           carry_st(c);
-          if (st.amul) operand_from(c, K, 1.0f, st.amul, false);   // (each thread rewrites exactly the elements it read)
+          if (st.amul) operand_from(c, K, 1.0f, st.amul, false, st.save_x);   // (each thread rewrites exactly the elements it read)
         }
       }
       stamp();  // step: operand written by this thread
@@ -486,11 +498,11 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         }
         if (!last) {
           if (flags & GEMNET_CHAIN_TO_A) {
-            operand_from(v, Knext, st.s_a, st.next_amul, FULL);
+            operand_from(v, Knext, st.s_a, st.next_amul, FULL, prog.step[s + 1].save_x);
           } else if (flags & GEMNET_CHAIN_A_FROM_CARRY) {
             float c[16];
             carry_ld(c);
-            operand_from(c, Knext, st.s_a, st.next_amul, FULL);
+            operand_from(c, Knext, st.s_a, st.next_amul, FULL, prog.step[s + 1].save_x);
           }
         }
       };
@@ -522,8 +534,10 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 using namespace gemnet;
 
 static long long* g_chain_prof = nullptr;
+namespace gemnet { void segbil_fwd_tc_set_profile_buffer(long long* p); }
 GEMNET_API void gemnet_chain_set_profile_buffer(void* device_int64_x256) {
   g_chain_prof = static_cast<long long*>(device_int64_x256);
+  gemnet::segbil_fwd_tc_set_profile_buffer(g_chain_prof);   // the same buffer serves the H7 forward kernel's stamps
 }
 
 GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t flags, void* stream) {

@@ -853,6 +853,23 @@ GEMNET_API int gemnet_segbilinear_pack(const float* W, int32_t S, int32_t C, int
   return backward ? launch_segbil_bwd_pack_tc(W, packed, as_stream(stream)) : launch_segbil_fwd_pack_tc(W, packed, as_stream(stream));
 }
 
+/* A[e,s,c] = sum_{t in seg(e)} sph[t,s] x[expand[t],c]  (phase 1 of the layer on its own: the weight gradient
+ * dL/dW[c,i,o] = sum_e (sum_s rbf_W1[e,i,s] A[e,s,c]) g[e,o] is two library contractions on top of it) */
+GEMNET_API int gemnet_segbilinear_segsum(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                                         int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O, float* A_out,
+                                         void* stream) {
+  const int sid = shape_id(S, C, I, O);
+  GEMNET_REQUIRE(sid != 0, "unsupported (S,C,I,O): built for (7,64,16,64) and (49,32,32,32)");
+  if (n_edges == 0) return 0;
+  GEMNET_REQUIRE(x && expand && rowptr && sph && A_out, "null pointer");
+  const unsigned wgrid = (unsigned)ceil_div(n_edges, kSplitWarps);
+  if (sid == 1)
+    launch_pdl(segsum_kernel<TripCfg, false>, wgrid, kSplitWarps * 32, 0, as_stream(stream), x, expand, rowptr, sph, n_edges, A_out);
+  else
+    launch_pdl(segsum_kernel<QuadCfg, false>, wgrid, kSplitWarps * 32, 0, as_stream(stream), x, expand, rowptr, sph, n_edges, A_out);
+  return check_launch("gemnet_segbilinear_segsum");
+}
+
 GEMNET_API int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O,
                                                       int32_t algo, int32_t backward) {
   const bool tc = (algo & GEMNET_SEGBIL_TC) && shape_id(S, C, I, O) == 1;

@@ -173,8 +173,14 @@ __global__ void __launch_bounds__(THREADS, 1)
 segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ expand,
                      const int32_t* __restrict__ rowptr, const float* __restrict__ sph,
                      const float* __restrict__ rbf_W1, const __nv_bfloat16* __restrict__ Wp, float scale,
-                     int64_t n_edges, int n_tiles, float* __restrict__ out) {
+                     int64_t n_edges, int n_tiles, float* __restrict__ out, long long* __restrict__ prof) {
   pdl_enter();
+  // diagnostics (gemnet_chain_set_profile_buffer): thread 0 of CTA 0 records clock64() at the phase boundaries
+  int prof_n = 0;
+  auto stamp = [&]() {
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && prof_n < 250) prof[prof_n++] = clock64();
+  };
+  stamp();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -253,6 +259,7 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
     int prev_tile = -1, it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t e0 = (int64_t)tile * TILE_M;
+      stamp();  // tile: start
       asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");  // As of the previous tile is no longer read
 
       // ---------------- phase 1: one HALF-warp per edge (two independent segments per warp), 4 columns per lane.
@@ -331,10 +338,13 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
             for (int s = 0; s < S; ++s) rw[i8][s] = 0.f;
         }
       }
+      stamp();  // tile: phase 1 of this warp done (+ rbf_W1 registers loaded)
       asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");  // As complete
+      stamp();  // tile: As complete (all warps)
 
       // epilogue of the PREVIOUS tile here: its MMAs had the whole phase 1 of this tile to finish
       if (warp < 4 && prev_tile >= 0) epilogue(it - 1, prev_tile);
+      stamp();  // tile: epilogue of the previous tile done
 
       // ---------------- phase 2: 16 chunks of 64 k; thread = (row el, column cq, i-half ih) -> 8 k-values
       const float* arow = As + el * AS_LD + cq;
@@ -369,9 +379,11 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));
       }
+      stamp();  // tile: phase 2 done (16 chunks handed to the MMA)
       prev_tile = tile;
     }
     if (warp < 4 && prev_tile >= 0) epilogue(it - 1, prev_tile);
+    stamp();  // last epilogue done
   } else if (warp == PRODUCER_WARPS) {
     // ============================================================ MMA issuer
     if (lane == 0) {
@@ -428,6 +440,9 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
 
 int64_t segbil_tc_workspace_bytes() { return tc::WPACK_BYTES; }
 
+static long long* g_h7_prof = nullptr;
+void segbil_fwd_tc_set_profile_buffer(long long* p) { g_h7_prof = p; }
+
 int launch_segbil_fwd_pack_tc(const float* W, void* packed, cudaStream_t st) {
   using namespace tc;
   pack_weight_kernel<<<(NCHUNK * O * KC + 255) / 256, 256, 0, st>>>(W, reinterpret_cast<__nv_bfloat16*>(packed));
@@ -456,7 +471,7 @@ int launch_segbil_fwd_tc_packed(const float* x, const int32_t* expand, const int
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = n_tiles < sms ? n_tiles : sms;
   launch_pdl(segbil_fwd_tc_kernel, grid, THREADS, SMEM_BYTES, st, x, expand, rowptr, sph, rbf_W1,
-             reinterpret_cast<const __nv_bfloat16*>(packed), scale, n_edges, n_tiles, out);
+             reinterpret_cast<const __nv_bfloat16*>(packed), scale, n_edges, n_tiles, out, g_h7_prof);
   return check_launch("gemnet_segbilinear_fwd(algo=1)");
 }
 

@@ -95,8 +95,9 @@ class DenseTC:
     @staticmethod
     def forward(ctx, x, W, act):
         x = _f32(x) if x.stride(-1) != 1 else x
-        need = ctx.needs_input_grad[0]
+        need = ctx.needs_input_grad[0] or getattr(ctx, "train", False)
         ctx.W, ctx.act = W, act
+        ctx.x = x if getattr(ctx, "train", False) else None
         if act and need:
             y, ctx.dact = dense_tc(x, packed_weight(W, False), act=1, want_dact=True)
         else:
@@ -106,6 +107,11 @@ class DenseTC:
     @staticmethod
     def backward(ctx, g):
         g = _f32(g)
+        if getattr(ctx, "train", False):   # training: dW = (g .* dact)^T x (library GEMM over the rows)
+            gz = g if ctx.dact is None else g * ctx.dact
+            ctx.tape.add_wgrad(ctx.W, torch.mm(gz.t(), ctx.x))
+            if not ctx.needs_input_grad[0]:
+                return None, None, None
         return dense_tc(g, packed_weight(ctx.W, True), xmul=ctx.dact), None, None
 
 
@@ -114,6 +120,8 @@ class ResidualTC:
 
     @staticmethod
     def forward(ctx, x, W1, W2, s):
+        if getattr(ctx, "train", False):
+            raise _lib.GemnetB200Error("training needs the chain-fused residual stacks (engine.fuse_ok): unsupported block structure")
         x = _f32(x)
         need = ctx.needs_input_grad[0]
         ctx.W1, ctx.W2, ctx.s = W1, W2, s

@@ -28,11 +28,29 @@ class _Linear:
     @staticmethod
     def forward(ctx, x, W):
         ctx.W = W
+        ctx.x = x if getattr(ctx, "train", False) else None
         return torch.mm(x, W.t())
 
     @staticmethod
     def backward(ctx, g):
+        if getattr(ctx, "train", False):
+            ctx.tape.add_wgrad(ctx.W, torch.mm(g.t(), ctx.x))
+            if not ctx.needs_input_grad[0]:
+                return None, None
         return torch.mm(g, ctx.W), None
+
+
+class _Embedding:
+    """h = weight[Z - 1] (embedding_block.py:29-34); training: the embedding table's gradient"""
+
+    @staticmethod
+    def forward(ctx, weight, Z):
+        ctx.idx, ctx.n = Z - 1, weight.shape[0]
+        return weight[ctx.idx]
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.zeros(ctx.n, g.shape[1], dtype=g.dtype, device=g.device).index_add_(0, ctx.idx, g), None
 
 
 class Tape:
@@ -41,8 +59,9 @@ class Tape:
     producer's (an event over everything the producer lane has enqueued so far).  Cross-lane tensors are parked
     in `keep` until the evaluation ends, so the caching allocator cannot hand their memory to the other stream."""
 
-    def __init__(self, enabled=True, streams=None):
+    def __init__(self, enabled=True, streams=None, train=False):
         self.enabled = enabled
+        self.train = train  # training: gradients w.r.t. the PARAMETERS are wanted too (weights are `require`d)
         self.closures = []
         self.grads = {}
         self.req = set()
@@ -136,7 +155,20 @@ class Tape:
         self.req.add(id(t))
 
     def needs(self, t):
-        return isinstance(t, torch.Tensor) and id(t) in self.req
+        if not isinstance(t, torch.Tensor):
+            return False
+        return id(t) in self.req or (self.train and t._base is not None and id(t._base) in self.req)
+
+    def add_wgrad(self, W, dW):
+        """gradient of a weight operand; W may be a column / row slice (view) of a parameter (EdgeEmbedding's three
+        blocks): the slice's gradient is embedded in a zero tensor of the parameter's shape"""
+        base = W._base if W._base is not None else W
+        if base is W:
+            self.add_grad(W, dW)
+            return
+        full = torch.zeros_like(base)
+        full.as_strided(W.shape, W.stride(), W.storage_offset() - base.storage_offset()).copy_(dW)
+        self.add_grad(base, full)
 
     def add_grad(self, t, g, scale=1.0, idx=None, mul=None):
         """Gradients are kept as lists of (tensor, scale, lane, idx, mul) summands and summed only when they are
@@ -149,8 +181,10 @@ class Tape:
         """Run Fn.forward; if any tensor argument depends on R, record Fn.backward."""
         ctx = _Ctx()
         ctx.needs_input_grad = tuple(self.enabled and self.needs(a) for a in args)
+        ctx.tape, ctx.train = self, self.train
+        fused_fn = getattr(Fn, "fused", False)
         out = Fn.forward(ctx, *args)
-        if not any(ctx.needs_input_grad):
+        if not any(ctx.needs_input_grad) and not (self.train and fused_fn):  # (a fused block always holds weights)
             return out
         outs = out if isinstance(out, tuple) else (out,)
         for o in outs:
@@ -309,7 +343,8 @@ class _Run:
         S = rbf_W1.shape[2]
         if algo == 1 and (S, mod.emb_size, mod.emb_size_interm, mod.units_out) != (7, 64, 16, 64):
             algo = 0
-        return self.t.apply(ops._SegBilinear, x, sph, rbf_W1, mod.weight.detach(), expand, rowptr, float(scale), int(algo))
+        W = mod.weight if self.t.train else mod.weight.detach()
+        return self.t.apply(ops._SegBilinear, x, sph, rbf_W1, W, expand, rowptr, float(scale), int(algo))
 
     def triplet_interaction(self, ti, m, basis, algo):
         p = self.p
@@ -478,9 +513,28 @@ def _lanes(model):
     return (torch.cuda.current_stream(),) + side_stream(model)[:n_side]
 
 
+def trainable(model):
+    """Can this model's TRAINING step run on the engine?  direct-force models (no double backward needed) with the
+    chain-fused block structure, one target, no force coupling."""
+    return (model.direct_forces and not model.forces_coupled and model.num_targets == 1 and fuse_ok(model)
+            and getattr(model, "chain_fusion", True) and getattr(model, "dense_algo", 1) == 1)
+
+
 @torch.no_grad()
-def energy_and_forces(model, inputs):
-    """GemNet.forward (gemnet.py:453-615) for inference: returns (E (nMol, T), F (nAtoms, 3) | (nAtoms, T, 3))."""
+def backward_train(tape, E_mol, F_j, gE, gF, params):
+    """dL/dparams from dL/dE, dL/dF through the tape of energy_and_forces(train=True)"""
+    if gE is not None:
+        tape.add_grad(E_mol, gE.contiguous())
+    if gF is not None:
+        tape.add_grad(F_j, gF.contiguous())
+    tape.backward()
+    return tuple(tape._take(id(p)) for p in params)
+
+
+@torch.no_grad()
+def energy_and_forces(model, inputs, train=False):
+    """GemNet.forward (gemnet.py:453-615): returns (E (nMol, T), F (nAtoms, 3) | (nAtoms, T, 3)); with train=True
+    (direct-force models) also the tape, for backward_train."""
     plan = graph.get_plan(inputs, model.triplets_only)
     Z, R = inputs["Z"], inputs["R"]
     dev = R.device
@@ -489,11 +543,16 @@ def energy_and_forces(model, inputs):
     n_passes = model.num_targets if (need_forces and model.num_targets > 1) else 1
     forces = []
     E_mol = None
-    streams = _lanes(model)
+    streams = None if train else _lanes(model)
     for target in range(n_passes):
-        tape = Tape(enabled=need_forces, streams=streams)
+        tape = Tape(enabled=need_forces or train, streams=streams, train=train)
         if need_forces:
             tape.require(R)
+        if train:
+            for prm in model.parameters():
+                if prm.requires_grad:
+                    tape.require(prm)
+        wt = (lambda prm: prm) if train else (lambda prm: prm.detach())
         run = _Run(model, tape, plan)
         A = tape.apply
 
@@ -509,12 +568,12 @@ def energy_and_forces(model, inputs):
             rad_g = A(_Gather42, rad_int, plan.abd_int_edge, plan)                           # (M, S*R)
             cbf4 = A(_MulBroadcastSph, rad_g, sph_abd, nR)                                   # (M, S*R)
         rb = model.rbf_basis
-        rbf = A(ops._BesselRbf, D_ca, rb.frequencies.detach(), rb.cutoff, rb.p)
+        rbf = A(ops._BesselRbf, D_ca, wt(rb.frequencies), rb.cutoff, rb.p)
         c3 = model.cbf_basis3
         rad = A(ops._SphBesselRadial, D_ca, S, nR, c3.cutoff, c3.p)
         basis["sph3"] = A(ops._TripletSph, R, plan.id_c, plan.id_a, plan.id3_reduce, plan.id3_expand, S)
 
-        h = model.atom_emb(Z)
+        h = A(_Embedding, model.atom_emb.embeddings.weight, Z) if train else model.atom_emb(Z)
         m = run.edge_embedding(model.edge_emb, h, rbf)
         use_fan = run.fuse and run.fuse_out and fused.rbf_fan_ok(model)
         if use_fan:  # every projection of the radial basis in one launch (13 / 17 K=16 GEMMs per direction otherwise)
@@ -524,9 +583,9 @@ def energy_and_forces(model, inputs):
         if not model.triplets_only:
             basis["rbf4"] = None if use_fan else run.linear(model.mlp_rbf4, rbf)
             basis["cbf4"] = run.linear(model.mlp_cbf4, cbf4)
-            basis["rbf_W1_4"] = A(ops._DownProj, rad, model.mlp_sbf4.weight.detach(), layers.l_of_s_tensor(S, True, dev))
+            basis["rbf_W1_4"] = A(ops._DownProj, rad, wt(model.mlp_sbf4.weight), layers.l_of_s_tensor(S, True, dev))
         basis["rbf3"] = None if use_fan else run.linear(model.mlp_rbf3, rbf)
-        basis["rbf_W1_3"] = A(ops._DownProj, rad, model.mlp_cbf3.weight.detach(), layers.l_of_s_tensor(S, False, dev))
+        basis["rbf_W1_3"] = A(ops._DownProj, rad, wt(model.mlp_cbf3.weight), layers.l_of_s_tensor(S, False, dev))
         basis["rbf_h"] = None if use_fan else run.linear(model.mlp_rbf_h, rbf)
         rbf_out = None if use_fan else run.linear(model.mlp_rbf_out, rbf)
 
@@ -560,7 +619,7 @@ def energy_and_forces(model, inputs):
                     0, id_undir, torch.ones(nE, dtype=F_ca.dtype, device=dev)).clamp(min=1)
                 F_ca = (summed / cnt[:, None])[id_undir]
             F_j = A(ops._ForceReadout, F_ca, V_ca, plan.id_a, plan.atom_perm, plan.atom_rowptr)
-            return E_mol, F_j
+            return (E_mol, F_j, tape) if train else (E_mol, F_j)
 
         seed = torch.zeros_like(E_mol)
         if model.num_targets > 1:

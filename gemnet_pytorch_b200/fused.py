@@ -41,6 +41,39 @@ def _terms(tl):
     return [Term(g, sc, idx=idx, mul=mul) for g, sc, idx, mul in tl]
 
 
+def _save_operands(steps, rows, like):
+    """training: every step stores its GEMM operand (the weight gradient's factor); a step that reuses its
+    predecessor's operand unchanged (no fill, predecessor without TO_A / A_FROM_CARRY) aliases the predecessor's"""
+    prev = None
+    for st in steps:
+        unchanged = prev is not None and not st.terms and not (prev.flags & (TO_A | A_FROM_CARRY))
+        if unchanged:
+            st.save_alias = prev if prev.save_x is not None else getattr(prev, "save_alias", None)
+        else:
+            st.save_x = _new(rows, st.K, like)
+        prev = st
+
+
+def _operand(st):
+    if st.save_x is not None:
+        return st.save_x
+    al = getattr(st, "save_alias", None)
+    return None if al is None else al.save_x
+
+
+def _weight_grads(tape, fwd_steps, bwd_steps):
+    """dW = (operand of the backward step)^T @ (operand of the forward step) for every weight both programs use"""
+    fmap = {}
+    for st in fwd_steps:
+        W = st.weight[3]
+        fmap[(W.data_ptr(), tuple(W.shape), tuple(W.stride()))] = _operand(st)
+    for st in bwd_steps:
+        W = st.weight[3]
+        a, gz = fmap.get((W.data_ptr(), tuple(W.shape), tuple(W.stride()))), _operand(st)
+        if a is not None and gz is not None:
+            tape.add_wgrad(W, ops.weight_grad(gz, a))
+
+
 def _is_silu(d):
     return isinstance(d._activation, layers.ScaledSiLU)
 
@@ -105,15 +138,18 @@ class TripPrologue:
     def forward(ctx, m, r, dense_in, down, s):
         Wb, Wd = dense_in.linear.weight, down.linear.weight
         E = m.shape[0]
-        need = any(ctx.needs_input_grad[:2])
+        need = any(ctx.needs_input_grad[:2]) or ctx.train
         ctx.aux = _new(E, Wb.shape[0], m) if need else None
         ctx.d1 = _new(E, Wb.shape[0], m) if need else None
         ctx.d2 = _new(E, Wd.shape[0], m) if need else None
         ctx.Wb, ctx.Wd, ctx.E = Wb, Wd, E
         x = _new(E, Wd.shape[0], m)
-        chain.run(Program(E, [
-            Step(_pw(Wb), terms=[Term(m)], flags=ACT | TO_A, s_acc=s, mul_early=r, aux=ctx.aux, dact=ctx.d1),
-            Step(_pw(Wd), flags=ACT, dact=ctx.d2, out=x)]))
+        steps = [Step(_pw(Wb), terms=[Term(m)], flags=ACT | TO_A, s_acc=s, mul_early=r, aux=ctx.aux, dact=ctx.d1),
+                 Step(_pw(Wd), flags=ACT, dact=ctx.d2, out=x)]
+        if ctx.train:
+            _save_operands(steps, E, m)
+        ctx.fsteps = steps
+        chain.run(Program(E, steps))
         return x
 
     @staticmethod
@@ -126,9 +162,13 @@ class TripPrologue:
         g_m = _new(ctx.E, ctx.Wb.shape[1], ctx.aux) if need_m else None
         steps = [Step(_pw(ctx.Wd, True), terms=_terms(gx), amul=ctx.d2, flags=TO_A, out=g_r, smul=ctx.aux,
                       next_amul=ctx.d1)]
-        if need_m:
+        if need_m or ctx.train:
             steps.append(Step(_pw(ctx.Wb, True), out=g_m))
+        if ctx.train:
+            _save_operands(steps, ctx.E, ctx.aux)
         chain.run(Program(ctx.E, steps))
+        if ctx.train:
+            _weight_grads(tape, ctx.fsteps, steps)
         return g_m, g_r, None, None, None
 
 
@@ -143,7 +183,7 @@ class Post:
         paths = [(x3, blk.trip_interaction)] + ([(x4, blk.quad_interaction)] if x4 is not None else [])
         c = layers.INV_SQRT_2 if x4 is None else layers.INV_SQRT_3
         E = m.shape[0]
-        need = any(ctx.needs_input_grad[:3])
+        need = any(ctx.needs_input_grad[:3]) or ctx.train
         H = blk.dense_ca.linear.weight.shape[0]
         steps, ups = [], []
         for j, (x, mod) in enumerate(paths):
@@ -161,6 +201,9 @@ class Post:
         _residual_fwd(steps, before, list(blk.layers_before_skip), need, E, m, tail=dict(scale=S2, post0=m, s_post0=S2))
         out = _new(E, H, m)
         _residual_fwd(steps, after, list(blk.layers_after_skip), need, E, m, tail=dict(out=out))
+        if ctx.train:
+            _save_operands(steps, E, m)
+        ctx.fsteps = steps
         chain.run(Program(E, steps))
         ctx.save = (ups, Wc, dc, before, after, c, E, H, plan.id_swap, x4 is not None)
         return out
@@ -179,7 +222,7 @@ class Post:
                       dict(flags=SET_CARRY | TO_A, out=gm_part, s_store=S2, next_amul=before[-1][3]))
         # before-skip stack reversed: ends with v = dL/dx0 ; x0 = ssilu(m Wc^T)*c + c*sum_p(...)
         _residual_bwd(steps, before, None, dict(flags=SET_CARRY | TO_A, next_amul=dc))
-        g_m = _new(E, H, like) if ctx.needs_input_grad[0] else None
+        g_m = _new(E, H, like) if (ctx.needs_input_grad[0] or ctx.train) else None
         grads_x = []
         n_up = len(ups)
         # dense_ca branch, then the up-projections straight from the carry (dL/dx0)
@@ -192,7 +235,11 @@ class Post:
             steps.append(Step(_pw(Wac, True), out=gb, out_idx=swap, flags=(A_FROM_CARRY if nxt is not None else 0),
                               s_a=c, next_amul=nxt))
             grads_x.append([(ga, 1.0, None, None), (gb, 1.0, None, None)])
+        if ctx.train:
+            _save_operands(steps, E, like)
         chain.run(Program(E, steps))
+        if ctx.train:
+            _weight_grads(tape, ctx.fsteps, steps)
         return g_m, grads_x[0], (grads_x[1] if has4 else None), None, None
 
 
@@ -210,7 +257,7 @@ class AtomChain:
         A = h.shape[1]
         Wpc, Wpa = W[:, :A], W[:, A:2 * A]
         n = x0.shape[0]
-        need = any(ctx.needs_input_grad[:2])
+        need = any(ctx.needs_input_grad[:2]) or ctx.train
         d0 = _new(n, W0.shape[0], x0) if need else None
         h2 = _new(n, A, x0)
         p_c, p_a = _new(n, W.shape[0], x0), _new(n, W.shape[0], x0)
@@ -219,6 +266,9 @@ class AtomChain:
         _residual_fwd(steps, saved, mlp[1:], need, n, x0, tail=dict(scale=S2, post0=h, s_post0=S2, out=h2))
         steps.append(Step(_pw(Wpc), out=p_c))
         steps.append(Step(_pw(Wpa), out=p_a))
+        if ctx.train:
+            _save_operands(steps, n, x0)
+        ctx.fsteps = steps
         chain.run(Program(n, steps))
         ctx.save = (W0, d0, saved, Wpc, Wpa, n, A)
         return h2, p_c, p_a
@@ -240,7 +290,11 @@ class AtomChain:
                       next_amul=saved[-1][3], **post)]
         _residual_bwd(steps, saved, None, dict(flags=TO_A, next_amul=d0))
         steps.append(Step(_pw(W0, True), out=g_x))
+        if ctx.train:
+            _save_operands(steps, n, d0)
         chain.run(Program(n, steps))
+        if ctx.train:
+            _weight_grads(tape, ctx.fsteps, steps)
         return g_x, g_h, None
 
 
@@ -255,13 +309,16 @@ class EdgeEmb:
         A = (W.shape[1] - m.shape[1]) // 2
         Wm = W[:, 2 * A:]
         E, H = m.shape[0], W.shape[0]
-        need = any(ctx.needs_input_grad[:3])
+        need = any(ctx.needs_input_grad[:3]) or ctx.train
         d0 = _new(E, H, m) if need else None
         out = _new(E, H, m)
         steps = [Step(_pw(Wm), terms=[Term(m)], pre0=p_c, pre0_idx=plan.id_c, pre1=p_a, pre1_idx=plan.id_a,
                       flags=ACT | SET_CARRY | TO_A, dact=d0)]
         saved = []
         _residual_fwd(steps, saved, list(blk.residual_m), need, E, m, tail=dict(scale=S2, post0=m, s_post0=S2, out=out))
+        if ctx.train:
+            _save_operands(steps, E, m)
+        ctx.fsteps = steps
         chain.run(Program(E, steps))
         ctx.save = (Wm, d0, saved, E, H, plan, p_c.shape[0])
         return out
@@ -278,7 +335,11 @@ class EdgeEmb:
         # carry = dL/dm'' for the whole program (one residual layer: nothing in between overwrites it)
         _residual_bwd(steps, saved, _terms(G), dict(flags=TO_A, mul_late=d0, out=g_z))
         steps.append(Step(_pw(Wm, True), flags=CARRY_ADD, s_carry=S2, out=g_m))
+        if ctx.train:
+            _save_operands(steps, E, d0)
         chain.run(Program(E, steps))
+        if ctx.train:
+            _weight_grads(tape, ctx.fsteps, steps)
         g_pc = ops.segment_sum_rows(g_z, plan.src_perm, plan.src_rowptr, n_atoms)
         g_pa = ops.segment_sum_rows(g_z, plan.atom_perm, plan.atom_rowptr, n_atoms)
         return g_m, g_pc, g_pa, None, None
@@ -294,12 +355,17 @@ class OutChain:
         W0 = mlp[0].linear.weight
         w_out = out_dense.linear.weight
         n = x0.shape[0]
-        need = ctx.needs_input_grad[0]
+        need = ctx.needs_input_grad[0] or ctx.train
         d0 = _new(n, W0.shape[0], x0) if need else None
         E_new = _new(n, 1, x0)
         steps = [Step(_pw(W0), terms=[Term(x0)], flags=ACT | SET_CARRY | TO_A, dact=d0)]
         saved = []
-        _residual_fwd(steps, saved, mlp[1:], need, n, x0, tail=dict(dot_w=w_out, dot_out=E_new, dot_in=E_prev))
+        ctx.v_last = _new(n, w_out.shape[1], x0) if ctx.train else None   # training: features the output layer sees
+        _residual_fwd(steps, saved, mlp[1:], need, n, x0,
+                      tail=dict(dot_w=w_out, dot_out=E_new, dot_in=E_prev, out=ctx.v_last))
+        if ctx.train:
+            _save_operands(steps, n, x0)
+        ctx.fsteps = steps
         chain.run(Program(n, steps))
         ctx.save = (W0, d0, saved, w_out, n)
         return E_new
@@ -313,12 +379,17 @@ class OutChain:
         gE = tape.reduce_terms(gE, 1, plain=True)
         g, sc, _, _ = gE[0]
         g_x = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] or ctx.train:
             g_x = _new(n, W0.shape[1], d0)
             steps = []
             _residual_bwd(steps, saved, [Term(g, sc, mul=w_out, kind=1)], dict(flags=TO_A, next_amul=d0))
             steps.append(Step(_pw(W0, True), out=g_x))
+            if ctx.train:
+                _save_operands(steps, n, d0)
             chain.run(Program(n, steps))
+            if ctx.train:
+                _weight_grads(tape, ctx.fsteps, steps)
+                tape.add_wgrad(w_out, ops.weight_grad(g if sc == 1.0 else g * sc, ctx.v_last))
         return g_x, ([(g, sc, None, None)] if ctx.needs_input_grad[1] else None), None, None
 
 
@@ -365,6 +436,7 @@ class RbfFan:
         groups = [g for g, _ in uses]
         out = ops.rbf_fan_fwd(rbf, W1s, W2s, groups)
         ctx.save = (rbf.shape[0], rbf.shape[1], W1s, W2s, groups)
+        ctx.rbf = rbf if ctx.train else None
         return tuple(out[j] for j in range(len(uses)))
 
     @staticmethod
@@ -379,7 +451,21 @@ class RbfFan:
             gs.append(g if sc == 1.0 else ops.lincomb([(g, sc)]))
         if all(g is None for g in gs):
             return None, None, None
-        return ops.rbf_fan_bwd(E, R, W1s, W2s, groups, gs), None, None
+        if ctx.train:   # weight gradients of both levels (plain GEMMs over the edges: library calls)
+            rbf = ctx.rbf
+            t = [torch.mm(rbf, W1.t()) for W1 in W1s]
+            acc = [None] * len(W1s)
+            for g, W2, gi in zip(gs, W2s, groups):
+                if g is None:
+                    continue
+                tape.add_wgrad(W2, ops.weight_grad(g, t[gi]))
+                tg = torch.mm(g, W2)
+                acc[gi] = tg if acc[gi] is None else acc[gi] + tg
+            for W1, tg in zip(W1s, acc):
+                if tg is not None:
+                    tape.add_wgrad(W1, ops.weight_grad(tg, rbf))
+        g_rbf = ops.rbf_fan_bwd(E, R, W1s, W2s, groups, gs) if ctx.needs_input_grad[0] else None
+        return g_rbf, None, None
 
 
 def rbf_fan_ok(model):

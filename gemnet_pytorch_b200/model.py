@@ -143,6 +143,12 @@ class GemNet(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs):
+        if self.use_engine and self.training and torch.is_grad_enabled() and engine.trainable(self):
+            # training step of a direct-force model on the engine: the chain-fused kernels forward and backward, weight
+            # gradients from the operands they saved (library GEMMs over the rows), bridged into torch.autograd so that
+            # the reference Trainer's loss.backward() (trainer.py:346) works unchanged
+            params = [p for p in self.parameters() if p.requires_grad]
+            return _EngineTrainFn.apply(self, inputs, *params)
         if self.use_engine and not self.training:
             E_mol, F_j = engine.energy_and_forces(self, inputs)
             if not self.direct_forces:
@@ -268,6 +274,22 @@ class GemNet(torch.nn.Module):
 
     def save_weights(self, path):
         torch.save(self.state_dict(), path)
+
+
+class _EngineTrainFn(torch.autograd.Function):
+    """(E, F) = engine.energy_and_forces(model, inputs, train=True) as one autograd node over all parameters."""
+
+    @staticmethod
+    def forward(ctx, model, inputs, *params):
+        E, F, tape = engine.energy_and_forces(model, inputs, train=True)
+        ctx.tape, ctx.outs, ctx.params = tape, (E, F), params
+        return E, F
+
+    @staticmethod
+    def backward(ctx, gE, gF):
+        grads = engine.backward_train(ctx.tape, ctx.outs[0], ctx.outs[1], gE, gF, ctx.params)
+        ctx.tape = None
+        return (None, None) + grads
 
 
 class GraphedGemNet:

@@ -339,16 +339,16 @@ def down_projection(rad, Wd, l_of_s):
 
 
 # ----------------------------------------------------------------------------- H7
-def _segbilinear_weight_grad(x, expand, rowptr, sph, rbf_W1, g_out_scaled):
-    """dL/dW (C,I,O) — training only.  Host-side composition of library tensor ops for now (the forward /
-    force path never needs it); a native kernel is listed as follow-up work in DESIGN.md."""
-    E = rbf_W1.shape[0]
-    counts = (rowptr[1:] - rowptr[:-1]).long()
-    reduce_ids = torch.repeat_interleave(torch.arange(E, device=x.device), counts)
-    A = torch.zeros(E, sph.shape[1], x.shape[1], dtype=x.dtype, device=x.device)
-    A.index_add_(0, reduce_ids, sph[:, :, None] * x[expand.long()][:, None, :])  # (E,S,C)
-    B = torch.einsum("eis,esc->eci", rbf_W1, A)  # (E,C,I)
-    return torch.einsum("eci,eo->cio", B, g_out_scaled)
+def _segbilinear_weight_grad(x, expand, rowptr, sph, rbf_W1, g_out_scaled, O=None):
+    """dL/dW (C,I,O) — training only: A (E,S,C) by the CSR segment-sum kernel (no (U,S,C) intermediate: that would be
+    8 GB for a GemNet-dQ batch), then two library contractions."""
+    E, I, S = rbf_W1.shape
+    C = x.shape[1]
+    A = torch.empty(E, S, C, dtype=torch.float32, device=x.device)
+    _check(_L().gemnet_segbilinear_segsum(_p(x), _p(_i32(expand)), _p(_i32(rowptr)), _p(sph), E, S, C, I,
+                                          g_out_scaled.shape[1], _p(A), _stream()), "gemnet_segbilinear_segsum")
+    B = torch.bmm(rbf_W1, A)                                   # (E, I, C) = (E,I,S) @ (E,S,C)
+    return torch.mm(B.transpose(1, 2).reshape(E, C * I).t(), g_out_scaled).view(C, I, -1)
 
 
 _segbil_packs = {}
@@ -766,3 +766,9 @@ def rbf_fan_bwd(E, R, W1s, W2s, groups, g_outs):
     _check(_L().gemnet_rbf_fan_bwd(E, R, _ptr_array(W1s), len(W1s), _ptr_array(W2s), (ctypes.c_int32 * J)(*groups), J, H,
                                    _ptr_array(g_outs), _p(ws), _p(g_rbf), _stream()), "gemnet_rbf_fan_bwd", kernels=2)
     return g_rbf
+
+
+def weight_grad(gz, a):
+    """dW (N, K) = gz^T (N x rows) @ a (rows x K): the weight gradient of a dense layer from the two operands the chain
+    kernels saved (training only).  A plain GEMM with the row count as reduction dimension: library call."""
+    return torch.mm(gz.t(), a)

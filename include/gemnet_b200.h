@@ -172,6 +172,10 @@ int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C
 int64_t gemnet_segbilinear_pack_bytes(int32_t S, int32_t C, int32_t I, int32_t O, int32_t backward);
 int gemnet_segbilinear_pack(const float* W, int32_t S, int32_t C, int32_t I, int32_t O, int32_t backward, void* packed,
                             void* stream);
+/* phase 1 on its own: A (E, S, C) = sum over the segment of sph[t,s] * x[expand[t],c] (training: dL/dW of the layer is
+ * two library contractions on top of it; no (U, S, C) intermediate) */
+int gemnet_segbilinear_segsum(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
+                              int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O, float* A_out, void* stream);
 int gemnet_segbilinear_fwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
                            const float* rbf_W1, const float* W, float scale, int64_t n_edges, int64_t n_units,
                            int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo, float* out, void* workspace,
@@ -330,6 +334,7 @@ typedef struct {
   const float* dot_w;
   float* dot_out;
   const float* dot_in;
+  float* save_x;  /* optional (M, K): this step's GEMM operand as written (training: the weight gradient's factor) */
 } gemnet_chain_step;
 
 typedef struct {

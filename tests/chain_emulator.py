@@ -51,6 +51,8 @@ def emulate(prog, settled=True, dtype=None):
                 carry = v.clone()
             A = v * st.amul.reshape(M, K).to(v.dtype) if st.amul is not None else v
         assert A is not None and A.shape == (M, K), f"step {i}: operand {None if A is None else A.shape} vs K={K}"
+        if st.save_x is not None:
+            st.save_x.copy_(A)
         z = A @ weight_matrix(st.weight, A.dtype).t()
 
         def rows(t, idx, width):
@@ -142,10 +144,10 @@ class _SegBilinearCPU:
     def backward(ctx, g):
         x, sph, rbf_W1, W, expand, rowptr, scale = ctx.save
         with torch.enable_grad():
-            xs = [t.detach().requires_grad_(True) for t in (x, sph, rbf_W1)]
-            out = _segbil(xs[0], xs[1], xs[2], W, expand, rowptr, scale)
+            xs = [t.detach().requires_grad_(True) for t in (x, sph, rbf_W1, W)]
+            out = _segbil(xs[0], xs[1], xs[2], xs[3], expand, rowptr, scale)
             gs = torch.autograd.grad(out, xs, g)
-        return gs[0], gs[1], gs[2], None, None, None, None, None
+        return gs[0], gs[1], gs[2], (gs[3] if ctx.needs_input_grad[3] else None), None, None, None, None
 
 
 def _e2a_forward(ctx, m, r, id_a, perm, rowptr, scale, had_scale):

@@ -124,6 +124,87 @@ def test_fused_blocks_match_oracle_blocks(name):
             assert err < 1e-9, f"gradient {k}: {err:.2e}"
 
 
+@pytest.mark.parametrize("name", ["dT", "dQ"])
+def test_training_weight_gradients_match_oracle(name):
+    """Tape(train=True): the fused blocks' backward also yields dL/dW for every weight they hold (operands saved by the
+    chain programs -> library GEMMs), equal to torch autograd on the oracle's blocks (float64)."""
+    from gemnet_pytorch_b200 import engine, fused
+    kw, model, oracle, inp = setup(name, [1, 4, 7], seed=13)
+    tri = kw["triplets_only"]
+    plan = cpu_plan(inp, tri)
+    E, A, T = plan.n_edges, plan.n_atoms, int(plan.id3_reduce.numel())
+    g = torch.Generator().manual_seed(4)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)  # noqa: E731
+    S = kw["num_spherical"]
+    rbf = rnd(E, kw["num_radial"])
+    leaves = {"h": rnd(A, 128), "m": rnd(E, 128), "sph3": rnd(T, S), "rbf_W1_3": rnd(E, 16, S) * 0.3}
+    if not tri:
+        M, Q = int(inp["id4_expand_intm_db"].numel()), int(inp["id4_expand_abd"].numel())
+        leaves.update({"cbf4": rnd(M, 16), "ylm": rnd(Q, S * S) * 0.3, "rbf_W1_4": rnd(E, 32, S * S) * 0.1})
+    GE, GF, Gm, Gh = rnd(A, 1), rnd(E, 1), rnd(E, 128), rnd(A, 128)
+
+    # ---- oracle blocks, parameters as autograd leaves
+    for v in oracle.p.values():
+        v.requires_grad_(True)
+    gd = {"id_swap": inp["id_swap"], "id3_expand_ba": inp["id3_expand_ba"], "id3_reduce_ca": inp["id3_reduce_ca"],
+          "Kidx3": inp["Kidx3"], "id_c": inp["id_c"], "id_a": inp["id_a"],
+          "rbf3": oracle.dense("mlp_rbf3", rbf, False), "rbf_h": oracle.dense("mlp_rbf_h", rbf, False),
+          "cbf3": (leaves["rbf_W1_3"], go.pad_by_segment(leaves["sph3"], inp["id3_reduce_ca"], inp["Kidx3"], E).transpose(1, 2))}
+    if not tri:
+        gd.update(rbf4=oracle.dense("mlp_rbf4", rbf, False), cbf4=leaves["cbf4"], Kidx4=inp["Kidx4"],
+                  id4_reduce_ca=inp["id4_reduce_ca"], id4_expand_intm_db=inp["id4_expand_intm_db"],
+                  id4_expand_abd=inp["id4_expand_abd"],
+                  sbf4=(leaves["rbf_W1_4"], go.pad_by_segment(leaves["ylm"], inp["id4_reduce_ca"], inp["Kidx4"], E).transpose(1, 2)))
+    rbf_out = oracle.dense("mlp_rbf_out", rbf, False)
+    h1, m1 = oracle.interaction_block("int_blocks.0", leaves["h"], leaves["m"], gd)
+    E0, F0 = oracle.output_block("out_blocks.1", h1, m1, rbf_out, inp["id_a"])
+    h2, m2 = oracle.interaction_block("int_blocks.1", h1, m1, gd)
+    E1, F1 = oracle.output_block("out_blocks.2", h2, m2, rbf_out, inp["id_a"])
+    loss = ((E0 + E1) * GE).sum() + ((F0 + F1) * GF).sum() + (m2 * Gm).sum() + (h2 * Gh).sum()
+    loss.backward()
+
+    # ---- fused engine in training mode
+    with ce.patched(), torch.no_grad():
+        tape = engine.Tape(enabled=True, train=True)
+        for prm in model.parameters():
+            tape.require(prm)
+        run = engine._Run(model, tape, plan)
+        assert run.fuse and run.fuse_out and fused.rbf_fan_ok(model)
+        level1, uses = fused.fan_layout(model)
+        outs = tape.apply(fused.RbfFan, rbf.clone(), level1, uses)
+        run.fan_out = {id(d): o for (_, d), o in zip(uses, outs)}
+        X = {k: v.clone() for k, v in leaves.items()}
+        tape.require(X["h"])
+        tape.require(X["m"])
+        basis = dict(X, rbf3=None, rbf_h=None, rbf4=None)
+        a1, b1 = run.interaction_block(model.int_blocks[0], X["h"], X["m"], basis, 0)
+        Ea, Fa = run.output_block_fused(model.out_blocks[1], b1, None, None, None)
+        a2, b2 = run.interaction_block(model.int_blocks[1], a1, b1, basis, 0)
+        Eb, Fb = run.output_block_fused(model.out_blocks[2], b2, None, Ea, Fa)
+        for ours, ref in ((Eb, E0 + E1), (Fb, F0 + F1)):
+            assert (ours - ref).abs().max() / ref.abs().max() < 1e-10
+        tape.add_grad(Eb, GE)
+        tape.add_grad(Fb, GF)
+        tape.add_grad(b2, Gm)
+        tape.add_grad(a2, Gh)
+        tape.backward()
+        checked = 0
+        for name_, prm in model.named_parameters():
+            if name_.endswith(".weight") and ".linear." not in name_ and not name_.startswith(("mlp_", "atom_emb", "int_blocks", "out_blocks")):
+                continue
+            key = name_.replace(".linear.weight", ".weight")
+            ref = oracle.p.get(key)
+            if ref is None or ref.grad is None or "scale_factor" in name_ or ref.grad.abs().max() == 0:
+                continue
+            ours = tape._take(id(prm))
+            if ours is None:
+                continue
+            err = (ours - ref.grad).abs().max() / ref.grad.abs().max()
+            assert err < 1e-9, f"{name_}: {err:.2e}"
+            checked += 1
+        assert checked >= (45 if tri else 60), checked
+
+
 @pytest.mark.parametrize("name", ["T", "Q"])
 def test_rbf_fan_layout_and_gradient(name):
     """fused.RbfFan on the tape: every level-2 projection of the radial basis equals layer(level1(rbf)), and the
