@@ -55,6 +55,7 @@ _SIGNATURES = {
     "gemnet_segment_sum_rows": [_P, _P, _P, _I64, _I32, _P, _P],
     "gemnet_dense_pack_floats": [_I32, _I32],
     "gemnet_dense_pack_weight": [_P, _I64, _I64, _I32, _I32, _P, _P],
+    "gemnet_dense_pack_many": [_P, _I32, _P],
     "gemnet_dense_tc": [_P, _P, _I64, _I32, _I32, _P, _I32, _I32, _F, _P, _F, _P, _P, _I32, _P],
     "gemnet_rbf_fan_fwd": [_P, _I64, _I32, _P, _I32, _P, _P, _I32, _I32, _P, _P],
     "gemnet_rbf_fan_bwd": [_I64, _I32, _P, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P],

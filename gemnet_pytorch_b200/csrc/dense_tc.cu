@@ -169,6 +169,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int64_t sn, in
   dst[(int64_t)(kb * 3 + 2) * N * KB + phys] = l;
 }
 
+// many weights in one launch (training: every image changes every optimiser step): blockIdx.y = table entry
+__global__ void pack_many_kernel(const gemnet_pack_desc* __restrict__ table) {
+  const gemnet_pack_desc d = table[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d.Np * d.Kp) return;
+  const int k = idx % d.Kp, n = idx / d.Kp;
+  const float w = (n < d.N && k < d.K) ? d.src[(int64_t)n * d.stride_n + (int64_t)k * d.stride_k] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const float r = w - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(r);
+  const __nv_bfloat16 l = __float2bfloat16_rn(r - __bfloat162float(m));
+  const int kb = k / KB, kl = k % KB;
+  const int phys = n * KB + (((kl >> 3) ^ (n & 7)) << 3) + (kl & 7);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d.dst);
+  dst[(int64_t)(kb * 3 + 0) * d.Np * KB + phys] = h;
+  dst[(int64_t)(kb * 3 + 1) * d.Np * KB + phys] = m;
+  dst[(int64_t)(kb * 3 + 2) * d.Np * KB + phys] = l;
+}
+
 static inline int64_t ceil_div_i(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 struct Params {
@@ -482,6 +501,14 @@ GEMNET_API int gemnet_dense_pack_weight(const float* W, int64_t stride_n, int64_
   dtc::pack_weight_kernel<<<(Np * Kp + 255) / 256, 256, 0, as_stream(stream)>>>(
       W, stride_n, stride_k, N, K, Np, Kp, reinterpret_cast<__nv_bfloat16*>(packed));
   return check_launch("gemnet_dense_pack_weight");
+}
+
+GEMNET_API int gemnet_dense_pack_many(const gemnet_pack_desc* table_device, int32_t n_entries, void* stream) {
+  GEMNET_REQUIRE(n_entries >= 0, "negative size");
+  if (n_entries == 0) return 0;
+  GEMNET_REQUIRE(table_device, "null pointer");
+  dtc::pack_many_kernel<<<dim3((128 * 128 + 255) / 256, n_entries), 256, 0, as_stream(stream)>>>(table_device);
+  return check_launch("gemnet_dense_pack_many");
 }
 
 GEMNET_API int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int32_t ldx,

@@ -48,6 +48,30 @@ def packed_weight(W, transpose):
 
 
 PACKER = [None]
+_table = [None, None]   # (signature of the cached entries, device table of gemnet_pack_desc)
+
+
+def refresh():
+    """Re-pack EVERY cached image in one launch (gemnet_dense_pack_many) and mark them current.  Training calls this at
+    the start of each step: the optimiser has changed every weight, and ~230 single-weight pack launches per step
+    would cost more than the step's GEMMs.  Inside a captured CUDA graph the launch is part of the graph, so replays
+    re-pack from the live weights."""
+    if not _packs or PACKER[0] is not None:
+        return
+    import numpy as np
+    entries = list(_packs.values())
+    sig = tuple((e[0].data_ptr(), e[3].data_ptr(), e[5]) for e in entries)
+    if _table[0] != sig:
+        rows = np.zeros((len(entries), 6), dtype=np.int64)
+        for i, e in enumerate(entries):
+            buf, N, K, W, _, tr, _ = e
+            sn, sk = (W.stride(1), W.stride(0)) if tr else (W.stride(0), W.stride(1))
+            Np, Kp = (64 if N <= 64 else 128), (64 if K <= 64 else 128)
+            rows[i] = (W.data_ptr(), buf.data_ptr(), sn, sk, N | (K << 32), Np | (Kp << 32))
+        _table[0], _table[1] = sig, torch.from_numpy(rows).to(entries[0][0].device)
+    _check(_L().gemnet_dense_pack_many(_table[1].data_ptr(), len(entries), _stream()), "gemnet_dense_pack_many")
+    for e in entries:
+        e[4], e[6] = True, e[3]._version
 
 
 def invalidate():

@@ -159,6 +159,19 @@ class Tape:
             return False
         return id(t) in self.req or (self.train and t._base is not None and id(t._base) in self.req)
 
+    def on_wgrad_stream(self, fn, tensors=()):
+        """run fn() (weight-gradient GEMMs) on the side stream `wstream` after what the current stream has enqueued;
+        backward_train joins it before the gradients are collected.  `tensors` are read there: kept alive until the
+        join so that the caching allocator cannot recycle them under the side stream."""
+        ws = getattr(self, "wstream", None)
+        if ws is None:
+            return fn()
+        self.keep.extend(tensors)
+        cur = torch.cuda.current_stream()
+        ws.wait_stream(cur)
+        with torch.cuda.stream(ws):
+            fn()
+
     def add_wgrad(self, W, dW):
         """gradient of a weight operand; W may be a column / row slice (view) of a parameter (EdgeEmbedding's three
         blocks): the slice's gradient is embedded in a zero tensor of the parameter's shape"""
@@ -528,7 +541,12 @@ def backward_train(tape, E_mol, F_j, gE, gF, params):
     if gF is not None:
         tape.add_grad(F_j, gF.contiguous())
     tape.backward()
-    return tuple(tape._take(id(p)) for p in params)
+    ws = getattr(tape, "wstream", None)
+    if ws is not None:
+        torch.cuda.current_stream().wait_stream(ws)
+    grads = tuple(tape._take(id(p)) for p in params)
+    tape.keep.clear()
+    return grads
 
 
 @torch.no_grad()
@@ -544,6 +562,8 @@ def energy_and_forces(model, inputs, train=False):
     forces = []
     E_mol = None
     streams = None if train else _lanes(model)
+    if train:
+        dense_ops.refresh()   # the optimiser changed every weight: ONE launch re-packs every tcgen05 image
     for target in range(n_passes):
         tape = Tape(enabled=need_forces or train, streams=streams, train=train)
         if need_forces:
@@ -552,6 +572,8 @@ def energy_and_forces(model, inputs, train=False):
             for prm in model.parameters():
                 if prm.requires_grad:
                     tape.require(prm)
+            if os.environ.get("GEMNET_B200_WGRAD_STREAM", "1") != "0":
+                tape.wstream = side_stream(model)[0]
         wt = (lambda prm: prm) if train else (lambda prm: prm.detach())
         run = _Run(model, tape, plan)
         A = tape.apply

@@ -41,17 +41,22 @@ def _terms(tl):
     return [Term(g, sc, idx=idx, mul=mul) for g, sc, idx, mul in tl]
 
 
-def _save_operands(steps, rows, like):
-    """training: every step stores its GEMM operand (the weight gradient's factor); a step that reuses its
-    predecessor's operand unchanged (no fill, predecessor without TO_A / A_FROM_CARRY) aliases the predecessor's"""
+def _wkey(st):
+    W = st.weight[3]
+    return (W.data_ptr(), tuple(W.shape), tuple(W.stride()))
+
+
+def _save_operands(steps, rows, like, fwd=None):
+    """training: every step stores its GEMM operand (the weight gradient's factor).  A step that reuses its
+    predecessor's operand unchanged (no fill, predecessor without TO_A / A_FROM_CARRY) aliases the predecessor's."""
     prev = None
     for st in steps:
-        unchanged = prev is not None and not st.terms and not (prev.flags & (TO_A | A_FROM_CARRY))
-        if unchanged:
+        if prev is not None and not st.terms and not (prev.flags & (TO_A | A_FROM_CARRY)):
             st.save_alias = prev if prev.save_x is not None else getattr(prev, "save_alias", None)
         else:
             st.save_x = _new(rows, st.K, like)
         prev = st
+    return None
 
 
 def _operand(st):
@@ -61,17 +66,22 @@ def _operand(st):
     return None if al is None else al.save_x
 
 
-def _weight_grads(tape, fwd_steps, bwd_steps):
-    """dW = (operand of the backward step)^T @ (operand of the forward step) for every weight both programs use"""
-    fmap = {}
-    for st in fwd_steps:
-        W = st.weight[3]
-        fmap[(W.data_ptr(), tuple(W.shape), tuple(W.stride()))] = _operand(st)
+def _weight_grads(tape, fwd_steps, fstack, bwd_steps, gstack):
+    """dW = (operand of the backward step)^T @ (operand of the forward step) for every weight both programs use:
+    library GEMMs with the row count as reduction dimension (cuBLAS split-K), issued on the tape's weight-gradient
+    stream so that they run beside the latency-bound chain kernels of the remaining backward pass.
+    (One batched GEMM per chain was measured slower: 7 x (128 x 128) outputs with K = 8186 and no split-K.)"""
+    fmap = {_wkey(st): _operand(st) for st in fwd_steps}
+    pairs = []
     for st in bwd_steps:
-        W = st.weight[3]
-        a, gz = fmap.get((W.data_ptr(), tuple(W.shape), tuple(W.stride()))), _operand(st)
+        a, gz = fmap.get(_wkey(st)), _operand(st)
         if a is not None and gz is not None:
+            pairs.append((st.weight[3], gz, a))
+
+    def work():
+        for W, gz, a in pairs:
             tape.add_wgrad(W, ops.weight_grad(gz, a))
+    tape.on_wgrad_stream(work, [t for _, gz, a in pairs for t in (gz, a)])
 
 
 def _is_silu(d):
@@ -146,8 +156,7 @@ class TripPrologue:
         x = _new(E, Wd.shape[0], m)
         steps = [Step(_pw(Wb), terms=[Term(m)], flags=ACT | TO_A, s_acc=s, mul_early=r, aux=ctx.aux, dact=ctx.d1),
                  Step(_pw(Wd), flags=ACT, dact=ctx.d2, out=x)]
-        if ctx.train:
-            _save_operands(steps, E, m)
+        ctx.fstack = _save_operands(steps, E, m) if ctx.train else None
         ctx.fsteps = steps
         chain.run(Program(E, steps))
         return x
@@ -164,11 +173,10 @@ class TripPrologue:
                       next_amul=ctx.d1)]
         if need_m or ctx.train:
             steps.append(Step(_pw(ctx.Wb, True), out=g_m))
-        if ctx.train:
-            _save_operands(steps, ctx.E, ctx.aux)
+        gstack = _save_operands(steps, ctx.E, ctx.aux, (ctx.fsteps, ctx.fstack)) if ctx.train else None
         chain.run(Program(ctx.E, steps))
         if ctx.train:
-            _weight_grads(tape, ctx.fsteps, steps)
+            _weight_grads(tape, ctx.fsteps, ctx.fstack, steps, gstack)
         return g_m, g_r, None, None, None
 
 
@@ -201,8 +209,7 @@ class Post:
         _residual_fwd(steps, before, list(blk.layers_before_skip), need, E, m, tail=dict(scale=S2, post0=m, s_post0=S2))
         out = _new(E, H, m)
         _residual_fwd(steps, after, list(blk.layers_after_skip), need, E, m, tail=dict(out=out))
-        if ctx.train:
-            _save_operands(steps, E, m)
+        ctx.fstack = _save_operands(steps, E, m) if ctx.train else None
         ctx.fsteps = steps
         chain.run(Program(E, steps))
         ctx.save = (ups, Wc, dc, before, after, c, E, H, plan.id_swap, x4 is not None)
@@ -235,11 +242,10 @@ class Post:
             steps.append(Step(_pw(Wac, True), out=gb, out_idx=swap, flags=(A_FROM_CARRY if nxt is not None else 0),
                               s_a=c, next_amul=nxt))
             grads_x.append([(ga, 1.0, None, None), (gb, 1.0, None, None)])
-        if ctx.train:
-            _save_operands(steps, E, like)
+        gstack = _save_operands(steps, E, like, (ctx.fsteps, ctx.fstack)) if ctx.train else None
         chain.run(Program(E, steps))
         if ctx.train:
-            _weight_grads(tape, ctx.fsteps, steps)
+            _weight_grads(tape, ctx.fsteps, ctx.fstack, steps, gstack)
         return g_m, grads_x[0], (grads_x[1] if has4 else None), None, None
 
 
@@ -266,8 +272,7 @@ class AtomChain:
         _residual_fwd(steps, saved, mlp[1:], need, n, x0, tail=dict(scale=S2, post0=h, s_post0=S2, out=h2))
         steps.append(Step(_pw(Wpc), out=p_c))
         steps.append(Step(_pw(Wpa), out=p_a))
-        if ctx.train:
-            _save_operands(steps, n, x0)
+        ctx.fstack = _save_operands(steps, n, x0) if ctx.train else None
         ctx.fsteps = steps
         chain.run(Program(n, steps))
         ctx.save = (W0, d0, saved, Wpc, Wpa, n, A)
@@ -290,11 +295,10 @@ class AtomChain:
                       next_amul=saved[-1][3], **post)]
         _residual_bwd(steps, saved, None, dict(flags=TO_A, next_amul=d0))
         steps.append(Step(_pw(W0, True), out=g_x))
-        if ctx.train:
-            _save_operands(steps, n, d0)
+        gstack = _save_operands(steps, n, d0, (ctx.fsteps, ctx.fstack)) if ctx.train else None
         chain.run(Program(n, steps))
         if ctx.train:
-            _weight_grads(tape, ctx.fsteps, steps)
+            _weight_grads(tape, ctx.fsteps, ctx.fstack, steps, gstack)
         return g_x, g_h, None
 
 
@@ -316,8 +320,7 @@ class EdgeEmb:
                       flags=ACT | SET_CARRY | TO_A, dact=d0)]
         saved = []
         _residual_fwd(steps, saved, list(blk.residual_m), need, E, m, tail=dict(scale=S2, post0=m, s_post0=S2, out=out))
-        if ctx.train:
-            _save_operands(steps, E, m)
+        ctx.fstack = _save_operands(steps, E, m) if ctx.train else None
         ctx.fsteps = steps
         chain.run(Program(E, steps))
         ctx.save = (Wm, d0, saved, E, H, plan, p_c.shape[0])
@@ -335,11 +338,10 @@ class EdgeEmb:
         # carry = dL/dm'' for the whole program (one residual layer: nothing in between overwrites it)
         _residual_bwd(steps, saved, _terms(G), dict(flags=TO_A, mul_late=d0, out=g_z))
         steps.append(Step(_pw(Wm, True), flags=CARRY_ADD, s_carry=S2, out=g_m))
-        if ctx.train:
-            _save_operands(steps, E, d0)
+        gstack = _save_operands(steps, E, d0, (ctx.fsteps, ctx.fstack)) if ctx.train else None
         chain.run(Program(E, steps))
         if ctx.train:
-            _weight_grads(tape, ctx.fsteps, steps)
+            _weight_grads(tape, ctx.fsteps, ctx.fstack, steps, gstack)
         g_pc = ops.segment_sum_rows(g_z, plan.src_perm, plan.src_rowptr, n_atoms)
         g_pa = ops.segment_sum_rows(g_z, plan.atom_perm, plan.atom_rowptr, n_atoms)
         return g_m, g_pc, g_pa, None, None
@@ -363,8 +365,7 @@ class OutChain:
         ctx.v_last = _new(n, w_out.shape[1], x0) if ctx.train else None   # training: features the output layer sees
         _residual_fwd(steps, saved, mlp[1:], need, n, x0,
                       tail=dict(dot_w=w_out, dot_out=E_new, dot_in=E_prev, out=ctx.v_last))
-        if ctx.train:
-            _save_operands(steps, n, x0)
+        ctx.fstack = _save_operands(steps, n, x0) if ctx.train else None
         ctx.fsteps = steps
         chain.run(Program(n, steps))
         ctx.save = (W0, d0, saved, w_out, n)
@@ -384,11 +385,10 @@ class OutChain:
             steps = []
             _residual_bwd(steps, saved, [Term(g, sc, mul=w_out, kind=1)], dict(flags=TO_A, next_amul=d0))
             steps.append(Step(_pw(W0, True), out=g_x))
-            if ctx.train:
-                _save_operands(steps, n, d0)
+            gstack = _save_operands(steps, n, d0, (ctx.fsteps, ctx.fstack)) if ctx.train else None
             chain.run(Program(n, steps))
             if ctx.train:
-                _weight_grads(tape, ctx.fsteps, steps)
+                _weight_grads(tape, ctx.fsteps, ctx.fstack, steps, gstack)
                 tape.add_wgrad(w_out, ops.weight_grad(g if sc == 1.0 else g * sc, ctx.v_last))
         return g_x, ([(g, sc, None, None)] if ctx.needs_input_grad[1] else None), None, None
 

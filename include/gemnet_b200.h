@@ -256,6 +256,15 @@ int gemnet_segment_sum_rows(const float* src, const int32_t* perm, const int32_t
 int64_t gemnet_dense_pack_floats(int32_t N, int32_t K);
 int gemnet_dense_pack_weight(const float* W, int64_t stride_n, int64_t stride_k, int32_t N, int32_t K, float* packed,
                              void* stream);
+/* the same for many weights in ONE launch: `table_device` = n_entries descriptors in DEVICE memory (training re-packs
+ * every image after every optimiser step; Np / Kp = N / K rounded up to 64 or 128 as gemnet_dense_pack_weight does) */
+typedef struct {
+  const float* src;
+  float* dst;
+  int64_t stride_n, stride_k;
+  int32_t N, K, Np, Kp;
+} gemnet_pack_desc;
+int gemnet_dense_pack_many(const gemnet_pack_desc* table_device, int32_t n_entries, void* stream);
 int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int32_t ldx, const float* packed,
                     int32_t N, int32_t act, float s_acc, const float* res, float s_res, float* y, float* dact,
                     int32_t flags, void* stream);
