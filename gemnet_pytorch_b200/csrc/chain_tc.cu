@@ -88,6 +88,9 @@ __device__ __forceinline__ float load_elem(const uint8_t* X, int row, int k) {
   return (__uint_as_float(h << 16) + __uint_as_float(m << 16)) + __uint_as_float(l << 16);
 }
 
+// kSave: the training variant (steps may store their operand, `save_x`); the inference variant compiles it away — the
+// extra pointers cost the epilogue ~1k cycles per step in register pressure even when they are NULL.
+template <bool kSave>
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, int weights_settled,
                 long long* __restrict__ prof) {
@@ -150,6 +153,9 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   const int f = q * 32 + lane;                  // feature (accumulator row = TMEM lane) of this thread
   const int e_loc = cg * 16;                    // first tile row of this thread's 16 values
   const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)e_loc;
+  // element (tile row e_loc + j, k = f) of the operand: xf_base + j * 128 + ((xf_g ^ (j & 7)) << 4)   (e_loc % 8 == 0)
+  uint8_t* const xf_base = X + (f >> 6) * CHUNK_BYTES + e_loc * 128 + (f & 7) * 2;
+  const int xf_g = (f & 63) >> 3;
   uint32_t gemm = 0;                            // GEMMs issued by this CTA (parity of acc_full)
   uint32_t wuse0 = 0, wuse1 = 0;                // fills of weight slot 0 / 1 consumed so far (thread 0)
 
@@ -180,8 +186,13 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       const int fc = min(f, Knext - 1);
       float w[16];
       if (full) {
+        if (s_a == 1.0f) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = vals[j] * s_a;
+          for (int j = 0; j < 16; ++j) w[j] = vals[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = vals[j] * s_a;
+        }
         if (amul) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) w[j] *= __ldg(amul + (rb + j) * Knext + fc);
@@ -198,9 +209,20 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       }
       if (f < (Knext > 64 ? 128 : 64)) {                    // inside the padded operand width
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) store_pair(X, e_loc + j, f, w[j], w[j + 1]);
+        for (int j = 0; j < 16; j += 2) {
+          uint32_t h, m, l;
+          split3(w[j], w[j + 1], h, m, l);
+          uint8_t* p0 = xf_base + j * 128 + ((xf_g ^ (j & 7)) << 4);
+          uint8_t* p1 = xf_base + (j + 1) * 128 + ((xf_g ^ ((j + 1) & 7)) << 4);
+          *reinterpret_cast<uint16_t*>(p0) = (uint16_t)h;
+          *reinterpret_cast<uint16_t*>(p1) = (uint16_t)(h >> 16);
+          *reinterpret_cast<uint16_t*>(p0 + SPLIT_BYTES) = (uint16_t)m;
+          *reinterpret_cast<uint16_t*>(p1 + SPLIT_BYTES) = (uint16_t)(m >> 16);
+          *reinterpret_cast<uint16_t*>(p0 + 2 * SPLIT_BYTES) = (uint16_t)l;
+          *reinterpret_cast<uint16_t*>(p1 + 2 * SPLIT_BYTES) = (uint16_t)(l >> 16);
+        }
       }
-      if (save != nullptr && kv) {                          // training: the operand itself (coalesced over f)
+      if (kSave && save != nullptr && kv) {                 // training: the operand itself (coalesced over f)
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (j < nv) save[(rb + j) * Knext + f] = w[j];
@@ -217,7 +239,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         const int gpr = 8 * NKB;                                   // granules (8 columns) per operand row
         const bool fold_amul = st.amul != nullptr && !st.load_set_carry;
         // the fill IS the operand unless a carry read-back multiplies it afterwards (then operand_from stores it)
-        const bool save_here = st.save_x != nullptr && !(st.load_set_carry && st.amul != nullptr);
+        const bool save_here = kSave && st.save_x != nullptr && !(st.load_set_carry && st.amul != nullptr);
         // PG (row, granule) pieces per thread: 64 rows x 8|16 granules = 512|1024 pieces, all loads in flight together
         auto fill = [&](auto pg_tag) {
           constexpr int PG = decltype(pg_tag)::value;
@@ -304,7 +326,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 #pragma unroll
           for (int j = 0; j < 16; ++j) c[j] = kin ? load_elem(X, e_loc + j, min(f, 64 * NKB - 1)) : 0.f;
           carry_st(c);
-          if (st.amul) operand_from(c, K, 1.0f, st.amul, false, st.save_x);   // (each thread rewrites exactly the elements it read)
+          if (st.amul) operand_from(c, K, 1.0f, st.amul, false, kSave ? st.save_x : nullptr);   // (each thread rewrites exactly the elements it read)
         }
       }
       stamp();  // step: operand written by this thread
@@ -417,23 +439,30 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
             v[j] += st.pre1[pr * N + fc];
           }
         }
-        if (flags & GEMNET_CHAIN_ACT) {
+        // the layer's output scale s_acc is folded into the activation's constant (no separate multiplies)
+        const bool act = (flags & GEMNET_CHAIN_ACT) != 0;
+        if (act) {
+          const float kk = kSiluScale * s_acc;
           if (need_d) {
   #pragma unroll
-            for (int j = 0; j < 16; ++j) scaled_silu(v[j], v[j], d[j]);
+            for (int j = 0; j < 16; ++j) scaled_silu(v[j], kk, v[j], d[j]);
           } else {
   #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = scaled_silu_value(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = scaled_silu_value(v[j], kk);
           }
-        } else if (need_d) {
+        } else {
   #pragma unroll
-          for (int j = 0; j < 16; ++j) d[j] = 1.f;
+          for (int j = 0; j < 16; ++j) v[j] *= s_acc;
+          if (need_d) {
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) d[j] = s_acc;
+          }
         }
         if (st.mul_early) {
   #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float t = __ldg(st.mul_early + off0 + (int64_t)JJ(j) * N);
-            if (st.aux && OKJ(j)) st.aux[(rb + j) * N + f] = v[j] * s_acc;
+            if (st.aux && OKJ(j)) st.aux[(rb + j) * N + f] = v[j];   // (already times s_acc)
             v[j] *= t;
             if (need_d) d[j] *= t;
           }
@@ -441,17 +470,14 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         if (need_d) {  // stored here: the derivative's registers are free for the rest of the program
   #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (OKJ(j)) st.dact[(rb + j) * N + f] = d[j] * s_acc;
+            if (OKJ(j)) st.dact[(rb + j) * N + f] = d[j];
         }
         if (flags & GEMNET_CHAIN_CARRY_ADD) {
           float c[16];
           carry_ld(c);
           const float sc = st.s_carry;
   #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_acc, c[j] * sc);
-        } else {
-  #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= s_acc;
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(c[j], sc, v[j]);
         }
         if (st.post0) {
           const float sp = st.s_post0;
@@ -491,18 +517,22 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         }
         if (flags & GEMNET_CHAIN_SET_CARRY) {
           const float sc = st.s_set_carry;
-          float c[16];
+          if (sc == 1.0f) {
+            carry_st(v);
+          } else {
+            float c[16];
   #pragma unroll
-          for (int j = 0; j < 16; ++j) c[j] = v[j] * sc;
-          carry_st(c);
+            for (int j = 0; j < 16; ++j) c[j] = v[j] * sc;
+            carry_st(c);
+          }
         }
         if (!last) {
           if (flags & GEMNET_CHAIN_TO_A) {
-            operand_from(v, Knext, st.s_a, st.next_amul, FULL, prog.step[s + 1].save_x);
+            operand_from(v, Knext, st.s_a, st.next_amul, FULL, kSave ? prog.step[s + 1].save_x : nullptr);
           } else if (flags & GEMNET_CHAIN_A_FROM_CARRY) {
             float c[16];
             carry_ld(c);
-            operand_from(c, Knext, st.s_a, st.next_amul, FULL, prog.step[s + 1].save_x);
+            operand_from(c, Knext, st.s_a, st.next_amul, FULL, kSave ? prog.step[s + 1].save_x : nullptr);
           }
         }
       };
@@ -557,10 +587,14 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
       GEMNET_REQUIRE(st.term[t].src && (st.term[t].kind == 0 || st.term[t].mul), "chain: operand term without source");
     GEMNET_REQUIRE(!st.dot_w || st.dot_out, "chain: dot_w without dot_out");
   }
+  bool save = false;
+  for (int s = 0; s < p.n_steps; ++s) save |= p.step[s].save_x != nullptr;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chain::chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(chain::chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          chain::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(chain::chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("chain_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return 1;
@@ -581,7 +615,8 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const int settled = (flags & GEMNET_DENSE_WEIGHTS_SETTLED) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel, p, n_tiles, settled, g_chain_prof);
+  cudaError_t e = save ? cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<true>, p, n_tiles, settled, g_chain_prof)
+                       : cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false>, p, n_tiles, settled, g_chain_prof);
   if (e != cudaSuccess) {
     set_error("gemnet_chain_tc: launch failed: %s", cudaGetErrorString(e));
     return 1;

@@ -116,19 +116,26 @@ __device__ __forceinline__ void join3(uint32_t h, uint32_t m, uint32_t l, float&
 constexpr float kSiluScale = 1.0f / 0.6f;
 constexpr float kShrinkPerStep = 1.25e-8f;  // mean relative toward-zero rounding loss of one tcgen05 accumulate
 
-// silu(z)/0.6 and its derivative; sigmoid and 1 - sigmoid from exp(-|z|): no overflow / cancellation
-__device__ __forceinline__ void scaled_silu(float z, float& v, float& d) {
-  const float t = __expf(-fabsf(z));            // ex2.approx: 2 ulp, no slow path
-  const float rr = __fdividef(1.0f, 1.0f + t);  // rcp.approx (1 + t in (1, 2])
-  const float sg = z >= 0.f ? rr : t * rr, oms = z >= 0.f ? t * rr : rr;
-  v = z * sg * kSiluScale;
-  d = sg * fmaf(z, oms, 1.0f) * kSiluScale;
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
-
-__device__ __forceinline__ float scaled_silu_value(float z) {
+// k * silu(z) and k * d/dz silu(z) (k = 1/0.6 times the layer's output scale, folded by the caller); sigmoid and
+// 1 - sigmoid from exp(-|z|): no overflow / cancellation; ex2.approx and rcp.approx (2 ulp), no slow paths
+__device__ __forceinline__ void scaled_silu(float z, float k, float& v, float& d) {
   const float t = __expf(-fabsf(z));
-  const float rr = __fdividef(1.0f, 1.0f + t);
-  return z * (z >= 0.f ? rr : t * rr) * kSiluScale;
+  const float rr = rcp_approx(1.0f + t);      // 1 + t in (1, 2]
+  const float p = t * rr;
+  const float sg = z >= 0.f ? rr : p, oms = z >= 0.f ? p : rr;
+  const float sk = sg * k;
+  v = z * sk;
+  d = sk * fmaf(z, oms, 1.0f);
+}
+__device__ __forceinline__ float scaled_silu_value(float z, float k) {
+  const float t = __expf(-fabsf(z));
+  const float rr = rcp_approx(1.0f + t);
+  return z * ((z >= 0.f ? rr : t * rr) * k);
 }
 
 }  // namespace tcx

@@ -1,4 +1,4 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_acceptance.py -m gpu -x -q 2>&1 | tail -4
-timeout 300 python bench.py --mode train --steps 20 --warmup 3 2> gpurun_out/train1.err | tail -1 | tee gpurun_out/bench_r02_train_n1.json | cut -c1-500; tail -2 gpurun_out/train1.err
-timeout 300 python bench.py --mode train --eager --steps 10 --warmup 3 2>/dev/null | tail -1 | cut -c1-260
+timeout 300 python -m pytest tests/test_gpu_chain.py -x -q -m gpu 2>&1 | tail -2
+python profiles/prof_chain_phases.py 8186 3 2>&1 | sed -n 1,12p
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --large-batch 0 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches_per_step')}, d['e2e']['ms_per_step'], d['roofline_chain']['us_per_launch'])"
