@@ -759,7 +759,8 @@ static int launch_fwd(const float* x, const int32_t* expand, const int32_t* rowp
 template <typename Cfg>
 static int launch_bwd(const float* x, const int32_t* expand, const int32_t* rowptr, const float* sph,
                       const float* rbf_W1, const float* W, float scale, int64_t n_edges, const float* g_out,
-                      float* g_x, float* g_sph, float* g_rbf_W1, float* workspace, cudaStream_t st) {
+                      float* g_x, float* g_sph, float* g_rbf_W1, float* workspace, cudaStream_t st,
+                      bool a_saved = false) {
   const size_t smem = sizeof(float) * (Cfg::EB * Cfg::LD + Cfg::EB * Cfg::O + Cfg::STAGE_FLOATS);
   static bool configured = false;
   if (!configured) {
@@ -772,7 +773,7 @@ static int launch_bwd(const float* x, const int32_t* expand, const int32_t* rowp
     const unsigned wgrid = (unsigned)ceil_div(n_edges, kSplitWarps);
     float* A = workspace;
     float* dA = workspace + n_edges * (Cfg::S * Cfg::C);
-    if (g_rbf_W1)
+    if (g_rbf_W1 && !a_saved)   // (a_saved: the forward's segment sums are still in the workspace head)
       launch_pdl(segsum_kernel<Cfg>, wgrid, kSplitWarps * 32, 0, st, x, expand, rowptr, sph, n_edges, A);
     launch_pdl(segbil_bwd_edges_kernel<Cfg>, grid, Cfg::THREADS, smem, st, rbf_W1, W, scale, n_edges, g_out, A, dA,
                g_rbf_W1);
@@ -911,6 +912,8 @@ GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, con
                                       const float* g_out, float* g_x, float* g_sph, float* g_rbf_W1, float* g_W,
                                       void* workspace, void* stream) {
   GEMNET_REQUIRE(n_edges >= 0 && n_units >= 0, "negative size");
+  const bool a_saved = (algo & GEMNET_SEGBIL_A_SAVED) != 0;
+  algo &= ~GEMNET_SEGBIL_A_SAVED;
   GEMNET_REQUIRE(algo >= 0 && algo <= 3 && algo != 2, "algo: 0 fp32 CUDA cores, 1 tcgen05, 3 tcgen05 with a pre-packed weight image");
   GEMNET_REQUIRE(g_W == nullptr, "g_W is computed by the host wrapper in this library version; pass NULL");
   const int sid = shape_id(S, C, I, O);
@@ -935,5 +938,6 @@ GEMNET_API int gemnet_segbilinear_bwd(const float* x, const int32_t* expand, con
   float* ws = split_enabled() ? static_cast<float*>(workspace) : nullptr;
   if (sid == 1)
     return launch_bwd<TripCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, ws, st);
-  return launch_bwd<QuadCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, ws, st);
+  return launch_bwd<QuadCfg>(x, expand, rowptr, sph, rbf_W1, W, scale, n_edges, g_out, g_x, g_sph, g_rbf_W1, ws, st,
+                             a_saved && ws != nullptr);
 }

@@ -391,10 +391,14 @@ class _SegBilinear(Function):
         else:
             algo = 0
             nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, algo, 0)
+            keep = nws > 0 and (any(ctx.needs_input_grad[:3]) if hasattr(ctx, "needs_input_grad") else False)
+            if keep:  # split pipeline + a backward will follow: keep the segment sums for it (workspace of bwd size)
+                nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, algo, 1)
             ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
             _check(_L().gemnet_segbilinear_fwd(_p(x), _p(_i32(expand)), _p(_i32(rowptr)), _p(sph), _p(rbf_W1), _p(W),
                                                scale, E, U, S, C, I, O, algo, _p(out), _p(ws), _stream()),
                    "gemnet_segbilinear_fwd", kernels=1 if ws is None else 2)
+            ctx.ws_saved = ws if keep else None
         ctx.save_for_backward(x, sph, rbf_W1, W, expand, rowptr)
         ctx.cfg = (scale, algo)
         return out
@@ -415,7 +419,11 @@ class _SegBilinear(Function):
             tc = bool(algo) and _tc_shape(S, C, I, O) and BWD_TC[0]
             a = 3 if tc else 0
             nws = _L().gemnet_segbilinear_workspace_bytes(E, S, C, I, O, a, 1)
-            ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
+            ws = getattr(ctx, "ws_saved", None)
+            if ws is not None and not tc and ws.numel() >= nws:
+                a |= 4  # GEMNET_SEGBIL_A_SAVED: the forward's segment sums are in the workspace head
+            else:
+                ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
             Wk = segbil_packed(W, True) if tc else W
             _check(_L().gemnet_segbilinear_bwd(_p(x), _p(expand), _p(rowptr), _p(sph), _p(rbf_W1), _p(Wk), scale, E, U,
                                                S, C, I, O, a, _p(g), _p(g_x), _p(g_sph), _p(g_rw), None, _p(ws),

@@ -166,6 +166,10 @@ int gemnet_downproj_bwd(const float* rad, const float* Wd, const int32_t* l_of_s
  * ---------------------------------------------------------------------------------------------- */
 #define GEMNET_SEGBIL_TC 1
 #define GEMNET_SEGBIL_PREPACKED 2
+/* _bwd only, fp32 split pipeline (the quadruplet shape): the workspace handed in is the one the forward call used
+ * (allocated with the BACKWARD size), whose head still holds the segment sums A (E,S,C): the backward skips
+ * recomputing them (166 us of a 700 us quadruplet backward at batch 64) */
+#define GEMNET_SEGBIL_A_SAVED 4
 int64_t gemnet_segbilinear_workspace_bytes(int64_t n_edges, int32_t S, int32_t C, int32_t I, int32_t O, int32_t algo,
                                            int32_t backward);
 /* packed bf16 hi/lo weight images of the tcgen05 kernels (0 bytes = no tensor-core kernel for the shape) */

@@ -65,6 +65,30 @@ def test_forward_matches_reference_fixture(name, dev):
     check(E, F, fx["E32"], fx["F32"])
 
 
+@pytest.mark.parametrize("fixture", ["model_Q_b64", "model_Q_c8", "model_T_c8_clusters"])
+def test_forward_matches_reference_fixture_other_configs(fixture, dev):
+    """BASELINE configs[2] (GemNet-Q, COLL batch 64) and configs[4] (cutoff 8 A: GemNet-Q on COLL molecules, GemNet-T on
+    the synthetic 18-atom clusters with 4 896 triplets each) against outputs of the UNMODIFIED reference
+    (oracle/make_golden_configs.py): float64 = truth, the reference's own float32 run = yardstick."""
+    fx = H.load_npz(f"{fixture}.npz")
+    kw = H.model_kwargs(fx)
+    sd = go.synthetic_state_dict(kw, seed=int(fx["seed"]))
+    model = make_model(kw, sd, dev)
+    from gemnet_pytorch_b200 import build_batch
+    if "mol_ids" in fx:
+        Rl, Zl = H.molecules(fx["mol_ids"].tolist())
+    else:
+        off = np.concatenate([[0], np.cumsum(fx["N"])])
+        Rl = [fx["R"][off[i]:off[i + 1]] for i in range(len(fx["N"]))]
+        Zl = [fx["Z"][off[i]:off[i + 1]] for i in range(len(fx["N"]))]
+    inputs = build_batch(Rl, Zl, kw["cutoff"], kw["int_cutoff"], kw["triplets_only"])
+    E, F = model(to_dev(inputs, dev))
+    dE, dF = check(E, F, fx["E64"], fx["F64"])
+    refE = np.abs(fx["E32"] - fx["E64"]).max() / np.abs(fx["E64"]).max()
+    refF = np.abs(fx["F32"] - fx["F64"]).max() / np.abs(fx["F64"]).max()
+    print(f"[{fixture}] ours vs ref64: dE {dE:.2e} dF {dF:.2e} | ref32 vs ref64: dE {refE:.2e} dF {refF:.2e}")
+
+
 @pytest.mark.parametrize("name", ["T", "Q"])
 def test_forward_accepts_reference_datacontainer_order(name, dev):
     """Inputs in the reference DataContainer's own (argsort-scrambled) within-segment order give the same result."""
