@@ -1,4 +1,6 @@
-timeout 300 python -m pytest tests/test_gpu_chain.py -x -q -m gpu 2>&1 | tail -2
-python profiles/prof_chain_phases.py 8186 3 2>&1 | sed -n 1,12p
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --large-batch 0 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches_per_step')}, d['e2e']['ms_per_step'], d['roofline_chain']['us_per_launch'])"
+O=gpurun_out
+mkdir -p $O
+N=$(nvidia-smi -L | wc -l)
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --mode train --steps 20 --warmup 3 2> $O/train_n$N.err | tail -1 | tee $O/bench_r02_train_n$N.json | cut -c1-1200
+tail -2 $O/train_n$N.err | cut -c1-300
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --large-batch 0 2> $O/infer_n$N.err | tail -1 | tee $O/bench_r02_T_n$N.json | cut -c1-400
