@@ -61,6 +61,7 @@ _SIGNATURES = {
     "gemnet_rbf_fan_bwd": [_I64, _I32, _P, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P],
     "gemnet_chain_tc": [_P, _I32, _P],
     "gemnet_chain_set_profile_buffer": [_P],
+    "gemnet_chain_set_tile_rows": [_I32],
     "gemnet_graph_build_host": [_P, _P, _I64, _D, _D, _I32, ctypes.POINTER(_P)],
     "gemnet_graph_size": [_P, ctypes.c_char_p],
     "gemnet_graph_copy_host": [_P, ctypes.c_char_p, _P],

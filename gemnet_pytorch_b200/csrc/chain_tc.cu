@@ -38,26 +38,34 @@ namespace chain {
 
 using namespace tcx;
 
-constexpr int TR = 64;                         // rows per tile (the N side of the MMA)
-constexpr int SPLIT_BYTES = TR * 128;          // one bf16 split of one 64-k chunk of the operand: 64 rows x 128 B
-constexpr int CHUNK_BYTES = 3 * SPLIT_BYTES;   // 24576
-constexpr int X_BYTES = 2 * CHUNK_BYTES;       // 49152
+// rows per tile (the N side of the MMA): 64, or 16 when that still gives at most one tile per SM (the atom-level
+// chains: 762 atoms at batch 64) — the MMAs of a step cost the same for any N <= 128, but the epilogue then has 4
+// instead of 16 values per thread.  Template parameter TR of the kernel; the shared-memory map is sized for 64.
+constexpr int X_BYTES = 2 * 3 * 64 * 128;      // 49152: operand, [chunk][split][row][128 B]
 constexpr int WSLOT_BYTES = 3 * 128 * 128;     // 49152: one 64-k chunk of a (<=128)-row weight image, three splits
 constexpr int W_SLOTS = 2;
 constexpr int THREADS = 512;
 constexpr int MISC_BYTES = 2048;               // barriers, TMEM slot, dot buffer (4 quadrants x TR floats)
 constexpr int SMEM_BYTES = 1024 + X_BYTES + W_SLOTS * WSLOT_BYTES + MISC_BYTES;
 constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t ACC_STRIDE = 64, CORR_COL = 128, CARRY_COL = 192;
+// 1: instantiate the FULL epilogue for N / K = 128 and 64 with immediate row strides (fewer address instructions,
+// but 1.5x the code: measured slower on B200 — instruction fetch)
+#ifndef GEMNET_CHAIN_STRIDE_SPEC
+#define GEMNET_CHAIN_STRIDE_SPEC 0
+#endif
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // byte offset (inside one split) of element (row, k) of the K-major SWIZZLE_128B operand: chunk k / 64, 16-byte granule
 // (k % 64) / 8 XOR-swizzled by the row
+template <int TR>
 __device__ __forceinline__ uint32_t x_offset(int row, int k) {
+  constexpr int CHUNK_BYTES = 3 * TR * 128;
   return (uint32_t)((k >> 6) * CHUNK_BYTES + row * 128 + (((((k & 63) >> 3)) ^ (row & 7)) << 4) + (k & 7) * 2);
 }
+template <int TR>
 __device__ __forceinline__ void store_granule(uint8_t* X, int row, int g, const float (&v)[8]) {
+  constexpr int SPLIT_BYTES = TR * 128, CHUNK_BYTES = 3 * SPLIT_BYTES;
   uint32_t h[4], m[4], l[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) split3(v[2 * u], v[2 * u + 1], h[u], m[u], l[u]);
@@ -66,22 +74,10 @@ __device__ __forceinline__ void store_granule(uint8_t* X, int row, int g, const 
   *reinterpret_cast<uint4*>(p + SPLIT_BYTES) = make_uint4(m[0], m[1], m[2], m[3]);
   *reinterpret_cast<uint4*>(p + 2 * SPLIT_BYTES) = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// two values of ONE feature k for two consecutive rows -> the three split tiles (2-byte stores; a warp writes 64
-// contiguous bytes per instruction: conflict free)
-__device__ __forceinline__ void store_pair(uint8_t* X, int row, int k, float v0, float v1) {
-  uint32_t h, m, l;
-  split3(v0, v1, h, m, l);
-  uint8_t* p0 = X + x_offset(row, k);
-  uint8_t* p1 = X + x_offset(row + 1, k);
-  *reinterpret_cast<uint16_t*>(p0) = (uint16_t)h;
-  *reinterpret_cast<uint16_t*>(p1) = (uint16_t)(h >> 16);
-  *reinterpret_cast<uint16_t*>(p0 + SPLIT_BYTES) = (uint16_t)m;
-  *reinterpret_cast<uint16_t*>(p1 + SPLIT_BYTES) = (uint16_t)(m >> 16);
-  *reinterpret_cast<uint16_t*>(p0 + 2 * SPLIT_BYTES) = (uint16_t)l;
-  *reinterpret_cast<uint16_t*>(p1 + 2 * SPLIT_BYTES) = (uint16_t)(l >> 16);
-}
+template <int TR>
 __device__ __forceinline__ float load_elem(const uint8_t* X, int row, int k) {
-  const uint8_t* p = X + x_offset(row, k);
+  constexpr int SPLIT_BYTES = TR * 128;
+  const uint8_t* p = X + x_offset<TR>(row, k);
   const uint32_t h = *reinterpret_cast<const uint16_t*>(p);
   const uint32_t m = *reinterpret_cast<const uint16_t*>(p + SPLIT_BYTES);
   const uint32_t l = *reinterpret_cast<const uint16_t*>(p + 2 * SPLIT_BYTES);
@@ -90,10 +86,78 @@ __device__ __forceinline__ float load_elem(const uint8_t* X, int row, int k) {
 
 // kSave: the training variant (steps may store their operand, `save_x`); the inference variant compiles it away — the
 // extra pointers cost the epilogue ~1k cycles per step in register pressure even when they are NULL.
-template <bool kSave>
+// what one thread of the epilogue owns: feature f (accumulator row = TMEM lane), tile rows e_loc .. e_loc + VPT - 1
+struct ThreadTile {
+  int f, nv, jmax, e_loc, xf_g;   // nv: rows of them inside M; jmax = max(nv - 1, 0)
+  int64_t rb, rbc;                // first row; the same clamped into [0, M)
+  uint8_t* xf_base;               // operand element (tile row e_loc + j, k = f): xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4)
+};
+
+// values of feature f for rows rb .. rb+15 -> the next operand (element (row, k = f)); zero beyond Knext / M
+// KC: the operand width when it is 128 or 64 (compile-time row stride: every access of the thread is then one base
+// pointer + an immediate), 0 = run-time stride
+template <bool kSave, int TR, int KC>
+__device__ __forceinline__ void operand_from(const ThreadTile& t, const float (&vals)[TR / 4], int Knext_rt, float s_a,
+                                             const float* amul, bool full, float* save) {
+  constexpr int VPT = TR / 4, SPLIT_BYTES = TR * 128;
+  const int f = t.f, nv = t.nv, jmax = t.jmax, e_loc = t.e_loc, xf_g = t.xf_g;
+  const int64_t rb = t.rb, rbc = t.rbc;
+  uint8_t* const xf_base = t.xf_base;
+  const int Knext = KC ? KC : Knext_rt;
+  const bool kv = f < Knext;
+  const int fc = min(f, Knext - 1);
+  float w[VPT];
+  if (full) {
+    if (s_a == 1.0f) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) w[j] = vals[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) w[j] = vals[j] * s_a;
+    }
+    if (amul) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) w[j] *= __ldg(amul + (rb * Knext + fc) + j * Knext);
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) w[j] = kv ? w[j] : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) w[j] = (kv && j < nv) ? vals[j] * s_a : 0.f;
+    if (amul) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) w[j] *= __ldg(amul + (rbc + min(j, jmax)) * Knext + fc);
+    }
+  }
+  if (f < (Knext > 64 ? 128 : 64)) {                    // inside the padded operand width
+#pragma unroll
+    for (int j = 0; j < VPT; j += 2) {
+      uint32_t h, m, l;
+      split3(w[j], w[j + 1], h, m, l);
+      uint8_t* p0 = xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4);       // (e_loc % 8 is 0 or 4)
+      uint8_t* p1 = xf_base + (j + 1) * 128 + ((xf_g ^ ((e_loc + j + 1) & 7)) << 4);
+      *reinterpret_cast<uint16_t*>(p0) = (uint16_t)h;
+      *reinterpret_cast<uint16_t*>(p1) = (uint16_t)(h >> 16);
+      *reinterpret_cast<uint16_t*>(p0 + SPLIT_BYTES) = (uint16_t)m;
+      *reinterpret_cast<uint16_t*>(p1 + SPLIT_BYTES) = (uint16_t)(m >> 16);
+      *reinterpret_cast<uint16_t*>(p0 + 2 * SPLIT_BYTES) = (uint16_t)l;
+      *reinterpret_cast<uint16_t*>(p1 + 2 * SPLIT_BYTES) = (uint16_t)(l >> 16);
+    }
+  }
+  if (kSave && save != nullptr && kv) {                 // training: the operand itself (coalesced over f)
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+      if (j < nv) save[(rb * Knext + f) + j * Knext] = w[j];
+  }
+}
+
+template <bool kSave, int TR>
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, int weights_settled,
                 long long* __restrict__ prof) {
+  constexpr int VPT = TR / 4;                                   // values per thread: rows of one feature
+  constexpr int SPLIT_BYTES = TR * 128, CHUNK_BYTES = 3 * SPLIT_BYTES;
+  constexpr uint32_t ACC_STRIDE = TR, CORR_COL = 2 * TR, CARRY_COL = 3 * TR;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -151,83 +215,35 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 
   const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (features 32q..32q+31), row group (16 rows)
   const int f = q * 32 + lane;                  // feature (accumulator row = TMEM lane) of this thread
-  const int e_loc = cg * 16;                    // first tile row of this thread's 16 values
+  const int e_loc = cg * VPT;                   // first tile row of this thread's VPT values
   const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)e_loc;
-  // element (tile row e_loc + j, k = f) of the operand: xf_base + j * 128 + ((xf_g ^ (j & 7)) << 4)   (e_loc % 8 == 0)
+  // element (tile row e_loc + j, k = f) of the operand: xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4)
   uint8_t* const xf_base = X + (f >> 6) * CHUNK_BYTES + e_loc * 128 + (f & 7) * 2;
   const int xf_g = (f & 63) >> 3;
   uint32_t gemm = 0;                            // GEMMs issued by this CTA (parity of acc_full)
   uint32_t wuse0 = 0, wuse1 = 0;                // fills of weight slot 0 / 1 consumed so far (thread 0)
 
-  auto carry_ld = [&](float (&c)[16]) {
-    uint32_t raw[16];
-    tmem_ld16_nowait(t_lane + CARRY_COL, raw);
+  auto carry_ld = [&](float (&c)[VPT]) {
+    uint32_t raw[VPT];
+    tmem_ld_nowait<VPT>(t_lane + CARRY_COL, raw);
     tmem_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) c[j] = __uint_as_float(raw[j]);
+    for (int j = 0; j < VPT; ++j) c[j] = __uint_as_float(raw[j]);
   };
-  auto carry_st = [&](const float (&c)[16]) {
-    uint32_t raw[16];
+  auto carry_st = [&](const float (&c)[VPT]) {
+    uint32_t raw[VPT];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) raw[j] = __float_as_uint(c[j]);
-    tmem_st16(t_lane + CARRY_COL, raw);
+    for (int j = 0; j < VPT; ++j) raw[j] = __float_as_uint(c[j]);
+    tmem_st<VPT>(t_lane + CARRY_COL, raw);
   };
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = (int64_t)tile * TR;
     const int64_t rb = r0 + e_loc;                          // first row of this thread's 16 values
-    const int nv = (int)max((int64_t)0, min((int64_t)16, M - rb));   // valid rows among them
+    const int nv = (int)max((int64_t)0, min((int64_t)VPT, M - rb));   // valid rows among them
     const int64_t rbc = nv > 0 ? rb : M - 1;                // clamped row base / index for loads (always in range)
     const int jmax = max(nv, 1) - 1;
-
-    // values of feature f for rows rb .. rb+15 -> the next operand (element (row, k = f)); zero beyond Knext / M
-    auto operand_from = [&](const float (&vals)[16], int Knext, float s_a, const float* amul, bool full, float* save) {
-      const bool kv = f < Knext;
-      const int fc = min(f, Knext - 1);
-      float w[16];
-      if (full) {
-        if (s_a == 1.0f) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = vals[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = vals[j] * s_a;
-        }
-        if (amul) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] *= __ldg(amul + (rb + j) * Knext + fc);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = kv ? w[j] : 0.f;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = (kv && j < nv) ? vals[j] * s_a : 0.f;
-        if (amul) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] *= __ldg(amul + (rbc + min(j, jmax)) * Knext + fc);
-        }
-      }
-      if (f < (Knext > 64 ? 128 : 64)) {                    // inside the padded operand width
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          uint32_t h, m, l;
-          split3(w[j], w[j + 1], h, m, l);
-          uint8_t* p0 = xf_base + j * 128 + ((xf_g ^ (j & 7)) << 4);
-          uint8_t* p1 = xf_base + (j + 1) * 128 + ((xf_g ^ ((j + 1) & 7)) << 4);
-          *reinterpret_cast<uint16_t*>(p0) = (uint16_t)h;
-          *reinterpret_cast<uint16_t*>(p1) = (uint16_t)(h >> 16);
-          *reinterpret_cast<uint16_t*>(p0 + SPLIT_BYTES) = (uint16_t)m;
-          *reinterpret_cast<uint16_t*>(p1 + SPLIT_BYTES) = (uint16_t)(m >> 16);
-          *reinterpret_cast<uint16_t*>(p0 + 2 * SPLIT_BYTES) = (uint16_t)l;
-          *reinterpret_cast<uint16_t*>(p1 + 2 * SPLIT_BYTES) = (uint16_t)(l >> 16);
-        }
-      }
-      if (kSave && save != nullptr && kv) {                 // training: the operand itself (coalesced over f)
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nv) save[(rb + j) * Knext + f] = w[j];
-      }
-    };
+    const ThreadTile tt{f, nv, jmax, e_loc, xf_g, rb, rbc, xf_base};
 
 #pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
@@ -247,7 +263,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
           int prow[PG], pgr[PG];
 #pragma unroll
           for (int h = 0; h < PG; ++h) {
-            const int p = tid + h * THREADS;
+            const int p = min(tid + h * THREADS, TR * gpr - 1);   // (threads beyond the tile's pieces: see `pin`)
             prow[h] = p / gpr;
             pgr[h] = p % gpr;
 #pragma unroll
@@ -305,28 +321,29 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
               v[h][0] *= m0.x; v[h][1] *= m0.y; v[h][2] *= m0.z; v[h][3] *= m0.w;
               v[h][4] *= m1.x; v[h][5] *= m1.y; v[h][6] *= m1.z; v[h][7] *= m1.w;
             }
+            const bool pin = tid + h * THREADS < TR * gpr;       // this thread owns a piece of the tile in pass h
             const bool valid = r0 + prow[h] < M && pgr[h] * 8 < K;
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[h][j] = valid ? v[h][j] : 0.f;
-            store_granule(X, prow[h], pgr[h], v[h]);
-            if (save_here && valid) {
+            if (pin) store_granule<TR>(X, prow[h], pgr[h], v[h]);
+            if (save_here && valid && pin) {
               float4* dst = reinterpret_cast<float4*>(st.save_x + (r0 + prow[h]) * K + pgr[h] * 8);
               dst[0] = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
               dst[1] = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
             }
           }
         };
-        if (NKB == 2) fill(std::integral_constant<int, 2>{});
+        if (TR * gpr > THREADS) fill(std::integral_constant<int, 2>{});
         else fill(std::integral_constant<int, 1>{});
         if (st.load_set_carry) {
           // the skip value is wanted in the epilogue's thread mapping: read it back from the (exact) operand split
           __syncthreads();
-          float c[16];
+          float c[VPT];
           const bool kin = f < 64 * NKB;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) c[j] = kin ? load_elem(X, e_loc + j, min(f, 64 * NKB - 1)) : 0.f;
+          for (int j = 0; j < VPT; ++j) c[j] = kin ? load_elem<TR>(X, e_loc + j, min(f, 64 * NKB - 1)) : 0.f;
           carry_st(c);
-          if (st.amul) operand_from(c, K, 1.0f, st.amul, false, kSave ? st.save_x : nullptr);   // (each thread rewrites exactly the elements it read)
+          if (st.amul) operand_from<kSave, TR, 0>(tt, c, K, 1.0f, st.amul, false, kSave ? st.save_x : nullptr);   // (each thread rewrites exactly the elements it read)
         }
       }
       stamp();  // step: operand written by this thread
@@ -339,7 +356,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       if (tid == 0) {
         tc_fence_after();
         const int Npad = N > 64 ? 128 : 64;
-        const uint32_t idesc = make_idesc(128, TR);     // D^T tile: 128 features x 64 rows
+        const uint32_t idesc = make_idesc(128, TR);     // D^T tile: 128 features x TR rows
         const uint32_t d_corr = tmem_base + CORR_COL;
         for (int kb = 0; kb < NKB; ++kb) {
           uint32_t& use = kb ? wuse1 : wuse0;
@@ -394,24 +411,28 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       // a warp whose 32 features lie beyond this step's output AND the next operand has nothing to do
       const bool warp_idle = 32 * q >= N && (last || 32 * q >= (Knext > 64 ? 128 : 64));
       // FULL (warp-uniform): all 16 rows and all 32 features of the warp are in range -> no clamps, no predicates
-      auto epilogue = [&](auto full_tag) {
+      // n_tag: N when it is 128 or 64 (FULL only) — compile-time row stride, so the 16 accesses of an array are one
+      // base pointer + immediates instead of four address instructions each; 0 = run-time stride
+      auto epilogue = [&](auto full_tag, auto n_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        const bool fv = FULL || f < N;
-        const int fc = FULL ? f : min(f, N - 1);
+        constexpr int NC = decltype(n_tag)::value;
+        const int NS = NC ? NC : st.N;     // this step's NS (row stride of its arrays)
+        const bool fv = FULL || f < NS;
+        const int fc = FULL ? f : min(f, NS - 1);
         const int64_t RB = FULL ? rb : rbc;
-        const int64_t off0 = RB * N + fc;                  // element j at off0 + JJ(j) * N
+        const int64_t off0 = RB * NS + fc;                  // element j at off0 + JJ(j) * N
         auto OKJ = [&](int j) { return FULL || (fv && j < nv); };
         auto JJ = [&](int j) { return FULL ? j : min(j, jmax); };
 
-        float v[16], d[16];
+        float v[VPT], d[VPT];
         {
-          uint32_t a0[16], a1[16], cc[16];
-          tmem_ld16_nowait(t_lane, a0);
-          tmem_ld16_nowait(t_lane + CORR_COL, cc);
-          if (NKB == 2) tmem_ld16_nowait(t_lane + ACC_STRIDE, a1);
+          uint32_t a0[VPT], a1[VPT], cc[VPT];
+          tmem_ld_nowait<VPT>(t_lane, a0);
+          tmem_ld_nowait<VPT>(t_lane + CORR_COL, cc);
+          if (NKB == 2) tmem_ld_nowait<VPT>(t_lane + ACC_STRIDE, a1);
           tmem_wait_ld();
   #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < VPT; ++j) {
             // compensated sum (dense_tc.cu): the mean truncation loss of the main chains goes through the small
             // correction sum, then ONE round-to-nearest add per accumulator
             float corr = fmaf(__uint_as_float(a0[j]), c0f, __uint_as_float(cc[j]));
@@ -425,18 +446,18 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         }
         if (st.pre0) {
   #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < VPT; ++j) {
             const int64_t rr = RB + JJ(j);
             const int64_t pr = st.pre0_idx ? (int64_t)__ldg(st.pre0_idx + rr) : rr;
-            v[j] += st.pre0[pr * N + fc];
+            v[j] += __ldg(st.pre0 + pr * NS + fc);
           }
         }
         if (st.pre1) {
   #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < VPT; ++j) {
             const int64_t rr = RB + JJ(j);
             const int64_t pr = st.pre1_idx ? (int64_t)__ldg(st.pre1_idx + rr) : rr;
-            v[j] += st.pre1[pr * N + fc];
+            v[j] += __ldg(st.pre1 + pr * NS + fc);
           }
         }
         // the layer's output scale s_acc is folded into the activation's constant (no separate multiplies)
@@ -445,70 +466,95 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
           const float kk = kSiluScale * s_acc;
           if (need_d) {
   #pragma unroll
-            for (int j = 0; j < 16; ++j) scaled_silu(v[j], kk, v[j], d[j]);
+            for (int j = 0; j < VPT; ++j) scaled_silu(v[j], kk, v[j], d[j]);
           } else {
   #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = scaled_silu_value(v[j], kk);
+            for (int j = 0; j < VPT; ++j) v[j] = scaled_silu_value(v[j], kk);
           }
         } else {
   #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= s_acc;
+          for (int j = 0; j < VPT; ++j) v[j] *= s_acc;
           if (need_d) {
   #pragma unroll
-            for (int j = 0; j < 16; ++j) d[j] = s_acc;
+            for (int j = 0; j < VPT; ++j) d[j] = s_acc;
           }
         }
         if (st.mul_early) {
+          const float* pm = st.mul_early + off0;
+          if (st.aux) {
+            float* pa = st.aux + off0;
   #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float t = __ldg(st.mul_early + off0 + (int64_t)JJ(j) * N);
-            if (st.aux && OKJ(j)) st.aux[(rb + j) * N + f] = v[j];   // (already times s_acc)
+            for (int j = 0; j < VPT; ++j)
+              if (OKJ(j)) pa[j * NS] = v[j];             // (already times s_acc)
+          }
+  #pragma unroll
+          for (int j = 0; j < VPT; ++j) {
+            const float t = __ldg(pm + JJ(j) * NS);
             v[j] *= t;
             if (need_d) d[j] *= t;
           }
         }
         if (need_d) {  // stored here: the derivative's registers are free for the rest of the program
+          float* pd = st.dact + off0;
   #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (OKJ(j)) st.dact[(rb + j) * N + f] = d[j];
+          for (int j = 0; j < VPT; ++j)
+            if (OKJ(j)) pd[j * NS] = d[j];
         }
         if (flags & GEMNET_CHAIN_CARRY_ADD) {
-          float c[16];
+          float c[VPT];
           carry_ld(c);
           const float sc = st.s_carry;
   #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(c[j], sc, v[j]);
+          for (int j = 0; j < VPT; ++j) v[j] = fmaf(c[j], sc, v[j]);
         }
         if (st.post0) {
           const float sp = st.s_post0;
+          const float* pp = st.post0 + off0;
   #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(st.post0[off0 + (int64_t)JJ(j) * N], sp, v[j]);
+          for (int j = 0; j < VPT; ++j) v[j] = fmaf(__ldg(pp + JJ(j) * NS), sp, v[j]);
         }
         if (st.post1) {
           const float sp = st.s_post1;
+          const float* pp = st.post1 + off0;
   #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(st.post1[off0 + (int64_t)JJ(j) * N], sp, v[j]);
+          for (int j = 0; j < VPT; ++j) v[j] = fmaf(__ldg(pp + JJ(j) * NS), sp, v[j]);
         }
         if (st.mul_late) {
+          const float* pm = st.mul_late + off0;
   #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= __ldg(st.mul_late + off0 + (int64_t)JJ(j) * N);
+          for (int j = 0; j < VPT; ++j) v[j] *= __ldg(pm + JJ(j) * NS);
         }
   #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (OKJ(j)) ? v[j] : 0.f;
+        for (int j = 0; j < VPT; ++j) v[j] = (OKJ(j)) ? v[j] : 0.f;
         if (st.out) {
           const float ss = st.s_store;
+          float o[VPT];
   #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float o = v[j] * ss;
-            if (st.smul) o *= __ldg(st.smul + off0 + (int64_t)JJ(j) * N);
-            const int64_t orow = st.out_idx ? (int64_t)__ldg(st.out_idx + RB + JJ(j)) : rb + j;
-            if (OKJ(j)) st.out[orow * N + f] = o;
+          for (int j = 0; j < VPT; ++j) o[j] = v[j] * ss;
+          if (st.smul) {
+            const float* pm = st.smul + off0;
+  #pragma unroll
+            for (int j = 0; j < VPT; ++j) o[j] *= __ldg(pm + JJ(j) * NS);
+          }
+          if (st.out_idx) {
+            const int* pi = st.out_idx + RB;
+            float* po = st.out + f;
+  #pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+              const int64_t orow = (int64_t)__ldg(pi + JJ(j));
+              if (OKJ(j)) po[orow * NS] = o[j];
+            }
+          } else {
+            float* po = st.out + off0;
+  #pragma unroll
+            for (int j = 0; j < VPT; ++j)
+              if (OKJ(j)) po[j * NS] = o[j];
           }
         }
         if (st.dot_w) {
           const float wv = __ldg(st.dot_w + fc);
   #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < VPT; ++j) {
             float p = v[j] * wv;                       // (0 for invalid features / rows)
   #pragma unroll
             for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
@@ -520,25 +566,34 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
           if (sc == 1.0f) {
             carry_st(v);
           } else {
-            float c[16];
+            float c[VPT];
   #pragma unroll
-            for (int j = 0; j < 16; ++j) c[j] = v[j] * sc;
+            for (int j = 0; j < VPT; ++j) c[j] = v[j] * sc;
             carry_st(c);
           }
         }
-        if (!last) {
-          if (flags & GEMNET_CHAIN_TO_A) {
-            operand_from(v, Knext, st.s_a, st.next_amul, FULL, kSave ? prog.step[s + 1].save_x : nullptr);
-          } else if (flags & GEMNET_CHAIN_A_FROM_CARRY) {
-            float c[16];
-            carry_ld(c);
-            operand_from(c, Knext, st.s_a, st.next_amul, FULL, kSave ? prog.step[s + 1].save_x : nullptr);
+        if (!last && (flags & (GEMNET_CHAIN_TO_A | GEMNET_CHAIN_A_FROM_CARRY))) {
+          if (!(flags & GEMNET_CHAIN_TO_A)) carry_ld(v);        // (v is dead after this point)
+          float* save = kSave ? prog.step[s + 1].save_x : nullptr;
+          if constexpr (NC != 0) {
+            if (Knext == 128) operand_from<kSave, TR, 128>(tt, v, Knext, st.s_a, st.next_amul, true, save);
+            else if (Knext == 64) operand_from<kSave, TR, 64>(tt, v, Knext, st.s_a, st.next_amul, true, save);
+            else operand_from<kSave, TR, 0>(tt, v, Knext, st.s_a, st.next_amul, true, save);
+          } else {
+            operand_from<kSave, TR, 0>(tt, v, Knext, st.s_a, st.next_amul, FULL, save);
           }
         }
       };
       if (!warp_idle) {
-        if (nv == 16 && 32 * q + 32 <= N) epilogue(std::true_type{});
-        else epilogue(std::false_type{});
+        const bool full = nv == VPT && 32 * q + 32 <= N;
+#if GEMNET_CHAIN_STRIDE_SPEC
+        if (full && N == 128) epilogue(std::true_type{}, std::integral_constant<int, 128>{});
+        else if (full && N == 64) epilogue(std::true_type{}, std::integral_constant<int, 64>{});
+        else epilogue(std::false_type{}, std::integral_constant<int, 0>{});
+#else
+        if (full) epilogue(std::true_type{}, std::integral_constant<int, 0>{});
+        else epilogue(std::false_type{}, std::integral_constant<int, 0>{});
+#endif
       }
       stamp();  // step: epilogue of this thread done
       if (st.dot_w) {
@@ -563,8 +618,15 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
 
 using namespace gemnet;
 
+static int g_chain_rows = 0;
 static long long* g_chain_prof = nullptr;
 namespace gemnet { void segbil_fwd_tc_set_profile_buffer(long long* p); }
+GEMNET_API int gemnet_chain_set_tile_rows(int rows) {
+  GEMNET_REQUIRE(rows == 0 || rows == 16 || rows == 64, "chain: tile rows must be 0 (automatic), 16 or 64");
+  g_chain_rows = rows;
+  return 0;
+}
+
 GEMNET_API void gemnet_chain_set_profile_buffer(void* device_int64_x256) {
   g_chain_prof = static_cast<long long*>(device_int64_x256);
   gemnet::segbil_fwd_tc_set_profile_buffer(g_chain_prof);   // the same buffer serves the H7 forward kernel's stamps
@@ -591,19 +653,25 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   for (int s = 0; s < p.n_steps; ++s) save |= p.step[s].save_x != nullptr;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chain::chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(chain::chain_tc_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          chain::SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(chain::chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
+      e = cudaFuncSetAttribute(chain::chain_tc_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(chain::chain_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(chain::chain_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("chain_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return 1;
     }
     configured = true;
   }
-  const int n_tiles = (int)ceil_div(p.M, chain::TR);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  // 16-row tiles while they still fit one per SM (atom-level chains): same MMA time per step, a quarter of the epilogue
+  const bool small = g_chain_rows ? g_chain_rows == 16 : ceil_div(p.M, 16) <= sms;
+  const int n_tiles = (int)ceil_div(p.M, small ? 16 : 64);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_tiles < sms ? n_tiles : sms);
   cfg.blockDim = dim3(chain::THREADS);
@@ -615,8 +683,13 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const int settled = (flags & GEMNET_DENSE_WEIGHTS_SETTLED) ? 1 : 0;
-  cudaError_t e = save ? cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<true>, p, n_tiles, settled, g_chain_prof)
-                       : cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false>, p, n_tiles, settled, g_chain_prof);
+  cudaError_t e;
+  if (small)
+    e = save ? cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<true, 16>, p, n_tiles, settled, g_chain_prof)
+             : cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false, 16>, p, n_tiles, settled, g_chain_prof);
+  else
+    e = save ? cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<true, 64>, p, n_tiles, settled, g_chain_prof)
+             : cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false, 64>, p, n_tiles, settled, g_chain_prof);
   if (e != cudaSuccess) {
     set_error("gemnet_chain_tc: launch failed: %s", cudaGetErrorString(e));
     return 1;

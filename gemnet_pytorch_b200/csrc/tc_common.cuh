@@ -94,6 +94,27 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+template <int NV>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t (&r)[NV]) {
+  if constexpr (NV == 16) tmem_ld16_nowait(taddr, r);
+  else tmem_ld4_nowait(taddr, r);
+}
+template <int NV>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[NV]) {
+  if constexpr (NV == 16) tmem_st16(taddr, r);
+  else tmem_st4(taddr, r);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // exact three-way bf16 split of two fp32 values: v = h + m + l (each packed as bf16x2, low half = first value)

@@ -358,6 +358,10 @@ typedef struct {
 } gemnet_chain_program;
 
 int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t flags, void* stream);
+/* rows per tile of the following launches: 0 (default) = automatic — 16-row tiles while ceil(M / 16) <= the SM count
+ * (atom-level chains; a quarter of the epilogue per step at the same MMA time), else 64; 16 / 64 force one variant
+ * (tests, measurements).  Results do not depend on it beyond fp32 summation order of the dot epilogue. */
+int gemnet_chain_set_tile_rows(int32_t rows);
 /* diagnostics: when non-NULL, thread 0 of CTA 0 of every following gemnet_chain_tc launch writes clock64() stamps of its
  * phase boundaries (<= 250 int64) to this device buffer; NULL (default) switches it off. */
 void gemnet_chain_set_profile_buffer(void* device_int64_x256);

@@ -18,7 +18,19 @@ def dev():
 
 
 def run_both(build, dev):
-    """build(out: dict-like allocator) -> Program; run the kernel and the interpreter on separate outputs, compare."""
+    """build(out: dict-like allocator) -> Program; run the kernel — with automatic, 16-row and 64-row tiles — and the
+    interpreter on separate outputs, compare."""
+    from gemnet_pytorch_b200 import _lib
+    try:
+        for rows in (0, 16, 64):
+            _lib.check(_lib.load().gemnet_chain_set_tile_rows(rows), "gemnet_chain_set_tile_rows")
+            out = _run_both(build, dev)
+    finally:
+        _lib.load().gemnet_chain_set_tile_rows(0)
+    return out
+
+
+def _run_both(build, dev):
     from gemnet_pytorch_b200 import chain
     res = []
     for which in (0, 1):
