@@ -42,12 +42,11 @@ using namespace tcx;
 // chains: 762 atoms at batch 64) — the MMAs of a step cost the same for any N <= 128, but the epilogue then has 4
 // instead of 16 values per thread.  Template parameter TR of the kernel; the shared-memory map is sized for 64.
 constexpr int X_BYTES = 2 * 3 * 64 * 128;      // 49152: operand, [chunk][split][row][128 B]
-constexpr int WSLOT_BYTES = 3 * 128 * 128;     // 49152: one 64-k chunk of a (<=128)-row weight image, three splits
-constexpr int W_SLOTS = 2;
 constexpr int THREADS = 512;
 constexpr int MISC_BYTES = 2048;               // barriers, TMEM slot, dot buffer (4 quadrants x TR floats)
-constexpr int SMEM_BYTES = 1024 + X_BYTES + W_SLOTS * WSLOT_BYTES + MISC_BYTES;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr int WSTAGE_BYTES = 3 * 64 * 128 * 4;  // 98304: staging buffer of one weight image on its way to tensor memory
+constexpr int SMEM_BYTES = 1024 + X_BYTES + WSTAGE_BYTES + MISC_BYTES;
+constexpr uint32_t W_COLS = 192;               // weight image in TMEM: 3 splits x (K / 2 <= 64) columns, 128 lanes
 // 1: instantiate the FULL epilogue for N / K = 128 and 64 with immediate row strides (fewer address instructions,
 // but 1.5x the code: measured slower on B200 — instruction fetch)
 #ifndef GEMNET_CHAIN_STRIDE_SPEC
@@ -157,21 +156,22 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
                 long long* __restrict__ prof) {
   constexpr int VPT = TR / 4;                                   // values per thread: rows of one feature
   constexpr int SPLIT_BYTES = TR * 128, CHUNK_BYTES = 3 * SPLIT_BYTES;
-  constexpr uint32_t ACC_STRIDE = TR, CORR_COL = 2 * TR, CARRY_COL = 3 * TR;
+  constexpr uint32_t ACC_STRIDE = TR, CORR_COL = 2 * TR, CARRY_COL = 3 * TR, W_COL = 4 * TR;
+  constexpr uint32_t TMEM_COLS = 4 * TR + W_COLS <= 256 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* X = sm;                                      // operand: [chunk][split][row][128 B]
   const uint32_t x_base = base;
-  const uint32_t w_base = base + X_BYTES;               // weight slots: [chunk][split][n][128 B]
-  const uint32_t bar_base = w_base + W_SLOTS * WSLOT_BYTES;
-  const uint32_t acc_full = bar_base;
-  auto w_full = [&](int s) { return bar_base + 8u + 8u * s; };
+  const uint32_t w_stage = base + X_BYTES;              // weight image in flight: u32 [column group][128 features][4]
+  const uint32_t bar_base = w_stage + WSTAGE_BYTES;
+  const uint32_t acc_full = bar_base, w_full = bar_base + 8;
   const uint32_t tmem_slot = bar_base + 32;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + X_BYTES + W_SLOTS * WSLOT_BYTES + 32);
-  float* dotbuf = reinterpret_cast<float*>(sm + X_BYTES + W_SLOTS * WSLOT_BYTES + 64);  // [4 quadrants][TR] floats
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + X_BYTES + WSTAGE_BYTES + 32);
+  float* dotbuf = reinterpret_cast<float*>(sm + X_BYTES + WSTAGE_BYTES + 64);  // [4 quadrants][TR] floats
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // the warp index as a warp-uniform value
   // diagnostics (gemnet_chain_set_profile_buffer): thread 0 of CTA 0 records clock64() at the phase boundaries
   int prof_n = 0;
   auto stamp = [&]() {
@@ -186,7 +186,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   griddep_launch();
   if (tid == 0) {
     mbar_init(acc_full, 1);
-    for (int s = 0; s < W_SLOTS; ++s) mbar_init(w_full(s), 1);
+    mbar_init(w_full, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -196,32 +196,62 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   const uint32_t tmem_base = *tmem_slot_ptr;
   stamp();  // 1: prologue done
 
-  // weight image of one GEMM -> the chunk slots (thread 0 only; the slots are free: every MMA that read them is done)
-  auto fetch_weights = [&](const gemnet_chain_step& st) {
+  const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (features 32q..32q+31), row group (16 rows)
+  const int f = q * 32 + lane;                  // feature (accumulator row = TMEM lane) of this thread
+
+  // Weight image of one GEMM -> tensor memory, where the MMA reads its A operand (M = 128 features = the lanes): the
+  // tensor pipe then fetches only the activation tile from shared memory per instruction and runs at its N / 2-cycle
+  // floor.  TMEM image (dense_tc.cu pack kernels): u32 [split][K / 8 column groups][128 features][4 columns], column c
+  // of a split = bf16 pair (k = 2c, 2c + 1).  One elected thread streams the NEXT GEMM's image into the staging buffer
+  // with cp.async.bulk as soon as the current image has been copied out of it (the copy runs under the MMAs and the
+  // epilogue); at the end of the epilogue — the GEMM that read the old image is complete — thread (feature, row group
+  // cg) moves a quarter of its feature's column groups into TMEM: up to 12 conflict-free 16-byte shared loads + 12
+  // tcgen05.st.
+  auto fetch_weights = [&](const gemnet_chain_step& st) {    // (one thread)
     const int NKB = st.K > 64 ? 2 : 1;
-    const uint32_t blk = (uint32_t)(st.N > 64 ? 128 : 64) * 128u;   // one (chunk, split) block of the image
-    for (int kb = 0; kb < NKB; ++kb) {
-      mbar_arrive_expect_tx(w_full(kb), 3 * blk);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(st.Wp) + (size_t)kb * 3 * blk;
-      for (int sp = 0; sp < 3; ++sp) bulk_g2s(w_base + kb * WSLOT_BYTES + sp * blk, src + (size_t)sp * blk, blk, w_full(kb));
-    }
+    const size_t smem_image = (size_t)NKB * 3 * (st.N > 64 ? 128 : 64) * 128;   // the dense_tc image comes first
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(st.Wp) + smem_image;
+    const uint32_t split_bytes = 16384u * NKB;
+    mbar_arrive_expect_tx(w_full, 3 * split_bytes);
+    for (int sp = 0; sp < 3; ++sp) bulk_g2s(w_stage + sp * split_bytes, src + (size_t)sp * split_bytes, split_bytes, w_full);
   };
-  if (tid == 0) {
+  uint32_t wfills = 0;                                        // images consumed from the staging buffer (parity of w_full)
+  // (all threads; in two halves.  Placing the first half inside the epilogue measured slower: the image has not
+  // always arrived by then)
+  auto weights_to_tmem = [&](const gemnet_chain_step& st, int part) {
+    const int npt = st.K > 64 ? 12 : 6;                       // column groups per thread (of 24 | 48)
+    const int half = npt >> 1;
+    if (part == 0) {
+      mbar_wait(w_full, wfills & 1u);
+      ++wfills;
+    }
+    const int g0 = cg * npt + part * half;
+    const uint4* src = reinterpret_cast<const uint4*>(sm + X_BYTES) + (size_t)g0 * 128 + f;
+    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + W_COL + (uint32_t)g0 * 4u;
+#pragma unroll
+    for (int i = 0; i < 6; i += 3) {                          // (three groups at a time: 12 registers)
+      if (i < half) {
+        const uint4 r0 = src[(size_t)i * 128], r1 = src[(size_t)(i + 1) * 128], r2 = src[(size_t)(i + 2) * 128];
+        tmem_st4_nowait(t0 + 4u * i, r0);
+        tmem_st4_nowait(t0 + 4u * (i + 1), r1);
+        tmem_st4_nowait(t0 + 4u * (i + 2), r2);
+      }
+    }
+    if (part == 1) tmem_wait_st();
+  };
+  if (warp_u == 0 && elect_one()) {
     if (!weights_settled) griddep_wait();  // the packed images may come from the kernel launched just before
     fetch_weights(prog.step[0]);
   }
   griddep_wait();
   stamp();  // 2: predecessor complete
 
-  const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (features 32q..32q+31), row group (16 rows)
-  const int f = q * 32 + lane;                  // feature (accumulator row = TMEM lane) of this thread
   const int e_loc = cg * VPT;                   // first tile row of this thread's VPT values
   const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)e_loc;
   // element (tile row e_loc + j, k = f) of the operand: xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4)
   uint8_t* const xf_base = X + (f >> 6) * CHUNK_BYTES + e_loc * 128 + (f & 7) * 2;
   const int xf_g = (f & 63) >> 3;
   uint32_t gemm = 0;                            // GEMMs issued by this CTA (parity of acc_full)
-  uint32_t wuse0 = 0, wuse1 = 0;                // fills of weight slot 0 / 1 consumed so far (thread 0)
 
   auto carry_ld = [&](float (&c)[VPT]) {
     uint32_t raw[VPT];
@@ -237,6 +267,8 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
     tmem_st<VPT>(t_lane + CARRY_COL, raw);
   };
 
+  weights_to_tmem(prog.step[0], 0);
+  weights_to_tmem(prog.step[0], 1);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = (int64_t)tile * TR;
     const int64_t rb = r0 + e_loc;                          // first row of this thread's 16 values
@@ -353,46 +385,44 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       tc_fence_before();     // this thread's tcgen05.ld / st of the previous step are done
       __syncthreads();
       stamp();  // step: all threads' operand parts visible
-      if (tid == 0) {
+      // the NEXT GEMM (of this tile, or the first of the CTA's next tile)
+      const bool last = s + 1 == n_steps;
+      const bool more = !last || tile + (int)gridDim.x < n_tiles;
+      const gemnet_chain_step& nst = prog.step[last ? 0 : s + 1];
+      if (warp_u == 0) {       // warp 0, converged; every operand below is warp-uniform (see elect_one)
         tc_fence_after();
-        const int Npad = N > 64 ? 128 : 64;
         const uint32_t idesc = make_idesc(128, TR);     // D^T tile: 128 features x TR rows
-        const uint32_t d_corr = tmem_base + CORR_COL;
+        const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t d_corr = tm_u + CORR_COL;
+        if (elect_one()) {
+        const uint32_t wsp = 32u * NKB;                 // TMEM columns per split of the weight image (K / 2)
         for (int kb = 0; kb < NKB; ++kb) {
-          uint32_t& use = kb ? wuse1 : wuse0;
-          mbar_wait(w_full(kb), use & 1u);
-          ++use;
-          stamp();  // step: weight chunk kb resident
-          tc_fence_after();
           const uint32_t xa = x_base + kb * CHUNK_BYTES;
           const uint64_t x_h = make_desc(xa), x_m = make_desc(xa + SPLIT_BYTES), x_l = make_desc(xa + 2 * SPLIT_BYTES);
-          const uint32_t wb = w_base + kb * WSLOT_BYTES;
-          const uint64_t w_h = make_desc(wb), w_m = make_desc(wb + Npad * 128), w_l = make_desc(wb + 2 * Npad * 128);
-          const uint32_t d_main = tmem_base + kb * ACC_STRIDE;
+          const uint32_t w_h = tm_u + W_COL + kb * 32u, w_m = w_h + wsp, w_l = w_m + wsp;
+          const uint32_t d_main = tm_u + kb * ACC_STRIDE;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle atom
-            umma_bf16(d_main, w_h + adv, x_h + adv, idesc, kk != 0);
-            umma_bf16(d_corr, w_h + adv, x_m + adv, idesc, (kb | kk) != 0);
-            umma_bf16(d_corr, w_m + adv, x_h + adv, idesc, 1u);
-            umma_bf16(d_corr, w_m + adv, x_m + adv, idesc, 1u);
-            umma_bf16(d_corr, w_h + adv, x_l + adv, idesc, 1u);
-            umma_bf16(d_corr, w_l + adv, x_h + adv, idesc, 1u);
+            const uint32_t wadv = 8u * kk;                  // ... = 8 TMEM columns of the weight image
+            umma_bf16_ts(d_main, w_h + wadv, x_h + adv, idesc, kk != 0);
+            umma_bf16_ts(d_corr, w_h + wadv, x_m + adv, idesc, (kb | kk) != 0);
+            umma_bf16_ts(d_corr, w_m + wadv, x_h + adv, idesc, 1u);
+            umma_bf16_ts(d_corr, w_m + wadv, x_m + adv, idesc, 1u);
+            umma_bf16_ts(d_corr, w_h + wadv, x_l + adv, idesc, 1u);
+            umma_bf16_ts(d_corr, w_l + wadv, x_h + adv, idesc, 1u);
           }
         }
         umma_commit(acc_full);
+        if (more) fetch_weights(nst);   // the staging buffer is free: every thread copied the current image out
+        }
+        __syncwarp();
         stamp();  // step: MMAs issued
       }
-      __syncwarp();
       mbar_wait(acc_full, gemm & 1u);
       ++gemm;
       tc_fence_after();
       stamp();  // step: accumulators complete
-      const bool last = s + 1 == n_steps;
-      if (tid == 0) {  // both weight slots are free now: stream the next GEMM's image in while the epilogue runs
-        if (!last) fetch_weights(prog.step[s + 1]);
-        else if (tile + (int)gridDim.x < n_tiles) fetch_weights(prog.step[0]);
-      }
 
       // ------------------------------------------------------------------ epilogue of this step's GEMM
       // thread = feature f, rows rb .. rb+15.  The pointwise program runs STAGE BY STAGE over the 16 values (feature
@@ -595,6 +625,11 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         else epilogue(std::false_type{}, std::integral_constant<int, 0>{});
 #endif
       }
+      // (the GEMM that read the previous image has completed: acc_full above)
+      if (more) {
+        weights_to_tmem(nst, 0);
+        weights_to_tmem(nst, 1);
+      }
       stamp();  // step: epilogue of this thread done
       if (st.dot_w) {
         __syncthreads();
@@ -622,7 +657,7 @@ static int g_chain_rows = 0;
 static long long* g_chain_prof = nullptr;
 namespace gemnet { void segbil_fwd_tc_set_profile_buffer(long long* p); }
 GEMNET_API int gemnet_chain_set_tile_rows(int rows) {
-  GEMNET_REQUIRE(rows == 0 || rows == 16 || rows == 64, "chain: tile rows must be 0 (automatic), 16 or 64");
+  GEMNET_REQUIRE(rows == 0 || rows == 16 || rows == 32 || rows == 64, "chain: tile rows must be 0 (automatic), 16 or 64");
   g_chain_rows = rows;
   return 0;
 }
@@ -660,6 +695,8 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(chain::chain_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(chain::chain_tc_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(chain::chain_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("chain_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -671,7 +708,8 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   // 16-row tiles while they still fit one per SM (atom-level chains): same MMA time per step, a quarter of the epilogue
   const bool small = g_chain_rows ? g_chain_rows == 16 : ceil_div(p.M, 16) <= sms;
-  const int n_tiles = (int)ceil_div(p.M, small ? 16 : 64);
+  const bool mid = g_chain_rows == 32 && !save;   // (measurement only)
+  const int n_tiles = (int)ceil_div(p.M, small ? 16 : mid ? 32 : 64);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_tiles < sms ? n_tiles : sms);
   cfg.blockDim = dim3(chain::THREADS);
@@ -684,7 +722,9 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const int settled = (flags & GEMNET_DENSE_WEIGHTS_SETTLED) ? 1 : 0;
   cudaError_t e;
-  if (small)
+  if (mid)
+    e = cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false, 32>, p, n_tiles, settled, g_chain_prof);
+  else if (small)
     e = save ? cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<true, 16>, p, n_tiles, settled, g_chain_prof)
              : cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false, 16>, p, n_tiles, settled, g_chain_prof);
   else

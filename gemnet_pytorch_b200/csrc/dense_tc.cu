@@ -96,6 +96,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of a converged warp (elect.sync).  tcgen05.mma / commit issued by it with warp-uniform operands take their
+// descriptors from uniform registers directly; under a thread-variant predicate (`if (lane == 0)`) ptxas wraps every
+// instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~66 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -152,6 +160,19 @@ constexpr float kShrinkPerStep = 1.25e-8f;  // mean relative toward-zero roundin
 
 // ---------------------------------------------------------------------------------------------- weight packing
 // image: [kb][split h|m|l][n][64 bf16, 16-byte chunks XOR-swizzled by (n & 7)];  element (n, k) = src[n*sn + k*sk]
+// Second image, behind the shared-memory one: the layout chain_tc.cu copies into tensor memory (its A operand).
+// u32 [split][K / 8 column groups][128 features][4 columns]; column c of a split holds the bf16 pair (k = 2c, 2c + 1).
+// Always 128 feature slots per group (rows >= N of a 64-row image stay unwritten: those TMEM lanes are never read).
+__device__ __forceinline__ void tmem_image_store(__nv_bfloat16* img, int Kp, int n, int k, __nv_bfloat16 h,
+                                                 __nv_bfloat16 m, __nv_bfloat16 l) {
+  const int groups = Kp >> 3;
+  const int64_t u = ((int64_t)(k >> 3) * 128 + n) * 4 + ((k >> 1) & 3);
+  const int64_t split = (int64_t)groups * 128 * 4;
+  img[2 * u + (k & 1)] = h;
+  img[2 * (u + split) + (k & 1)] = m;
+  img[2 * (u + 2 * split) + (k & 1)] = l;
+}
+
 __global__ void pack_weight_kernel(const float* __restrict__ src, int64_t sn, int64_t sk, int N_src, int K_src, int N,
                                    int K, __nv_bfloat16* __restrict__ dst) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,6 +188,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int64_t sn, in
   dst[(int64_t)(kb * 3 + 0) * N * KB + phys] = h;
   dst[(int64_t)(kb * 3 + 1) * N * KB + phys] = m;
   dst[(int64_t)(kb * 3 + 2) * N * KB + phys] = l;
+  tmem_image_store(dst + (int64_t)(K / KB) * 3 * N * KB, K, n, k, h, m, l);
 }
 
 // many weights in one launch (training: every image changes every optimiser step): blockIdx.y = table entry
@@ -186,6 +208,7 @@ __global__ void pack_many_kernel(const gemnet_pack_desc* __restrict__ table) {
   dst[(int64_t)(kb * 3 + 0) * d.Np * KB + phys] = h;
   dst[(int64_t)(kb * 3 + 1) * d.Np * KB + phys] = m;
   dst[(int64_t)(kb * 3 + 2) * d.Np * KB + phys] = l;
+  tmem_image_store(dst + (int64_t)(d.Kp / KB) * 3 * d.Np * KB, d.Kp, n, k, h, m, l);
 }
 
 static inline int64_t ceil_div_i(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -226,7 +249,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(sm + W_BYTES + kStages * STAGE_BYTES + 8 * (2 * kStages + 3));
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (as a warp-uniform value: see elect_one)
   const int n_off = blockIdx.y * N;  // column slab of this CTA (small-M launches split N = 128 over two CTAs)
   // Programmatic dependent launch: let the NEXT kernel of the stream start its prologue (barriers, TMEM, weight
   // image) while this one runs.  Everything here that touches activations waits in griddep_wait() for the
@@ -247,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   // One K chunk (kb) of one row tile: 128 rows x 64 columns of x (.* xmul) -> exact bf16 triple -> operand stage.
   // `ptid` = index of the thread in its 256-thread producer group.
@@ -383,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const Params p, in
     }
   } else if (warp == PRODUCER_WARPS) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(w_bar, 0);  // weight image resident
       uint32_t g = 0;
       for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -490,7 +514,8 @@ static inline int round_n(int N) { return N <= 64 ? 64 : 128; }
 
 GEMNET_API int64_t gemnet_dense_pack_floats(int32_t N, int32_t K) {
   if (N < 1 || N > 128 || K < 1 || K > 128) return -1;
-  return (int64_t)(round_k(K) / dtc::KB) * 3 * round_n(N) * dtc::KB / 2;  // bf16 image, counted in 4-byte units
+  // the shared-memory image (dense_tc) + the tensor-memory image (chain_tc), bf16, counted in 4-byte units
+  return (int64_t)(round_k(K) / dtc::KB) * 3 * round_n(N) * dtc::KB / 2 + (int64_t)3 * (round_k(K) / 2) * 128;
 }
 
 GEMNET_API int gemnet_dense_pack_weight(const float* W, int64_t stride_n, int64_t stride_k, int32_t N, int32_t K,

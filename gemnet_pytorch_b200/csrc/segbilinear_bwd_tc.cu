@@ -78,7 +78,8 @@ segbil_bwd_edges_tc_kernel(const float* __restrict__ rbf_W1, const __nv_bfloat16
   const uint32_t tmem_slot = bar_base + 72;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + A_BYTES + 2 * W_SLOT + 72);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (as a warp-uniform value: see tcx::elect_one)
   griddep_launch();
   if (tid == 0) {
     mbar_init(a_ready, EPI_WARPS);
@@ -94,7 +95,7 @@ segbil_bwd_edges_tc_kernel(const float* __restrict__ rbf_W1, const __nv_bfloat16
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   if (warp < EPI_WARPS) {
     // ===================================================================== operand producers + epilogue roles
@@ -223,7 +224,7 @@ segbil_bwd_edges_tc_kernel(const float* __restrict__ rbf_W1, const __nv_bfloat16
     tc_fence_before();
   } else if (warp == EPI_WARPS) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // (tc_common.cuh: uniform operands, no per-instruction election loop)
       const uint32_t idesc = make_idesc(TM, NCH);
       uint32_t g = 0;
       for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {

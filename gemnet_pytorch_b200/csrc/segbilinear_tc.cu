@@ -104,6 +104,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of a converged warp (elect.sync).  tcgen05.mma / commit issued by it with warp-uniform operands take their
+// descriptors from uniform registers directly; under a thread-variant predicate (`if (lane == 0)`) ptxas wraps every
+// instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~66 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -196,7 +204,8 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(sm + kStages * STAGE_BYTES + AS_BYTES + 8 * (2 * kStages + 4));
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (as a warp-uniform value: see elect_one)
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -213,7 +222,7 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   if (warp < PRODUCER_WARPS) {
     // ============================================================ producers (+ epilogue on warps 0-3)
@@ -386,7 +395,7 @@ segbil_fwd_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ ex
     stamp();  // last epilogue done
   } else if (warp == PRODUCER_WARPS) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t g = 0;
       for (int it = 0, tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int slot = it & 1;

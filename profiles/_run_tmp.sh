@@ -1,6 +1,10 @@
 O=gpurun_out
 mkdir -p $O
-timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --large-batch 0 2> $O/b.err | tail -1 | cut -c1-170
-timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --large-batch 0 2> $O/b.err | tail -1 | cut -c1-170
-timeout 500 python -m pytest tests/test_gpu_chain.py -x -q 2>&1 | tail -2
-timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --large-batch 0 2> $O/b.err | tail -1 | cut -c1-170
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2> $O/b.err | tail -1 | tee $O/bench_elect.json | cut -c1-250
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_elect.json'))
+for k in d:
+    if k.startswith('roofline') or k in ('e2e','gpu_launches'): print(k, json.dumps(d[k])[:300])
+PY

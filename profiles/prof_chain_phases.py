@@ -21,6 +21,8 @@ for j in range(1, n):
     steps.append(Step(pw[j], flags=ACT | CARRY_ADD | SET_CARRY | TO_A, dact=bufs[1 + j]))
 steps[-1].out = bufs[0]
 prog = Program(M, steps)
+import os
+_lib.check(_lib.load().gemnet_chain_set_tile_rows(int(os.environ.get('CHAIN_ROWS', '0'))), 'rows')
 for _ in range(3):
     chain.run(prog)
 buf = torch.zeros(256, dtype=torch.int64, device=dev)
@@ -30,7 +32,7 @@ torch.cuda.synchronize()
 _lib.load().gemnet_chain_set_profile_buffer(None)
 t = buf.cpu().tolist()
 names = ["kernel start", "prologue done (barriers, TMEM alloc)", "predecessor complete (griddepcontrol.wait)"]
-per_step = ["operand written (this thread)", "operand visible (__syncthreads)", "weight chunk 0 resident", "weight chunk 1 resident",
+per_step = ["operand written (this thread)", "operand visible (__syncthreads)",
             "MMAs issued", "accumulators complete", "epilogue done (this thread)"]
 labels = names + [f"step {s}: {p}" for s in range(n) for p in per_step]
 t = [v for v in t if v]
