@@ -42,7 +42,13 @@ using namespace tcx;
 // chains: 762 atoms at batch 64) — the MMAs of a step cost the same for any N <= 128, but the epilogue then has 4
 // instead of 16 values per thread.  Template parameter TR of the kernel; the shared-memory map is sized for 64.
 constexpr int X_BYTES = 2 * 3 * 64 * 128;      // 49152: operand, [chunk][split][row][128 B]
-constexpr int THREADS = 512;
+// Warp roles (warp-specialised; register budgets re-balanced with setmaxnreg, warpgroup = 4 warps):
+//   warps  0..15  workers: operand fill + epilogue                                  (4 warpgroups, 104 registers)
+//   warp   16     issuer: tcgen05.mma of every (step, half) + cp.async.bulk of the weight images
+//   warps  20..23 weight movers: staged image -> tensor memory, one TMEM lane quadrant each   (warps 17..19 idle)
+constexpr int WORKERS = 512;
+constexpr int ISSUER_WARP = WORKERS / 32, MOVER_WARP0 = ISSUER_WARP + 4;
+constexpr int THREADS = WORKERS + 256;
 constexpr int MISC_BYTES = 2048;               // barriers, TMEM slot, dot buffer (4 quadrants x TR floats)
 constexpr int WSTAGE_BYTES = 3 * 64 * 128 * 4;  // 98304: staging buffer of one weight image on its way to tensor memory
 constexpr int SMEM_BYTES = 1024 + X_BYTES + WSTAGE_BYTES + MISC_BYTES;
@@ -95,10 +101,10 @@ struct ThreadTile {
 // values of feature f for rows rb .. rb+15 -> the next operand (element (row, k = f)); zero beyond Knext / M
 // KC: the operand width when it is 128 or 64 (compile-time row stride: every access of the thread is then one base
 // pointer + an immediate), 0 = run-time stride
-template <bool kSave, int TR, int KC>
-__device__ __forceinline__ void operand_from(const ThreadTile& t, const float (&vals)[TR / 4], int Knext_rt, float s_a,
+template <bool kSave, int TR, int VPT, int KC>
+__device__ __forceinline__ void operand_from(const ThreadTile& t, const float (&vals)[VPT], int Knext_rt, float s_a,
                                              const float* amul, bool full, float* save) {
-  constexpr int VPT = TR / 4, SPLIT_BYTES = TR * 128;
+  constexpr int SPLIT_BYTES = TR * 128;
   const int f = t.f, nv = t.nv, jmax = t.jmax, e_loc = t.e_loc, xf_g = t.xf_g;
   const int64_t rb = t.rb, rbc = t.rbc;
   uint8_t* const xf_base = t.xf_base;
@@ -154,9 +160,15 @@ template <bool kSave, int TR>
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, int weights_settled,
                 long long* __restrict__ prof) {
-  constexpr int VPT = TR / 4;                                   // values per thread: rows of one feature
+  // A 64-row tile is worked on as two 32-row HALVES, software-pipelined: while the threads run the epilogue of one
+  // half (and write its rows of the next operand), the tensor pipe runs the other half's GEMM.
+  constexpr int HALVES = TR >= 64 ? 2 : 1;
+  constexpr int HR = TR / HALVES;                               // rows per half = N of one MMA
+  constexpr int VPT = HR / 4;                                   // values per thread and half: rows of one feature
+  static_assert(HR * 16 <= WORKERS, "one operand-fill piece per thread");
   constexpr int SPLIT_BYTES = TR * 128, CHUNK_BYTES = 3 * SPLIT_BYTES;
-  constexpr uint32_t ACC_STRIDE = TR, CORR_COL = 2 * TR, CARRY_COL = 3 * TR, W_COL = 4 * TR;
+  // TMEM columns of one half: main accumulator of K chunk 0 / 1, correction accumulator, carry; then the weight image
+  constexpr uint32_t ACC_STRIDE = HR, CORR_COL = 2 * HR, CARRY_COL = 3 * HR, HCOLS = 4 * HR, W_COL = 4 * TR;
   constexpr uint32_t TMEM_COLS = 4 * TR + W_COLS <= 256 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -165,7 +177,9 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   const uint32_t x_base = base;
   const uint32_t w_stage = base + X_BYTES;              // weight image in flight: u32 [column group][128 features][4]
   const uint32_t bar_base = w_stage + WSTAGE_BYTES;
-  const uint32_t acc_full = bar_base, w_full = bar_base + 8;
+  auto acc_full = [&](int hf) { return bar_base + 8u * hf; };   // GEMM of half hf complete (tcgen05.commit)
+  const uint32_t w_full = bar_base + 16;                        // weight image landed in the staging buffer
+  auto op_ready = [&](int hf) { return bar_base + 40u + 8u * hf; };   // the 16 worker warps finished operand (+ weights)
   const uint32_t tmem_slot = bar_base + 32;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + X_BYTES + WSTAGE_BYTES + 32);
   float* dotbuf = reinterpret_cast<float*>(sm + X_BYTES + WSTAGE_BYTES + 64);  // [4 quadrants][TR] floats
@@ -185,8 +199,11 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   // touches activations waits in griddep_wait() for the PREVIOUS kernel to have completed and flushed.
   griddep_launch();
   if (tid == 0) {
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full(0), 1);
+    mbar_init(acc_full(1), 1);
     mbar_init(w_full, 1);
+    mbar_init(op_ready(0), WORKERS / 32 + 4);   // + the four weight movers: this GEMM's image is in TMEM
+    mbar_init(op_ready(1), WORKERS / 32);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -202,11 +219,10 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   // Weight image of one GEMM -> tensor memory, where the MMA reads its A operand (M = 128 features = the lanes): the
   // tensor pipe then fetches only the activation tile from shared memory per instruction and runs at its N / 2-cycle
   // floor.  TMEM image (dense_tc.cu pack kernels): u32 [split][K / 8 column groups][128 features][4 columns], column c
-  // of a split = bf16 pair (k = 2c, 2c + 1).  One elected thread streams the NEXT GEMM's image into the staging buffer
-  // with cp.async.bulk as soon as the current image has been copied out of it (the copy runs under the MMAs and the
-  // epilogue); at the end of the epilogue — the GEMM that read the old image is complete — thread (feature, row group
-  // cg) moves a quarter of its feature's column groups into TMEM: up to 12 conflict-free 16-byte shared loads + 12
-  // tcgen05.st.
+  // of a split = bf16 pair (k = 2c, 2c + 1).  The issuer streams the NEXT GEMM's image into the staging buffer with
+  // cp.async.bulk as soon as the current image has been moved out of it; the four mover warps copy it into TMEM
+  // (conflict-free 16-byte shared loads + tcgen05.st, lane = feature) once the GEMM that read the old image is complete
+  // — under the workers' epilogues, off their critical path.
   auto fetch_weights = [&](const gemnet_chain_step& st) {    // (one thread)
     const int NKB = st.K > 64 ? 2 : 1;
     const size_t smem_image = (size_t)NKB * 3 * (st.N > 64 ? 128 : 64) * 128;   // the dense_tc image comes first
@@ -215,228 +231,79 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
     mbar_arrive_expect_tx(w_full, 3 * split_bytes);
     for (int sp = 0; sp < 3; ++sp) bulk_g2s(w_stage + sp * split_bytes, src + (size_t)sp * split_bytes, split_bytes, w_full);
   };
-  uint32_t wfills = 0;                                        // images consumed from the staging buffer (parity of w_full)
-  // (all threads; in two halves.  Placing the first half inside the epilogue measured slower: the image has not
-  // always arrived by then)
-  auto weights_to_tmem = [&](const gemnet_chain_step& st, int part) {
-    const int npt = st.K > 64 ? 12 : 6;                       // column groups per thread (of 24 | 48)
-    const int half = npt >> 1;
-    if (part == 0) {
-      mbar_wait(w_full, wfills & 1u);
-      ++wfills;
-    }
-    const int g0 = cg * npt + part * half;
-    const uint4* src = reinterpret_cast<const uint4*>(sm + X_BYTES) + (size_t)g0 * 128 + f;
-    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + W_COL + (uint32_t)g0 * 4u;
-#pragma unroll
-    for (int i = 0; i < 6; i += 3) {                          // (three groups at a time: 12 registers)
-      if (i < half) {
-        const uint4 r0 = src[(size_t)i * 128], r1 = src[(size_t)(i + 1) * 128], r2 = src[(size_t)(i + 2) * 128];
-        tmem_st4_nowait(t0 + 4u * i, r0);
-        tmem_st4_nowait(t0 + 4u * (i + 1), r1);
-        tmem_st4_nowait(t0 + 4u * (i + 2), r2);
-      }
-    }
-    if (part == 1) tmem_wait_st();
-  };
-  if (warp_u == 0 && elect_one()) {
+  if (warp_u == ISSUER_WARP && elect_one()) {
     if (!weights_settled) griddep_wait();  // the packed images may come from the kernel launched just before
     fetch_weights(prog.step[0]);
   }
   griddep_wait();
+  auto worker_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); };   // (the 16 worker warps)
   stamp();  // 2: predecessor complete
-
-  const int e_loc = cg * VPT;                   // first tile row of this thread's VPT values
-  const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)e_loc;
-  // element (tile row e_loc + j, k = f) of the operand: xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4)
-  uint8_t* const xf_base = X + (f >> 6) * CHUNK_BYTES + e_loc * 128 + (f & 7) * 2;
   const int xf_g = (f & 63) >> 3;
-  uint32_t gemm = 0;                            // GEMMs issued by this CTA (parity of acc_full)
+  uint32_t done0 = 0, done1 = 0;   // GEMMs of half 0 / 1 whose completion has been consumed (parity of acc_full(half))
 
-  auto carry_ld = [&](float (&c)[VPT]) {
-    uint32_t raw[VPT];
-    tmem_ld_nowait<VPT>(t_lane + CARRY_COL, raw);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < VPT; ++j) c[j] = __uint_as_float(raw[j]);
-  };
-  auto carry_st = [&](const float (&c)[VPT]) {
-    uint32_t raw[VPT];
-#pragma unroll
-    for (int j = 0; j < VPT; ++j) raw[j] = __float_as_uint(c[j]);
-    tmem_st<VPT>(t_lane + CARRY_COL, raw);
-  };
-
-  weights_to_tmem(prog.step[0], 0);
-  weights_to_tmem(prog.step[0], 1);
+  if (warp_u < ISSUER_WARP) {
+  // ====================================================================== worker warps
+  // (the pool holds only what this CTA's other warps release: 256 threads x (80 - 32) = 512 x 24 registers)
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = (int64_t)tile * TR;
-    const int64_t rb = r0 + e_loc;                          // first row of this thread's 16 values
-    const int nv = (int)max((int64_t)0, min((int64_t)VPT, M - rb));   // valid rows among them
-    const int64_t rbc = nv > 0 ? rb : M - 1;                // clamped row base / index for loads (always in range)
-    const int jmax = max(nv, 1) - 1;
-    const ThreadTile tt{f, nv, jmax, e_loc, xf_g, rb, rbc, xf_base};
-
+    // Software pipeline over (step s, half hf): [epilogue of (s - 1, hf), which writes the half's rows of operand s]
+    // -> [operand fill from global memory, if step s loads one] -> barrier -> elected lane issues the MMAs of (s, hf).
+    // The GEMM of the other half runs on the tensor pipe meanwhile.  s == n_steps only drains the last epilogues.
 #pragma unroll 1
-    for (int s = 0; s < n_steps; ++s) {
-      const gemnet_chain_step& st = prog.step[s];
+    for (int s = 0; s <= n_steps; ++s) {
+#pragma unroll 1
+      for (int hf = 0; hf < HALVES; ++hf) {
+      // ------------------------------------------------------------------ this thread's part of the half
+      const int e_loc = hf * HR + cg * VPT;         // first tile row of this thread's VPT values
+      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * HCOLS + cg * VPT);
+      // element (tile row e_loc + j, k = f) of the operand: xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4)
+      uint8_t* const xf_base = X + (f >> 6) * CHUNK_BYTES + e_loc * 128 + (f & 7) * 2;
+      const int64_t rb = r0 + e_loc;                          // first row of this thread's values
+      const int nv = (int)max((int64_t)0, min((int64_t)VPT, M - rb));   // valid rows among them
+      const int64_t rbc = nv > 0 ? rb : M - 1;                // clamped row base / index for loads (always in range)
+      const int jmax = max(nv, 1) - 1;
+      const ThreadTile tt{f, nv, jmax, e_loc, xf_g, rb, rbc, xf_base};
+      auto carry_ld = [&](float (&c)[VPT]) {
+        uint32_t raw[VPT];
+        tmem_ld_nowait<VPT>(t_lane + CARRY_COL, raw);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) c[j] = __uint_as_float(raw[j]);
+      };
+      auto carry_st = [&](const float (&c)[VPT]) {
+        uint32_t raw[VPT];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) raw[j] = __float_as_uint(c[j]);
+        tmem_st<VPT>(t_lane + CARRY_COL, raw);
+      };
+
+      if (s > 0) {
+      // ================================================================== epilogue of GEMM (s - 1, hf)
+      const gemnet_chain_step& st = prog.step[s - 1];
       const int K = st.K, N = st.N;
       const int NKB = K > 64 ? 2 : 1;
-      // ------------------------------------------------------------------ operand fill from global memory
-      if (st.n_terms > 0) {
-        const int gpr = 8 * NKB;                                   // granules (8 columns) per operand row
-        const bool fold_amul = st.amul != nullptr && !st.load_set_carry;
-        // the fill IS the operand unless a carry read-back multiplies it afterwards (then operand_from stores it)
-        const bool save_here = kSave && st.save_x != nullptr && !(st.load_set_carry && st.amul != nullptr);
-        // PG (row, granule) pieces per thread: 64 rows x 8|16 granules = 512|1024 pieces, all loads in flight together
-        auto fill = [&](auto pg_tag) {
-          constexpr int PG = decltype(pg_tag)::value;
-          float v[PG][8];
-          int prow[PG], pgr[PG];
-#pragma unroll
-          for (int h = 0; h < PG; ++h) {
-            const int p = min(tid + h * THREADS, TR * gpr - 1);   // (threads beyond the tile's pieces: see `pin`)
-            prow[h] = p / gpr;
-            pgr[h] = p % gpr;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[h][j] = 0.f;
-          }
-          for (int t = 0; t < st.n_terms; ++t) {
-            const gemnet_chain_term& tm = st.term[t];
-            float4 a0[PG], a1[PG];
-            if (tm.kind == 0) {
-#pragma unroll
-              for (int h = 0; h < PG; ++h) {
-                // out-of-range pieces read a clamped (valid) address and are zeroed below: no divergent branches
-                const int64_t rr = min(r0 + prow[h], M - 1);
-                const int col = min(pgr[h] * 8, K - 8);
-                const int64_t sr = tm.idx ? (int64_t)__ldg(tm.idx + rr) : rr;
-                a0[h] = ldg4(tm.src + sr * K + col);
-                a1[h] = ldg4(tm.src + sr * K + col + 4);
-              }
-              if (tm.mul) {
-#pragma unroll
-                for (int h = 0; h < PG; ++h) {
-                  const int64_t rr = min(r0 + prow[h], M - 1);
-                  const int col = min(pgr[h] * 8, K - 8);
-                  const float4 m0 = ldg4(tm.mul + rr * K + col), m1 = ldg4(tm.mul + rr * K + col + 4);
-                  a0[h].x *= m0.x; a0[h].y *= m0.y; a0[h].z *= m0.z; a0[h].w *= m0.w;
-                  a1[h].x *= m1.x; a1[h].y *= m1.y; a1[h].z *= m1.z; a1[h].w *= m1.w;
-                }
-              }
-            } else {  // outer product src[row] * mul[col]
-#pragma unroll
-              for (int h = 0; h < PG; ++h) {
-                const int64_t rr = min(r0 + prow[h], M - 1);
-                const int col = min(pgr[h] * 8, K - 8);
-                const float a = __ldg(tm.src + rr);
-                const float4 m0 = ldg4(tm.mul + col), m1 = ldg4(tm.mul + col + 4);
-                a0[h] = make_float4(a * m0.x, a * m0.y, a * m0.z, a * m0.w);
-                a1[h] = make_float4(a * m1.x, a * m1.y, a * m1.z, a * m1.w);
-              }
-            }
-            const float sc = tm.scale;
-#pragma unroll
-            for (int h = 0; h < PG; ++h) {
-              v[h][0] = fmaf(sc, a0[h].x, v[h][0]); v[h][1] = fmaf(sc, a0[h].y, v[h][1]);
-              v[h][2] = fmaf(sc, a0[h].z, v[h][2]); v[h][3] = fmaf(sc, a0[h].w, v[h][3]);
-              v[h][4] = fmaf(sc, a1[h].x, v[h][4]); v[h][5] = fmaf(sc, a1[h].y, v[h][5]);
-              v[h][6] = fmaf(sc, a1[h].z, v[h][6]); v[h][7] = fmaf(sc, a1[h].w, v[h][7]);
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < PG; ++h) {
-            if (fold_amul) {
-              const int64_t rr = min(r0 + prow[h], M - 1);
-              const int col = min(pgr[h] * 8, K - 8);
-              const float4 m0 = ldg4(st.amul + rr * K + col), m1 = ldg4(st.amul + rr * K + col + 4);
-              v[h][0] *= m0.x; v[h][1] *= m0.y; v[h][2] *= m0.z; v[h][3] *= m0.w;
-              v[h][4] *= m1.x; v[h][5] *= m1.y; v[h][6] *= m1.z; v[h][7] *= m1.w;
-            }
-            const bool pin = tid + h * THREADS < TR * gpr;       // this thread owns a piece of the tile in pass h
-            const bool valid = r0 + prow[h] < M && pgr[h] * 8 < K;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[h][j] = valid ? v[h][j] : 0.f;
-            if (pin) store_granule<TR>(X, prow[h], pgr[h], v[h]);
-            if (save_here && valid && pin) {
-              float4* dst = reinterpret_cast<float4*>(st.save_x + (r0 + prow[h]) * K + pgr[h] * 8);
-              dst[0] = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
-              dst[1] = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
-            }
-          }
-        };
-        if (TR * gpr > THREADS) fill(std::integral_constant<int, 2>{});
-        else fill(std::integral_constant<int, 1>{});
-        if (st.load_set_carry) {
-          // the skip value is wanted in the epilogue's thread mapping: read it back from the (exact) operand split
-          __syncthreads();
-          float c[VPT];
-          const bool kin = f < 64 * NKB;
-#pragma unroll
-          for (int j = 0; j < VPT; ++j) c[j] = kin ? load_elem<TR>(X, e_loc + j, min(f, 64 * NKB - 1)) : 0.f;
-          carry_st(c);
-          if (st.amul) operand_from<kSave, TR, 0>(tt, c, K, 1.0f, st.amul, false, kSave ? st.save_x : nullptr);   // (each thread rewrites exactly the elements it read)
-        }
+      const bool last = s == n_steps;
+      {
+        uint32_t& done = hf ? done1 : done0;
+        mbar_wait(acc_full(hf), done & 1u);
+        ++done;
       }
-      stamp();  // step: operand written by this thread
-
-      // ------------------------------------------------------------------ GEMM: operand complete -> thread 0 issues
-      fence_proxy_async();   // generic-proxy writes of X -> visible to the tensor-core (async) proxy
-      tc_fence_before();     // this thread's tcgen05.ld / st of the previous step are done
-      __syncthreads();
-      stamp();  // step: all threads' operand parts visible
-      // the NEXT GEMM (of this tile, or the first of the CTA's next tile)
-      const bool last = s + 1 == n_steps;
-      const bool more = !last || tile + (int)gridDim.x < n_tiles;
-      const gemnet_chain_step& nst = prog.step[last ? 0 : s + 1];
-      if (warp_u == 0) {       // warp 0, converged; every operand below is warp-uniform (see elect_one)
-        tc_fence_after();
-        const uint32_t idesc = make_idesc(128, TR);     // D^T tile: 128 features x TR rows
-        const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint32_t d_corr = tm_u + CORR_COL;
-        if (elect_one()) {
-        const uint32_t wsp = 32u * NKB;                 // TMEM columns per split of the weight image (K / 2)
-        for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t xa = x_base + kb * CHUNK_BYTES;
-          const uint64_t x_h = make_desc(xa), x_m = make_desc(xa + SPLIT_BYTES), x_l = make_desc(xa + 2 * SPLIT_BYTES);
-          const uint32_t w_h = tm_u + W_COL + kb * 32u, w_m = w_h + wsp, w_l = w_m + wsp;
-          const uint32_t d_main = tm_u + kb * ACC_STRIDE;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle atom
-            const uint32_t wadv = 8u * kk;                  // ... = 8 TMEM columns of the weight image
-            umma_bf16_ts(d_main, w_h + wadv, x_h + adv, idesc, kk != 0);
-            umma_bf16_ts(d_corr, w_h + wadv, x_m + adv, idesc, (kb | kk) != 0);
-            umma_bf16_ts(d_corr, w_m + wadv, x_h + adv, idesc, 1u);
-            umma_bf16_ts(d_corr, w_m + wadv, x_m + adv, idesc, 1u);
-            umma_bf16_ts(d_corr, w_h + wadv, x_l + adv, idesc, 1u);
-            umma_bf16_ts(d_corr, w_l + wadv, x_h + adv, idesc, 1u);
-          }
-        }
-        umma_commit(acc_full);
-        if (more) fetch_weights(nst);   // the staging buffer is free: every thread copied the current image out
-        }
-        __syncwarp();
-        stamp();  // step: MMAs issued
-      }
-      mbar_wait(acc_full, gemm & 1u);
-      ++gemm;
       tc_fence_after();
-      stamp();  // step: accumulators complete
-
+      stamp();  // accumulators of (s - 1, hf) complete
       // ------------------------------------------------------------------ epilogue of this step's GEMM
       // thread = feature f, rows rb .. rb+15.  The pointwise program runs STAGE BY STAGE over the 16 values (feature
       // tests outside the element loops): 16 independent dependency chains per stage, one uniform branch per
       // disabled feature, and every global access is a coalesced line per warp (lanes = consecutive features).
       const int flags = st.flags;
-      const int Knext = last ? 0 : prog.step[s + 1].K;
+      const int Knext = last ? 0 : prog.step[s].K;
       const float c0f = kShrinkPerStep * (float)min(4, (K + 15) / 16);
       const float c1f = kShrinkPerStep * (float)max(0, min(4, (K - 64 + 15) / 16));
       const float s_acc = st.s_acc;
       const bool need_d = st.dact != nullptr;
-      if (st.dot_w) {   // idle / partial warps must not leave stale partial sums
-        if (tid < 4 * TR) dotbuf[tid] = 0.f;
-        __syncthreads();
+      if (st.dot_w) {   // idle / partial warps must not leave stale partial sums (this half's rows)
+        if (tid < 4 * HR) dotbuf[(tid / HR) * TR + hf * HR + tid % HR] = 0.f;
+        worker_sync();
       }
       // a warp whose 32 features lie beyond this step's output AND the next operand has nothing to do
       const bool warp_idle = 32 * q >= N && (last || 32 * q >= (Knext > 64 ? 128 : 64));
@@ -604,13 +471,13 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         }
         if (!last && (flags & (GEMNET_CHAIN_TO_A | GEMNET_CHAIN_A_FROM_CARRY))) {
           if (!(flags & GEMNET_CHAIN_TO_A)) carry_ld(v);        // (v is dead after this point)
-          float* save = kSave ? prog.step[s + 1].save_x : nullptr;
+          float* save = kSave ? prog.step[s].save_x : nullptr;
           if constexpr (NC != 0) {
-            if (Knext == 128) operand_from<kSave, TR, 128>(tt, v, Knext, st.s_a, st.next_amul, true, save);
-            else if (Knext == 64) operand_from<kSave, TR, 64>(tt, v, Knext, st.s_a, st.next_amul, true, save);
-            else operand_from<kSave, TR, 0>(tt, v, Knext, st.s_a, st.next_amul, true, save);
+            if (Knext == 128) operand_from<kSave, TR, VPT, 128>(tt, v, Knext, st.s_a, st.next_amul, true, save);
+            else if (Knext == 64) operand_from<kSave, TR, VPT, 64>(tt, v, Knext, st.s_a, st.next_amul, true, save);
+            else operand_from<kSave, TR, VPT, 0>(tt, v, Knext, st.s_a, st.next_amul, true, save);
           } else {
-            operand_from<kSave, TR, 0>(tt, v, Knext, st.s_a, st.next_amul, FULL, save);
+            operand_from<kSave, TR, VPT, 0>(tt, v, Knext, st.s_a, st.next_amul, FULL, save);
           }
         }
       };
@@ -625,19 +492,207 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
         else epilogue(std::false_type{}, std::integral_constant<int, 0>{});
 #endif
       }
-      // (the GEMM that read the previous image has completed: acc_full above)
-      if (more) {
-        weights_to_tmem(nst, 0);
-        weights_to_tmem(nst, 1);
-      }
       stamp();  // step: epilogue of this thread done
       if (st.dot_w) {
-        __syncthreads();
-        if (tid < TR && r0 + tid < M)
-          st.dot_out[r0 + tid] = ((dotbuf[tid] + dotbuf[TR + tid]) + (dotbuf[2 * TR + tid] + dotbuf[3 * TR + tid])) +
-                                 (st.dot_in ? st.dot_in[r0 + tid] : 0.f);
+        worker_sync();
+        const int dr = hf * HR + tid;                       // (tile row)
+        if (tid < HR && r0 + dr < M)
+          st.dot_out[r0 + dr] = ((dotbuf[dr] + dotbuf[TR + dr]) + (dotbuf[2 * TR + dr] + dotbuf[3 * TR + dr])) +
+                                (st.dot_in ? st.dot_in[r0 + dr] : 0.f);
+      }
+      }
+      if (s == n_steps) continue;
+
+      const gemnet_chain_step& st = prog.step[s];
+      const int K = st.K, N = st.N;
+      const int NKB = K > 64 ? 2 : 1;
+      // ------------------------------------------------------------------ operand fill from global memory
+      if (st.n_terms > 0) {
+        const int gpr = 8 * NKB;                                   // granules (8 columns) per operand row
+        const bool fold_amul = st.amul != nullptr && !st.load_set_carry;
+        // the fill IS the operand unless a carry read-back multiplies it afterwards (then operand_from stores it)
+        const bool save_here = kSave && st.save_x != nullptr && !(st.load_set_carry && st.amul != nullptr);
+        // (row, granule) pieces: 32 rows x 8|16 granules = 256|512, one per thread, all loads in flight together
+        auto fill = [&](auto pg_tag) {
+          constexpr int PG = decltype(pg_tag)::value;
+          float v[PG][8];
+          int prow[PG], pgr[PG];
+#pragma unroll
+          for (int h = 0; h < PG; ++h) {
+            const int p = min(tid + h * WORKERS, HR * gpr - 1);   // (threads beyond the half's pieces: see `pin`)
+            prow[h] = hf * HR + p / gpr;
+            pgr[h] = p % gpr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[h][j] = 0.f;
+          }
+          for (int t = 0; t < st.n_terms; ++t) {
+            const gemnet_chain_term& tm = st.term[t];
+            float4 a0[PG], a1[PG];
+            if (tm.kind == 0) {
+#pragma unroll
+              for (int h = 0; h < PG; ++h) {
+                // out-of-range pieces read a clamped (valid) address and are zeroed below: no divergent branches
+                const int64_t rr = min(r0 + prow[h], M - 1);
+                const int col = min(pgr[h] * 8, K - 8);
+                const int64_t sr = tm.idx ? (int64_t)__ldg(tm.idx + rr) : rr;
+                a0[h] = ldg4(tm.src + sr * K + col);
+                a1[h] = ldg4(tm.src + sr * K + col + 4);
+              }
+              if (tm.mul) {
+#pragma unroll
+                for (int h = 0; h < PG; ++h) {
+                  const int64_t rr = min(r0 + prow[h], M - 1);
+                  const int col = min(pgr[h] * 8, K - 8);
+                  const float4 m0 = ldg4(tm.mul + rr * K + col), m1 = ldg4(tm.mul + rr * K + col + 4);
+                  a0[h].x *= m0.x; a0[h].y *= m0.y; a0[h].z *= m0.z; a0[h].w *= m0.w;
+                  a1[h].x *= m1.x; a1[h].y *= m1.y; a1[h].z *= m1.z; a1[h].w *= m1.w;
+                }
+              }
+            } else {  // outer product src[row] * mul[col]
+#pragma unroll
+              for (int h = 0; h < PG; ++h) {
+                const int64_t rr = min(r0 + prow[h], M - 1);
+                const int col = min(pgr[h] * 8, K - 8);
+                const float a = __ldg(tm.src + rr);
+                const float4 m0 = ldg4(tm.mul + col), m1 = ldg4(tm.mul + col + 4);
+                a0[h] = make_float4(a * m0.x, a * m0.y, a * m0.z, a * m0.w);
+                a1[h] = make_float4(a * m1.x, a * m1.y, a * m1.z, a * m1.w);
+              }
+            }
+            const float sc = tm.scale;
+#pragma unroll
+            for (int h = 0; h < PG; ++h) {
+              v[h][0] = fmaf(sc, a0[h].x, v[h][0]); v[h][1] = fmaf(sc, a0[h].y, v[h][1]);
+              v[h][2] = fmaf(sc, a0[h].z, v[h][2]); v[h][3] = fmaf(sc, a0[h].w, v[h][3]);
+              v[h][4] = fmaf(sc, a1[h].x, v[h][4]); v[h][5] = fmaf(sc, a1[h].y, v[h][5]);
+              v[h][6] = fmaf(sc, a1[h].z, v[h][6]); v[h][7] = fmaf(sc, a1[h].w, v[h][7]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < PG; ++h) {
+            if (fold_amul) {
+              const int64_t rr = min(r0 + prow[h], M - 1);
+              const int col = min(pgr[h] * 8, K - 8);
+              const float4 m0 = ldg4(st.amul + rr * K + col), m1 = ldg4(st.amul + rr * K + col + 4);
+              v[h][0] *= m0.x; v[h][1] *= m0.y; v[h][2] *= m0.z; v[h][3] *= m0.w;
+              v[h][4] *= m1.x; v[h][5] *= m1.y; v[h][6] *= m1.z; v[h][7] *= m1.w;
+            }
+            const bool pin = tid + h * WORKERS < HR * gpr;       // this thread owns a piece of the half
+            const bool valid = r0 + prow[h] < M && pgr[h] * 8 < K;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[h][j] = valid ? v[h][j] : 0.f;
+            if (pin) store_granule<TR>(X, prow[h], pgr[h], v[h]);
+            if (save_here && valid && pin) {
+              float4* dst = reinterpret_cast<float4*>(st.save_x + (r0 + prow[h]) * K + pgr[h] * 8);
+              dst[0] = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
+              dst[1] = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
+            }
+          }
+        };
+        fill(std::integral_constant<int, 1>{});
+        if (st.load_set_carry) {
+          // the skip value is wanted in the epilogue's thread mapping: read it back from the (exact) operand split
+          worker_sync();
+          float c[VPT];
+          const bool kin = f < 64 * NKB;
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) c[j] = kin ? load_elem<TR>(X, e_loc + j, min(f, 64 * NKB - 1)) : 0.f;
+          carry_st(c);
+          if (st.amul) operand_from<kSave, TR, VPT, 0>(tt, c, K, 1.0f, st.amul, false, kSave ? st.save_x : nullptr);   // (each thread rewrites exactly the elements it read)
+        }
+      }
+      stamp();  // step: operand written by this thread
+      // ------------------------------------------------------------------ hand the half to the issuer warp
+      fence_proxy_async();   // generic-proxy writes of X -> visible to the tensor-core (async) proxy
+      tc_fence_before();     // this thread's tcgen05.ld / st are done
+      __syncwarp();
+      if (lane == 0) mbar_arrive(op_ready(hf));
+      stamp();  // operand of (s, hf) handed over
       }
     }
+  }
+  } else {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+  if (warp_u == ISSUER_WARP) {
+  // ====================================================================== issuer warp: MMAs and weight fetches
+  // (converged; every operand is warp-uniform, one elected lane issues: see elect_one)
+  const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+  uint32_t ready0 = 0, ready1 = 0;   // operands of half 0 / 1 consumed (parity of op_ready(half))
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+    for (int s = 0; s < n_steps; ++s) {
+      const gemnet_chain_step& st = prog.step[s];
+      const int NKB = st.K > 64 ? 2 : 1;
+      // the NEXT GEMM (of this tile, or the first of the CTA's next tile)
+      const bool more = s + 1 < n_steps || tile + (int)gridDim.x < n_tiles;
+      const gemnet_chain_step& nst = prog.step[s + 1 < n_steps ? s + 1 : 0];
+#pragma unroll 1
+      for (int hf = 0; hf < HALVES; ++hf) {
+        {
+          uint32_t& ready = hf ? ready1 : ready0;
+          mbar_wait(op_ready(hf), ready & 1u);     // every worker warp: operand rows (+ weight image) written
+          ++ready;
+        }
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(128, HR);     // D^T of this half: 128 features x HR rows
+        const uint32_t d_corr = tm_u + hf * HCOLS + CORR_COL;
+        if (elect_one()) {
+          const uint32_t wsp = 32u * NKB;                 // TMEM columns per split of the weight image (K / 2)
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint32_t xa = x_base + kb * CHUNK_BYTES + hf * (HR * 128);
+            const uint64_t x_h = make_desc(xa), x_m = make_desc(xa + SPLIT_BYTES), x_l = make_desc(xa + 2 * SPLIT_BYTES);
+            const uint32_t w_h = tm_u + W_COL + kb * 32u, w_m = w_h + wsp, w_l = w_m + wsp;
+            const uint32_t d_main = tm_u + hf * HCOLS + kb * ACC_STRIDE;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle atom
+              const uint32_t wadv = 8u * kk;                  // ... = 8 TMEM columns of the weight image
+              umma_bf16_ts(d_main, w_h + wadv, x_h + adv, idesc, kk != 0);
+              umma_bf16_ts(d_corr, w_h + wadv, x_m + adv, idesc, (kb | kk) != 0);
+              umma_bf16_ts(d_corr, w_m + wadv, x_h + adv, idesc, 1u);
+              umma_bf16_ts(d_corr, w_m + wadv, x_m + adv, idesc, 1u);
+              umma_bf16_ts(d_corr, w_h + wadv, x_l + adv, idesc, 1u);
+              umma_bf16_ts(d_corr, w_l + wadv, x_h + adv, idesc, 1u);
+            }
+          }
+          umma_commit(acc_full(hf));
+          // the staging buffer is free (the movers arrived on op_ready(0) after copying this GEMM's image out)
+          if (hf == 0 && more) fetch_weights(nst);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  } else if (warp_u >= MOVER_WARP0) {
+  // ====================================================================== weight movers: staging buffer -> TMEM
+  const int qd = warp_u & 3;                                   // TMEM lane quadrant of this warp
+  const uint4* src0 = reinterpret_cast<const uint4*>(sm + X_BYTES) + (qd * 32 + lane);
+  const uint32_t t0 = tmem_base + ((uint32_t)(qd * 32) << 16) + W_COL;
+  uint32_t g = 0;                                              // GEMM images moved so far (parities of w_full / acc_full)
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+    for (int s = 0; s < n_steps; ++s, ++g) {
+      const int groups = prog.step[s].K > 64 ? 48 : 24;        // column groups of 4 (3 splits x K / 8)
+      if (g > 0) {   // the GEMM that reads the previous image: its last half must be complete
+        mbar_wait(acc_full(HALVES - 1), (g - 1) & 1u);
+        tc_fence_after();
+      }
+      mbar_wait(w_full, g & 1u);
+#pragma unroll 1
+      for (int i = 0; i < groups; i += 8) {
+        uint4 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = src0[(size_t)(i + j) * 128];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tmem_st4_nowait(t0 + 4u * (i + j), r[j]);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(op_ready(0));
+    }
+  }
+  }
   }
 
   tc_fence_before();

@@ -27,7 +27,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && spin > (1u << 26)) __trap();  // never hang the device on a protocol bug
+    if (!done && spin > (1u << 22)) __trap();  // never hang the device on a protocol bug (seconds, not minutes)
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -31,10 +31,17 @@ chain.run(prog)
 torch.cuda.synchronize()
 _lib.load().gemnet_chain_set_profile_buffer(None)
 t = buf.cpu().tolist()
-names = ["kernel start", "prologue done (barriers, TMEM alloc)", "predecessor complete (griddepcontrol.wait)"]
-per_step = ["operand written (this thread)", "operand visible (__syncthreads)",
-            "MMAs issued", "accumulators complete", "epilogue done (this thread)"]
-labels = names + [f"step {s}: {p}" for s in range(n) for p in per_step]
+# stamps (chain_tc.cu): kernel start, prologue done, predecessor complete, then per (step s, half hf) of the software
+# pipeline: [s > 0: accumulators of (s-1, hf) complete, epilogue of (s-1, hf) done], [s < n: operand written, operand
+# handed to the issuer warp (mbarrier arrive)] — thread 0 = a worker thread
+halves = 2 if int(os.environ.get('CHAIN_ROWS', '0')) in (0, 64) and M > 148 * 16 else 1
+labels = ["kernel start", "prologue done (barriers, TMEM alloc)", "predecessor complete (griddepcontrol.wait)"]
+for s_ in range(n + 1):
+    for h in range(halves):
+        if s_ > 0:
+            labels += [f"({s_ - 1},{h}) accumulators complete", f"({s_ - 1},{h}) epilogue done"]
+        if s_ < n:
+            labels += [f"({s_},{h}) operand written (+ weights in TMEM)", f"({s_},{h}) handed to the issuer warp"]
 t = [v for v in t if v]
 print(f"M={M} steps={n}: total {t[-1] - t[0]} cycles")
 for i in range(1, len(t)):
