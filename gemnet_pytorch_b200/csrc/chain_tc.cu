@@ -3,29 +3,38 @@
 // interaction block in each direction, every one a 128x128 GEMM that finishes in microseconds.  Here a 64-row tile of
 // the activation stays on chip for the whole chain.
 //
-// The GEMM is issued TRANSPOSED: D^T (features x rows) = W (features x K) @ X^T, i.e. the packed weight image is the
-// M-side operand (M = 128 output features = the 128 TMEM lanes) and the activation tile is the N-side operand (N = 64
-// rows).  With the accumulator in that orientation a warp's 32 lanes are 32 consecutive FEATURES of one row, so
-//   * every global access of the epilogue (stores of the activation derivative and of the outputs, loads of skip /
-//     Hadamard / gathered terms) is a fully coalesced 128-byte line per warp instruction,
-//   * a 64-row tile keeps all 512 threads busy with 16 values each (a row-per-lane layout would idle half the lanes),
-//     so batch 64 (8186 edges) runs on 128 CTAs instead of 64, and the MMA of a step costs 32 instead of 64 cycles per
-//     K16 instruction.
+// The GEMM is issued TRANSPOSED: D^T (features x rows) = W (features x K) @ X^T, i.e. the weight image is the M-side
+// operand (M = 128 output features = the 128 TMEM lanes) and the activation tile is the N-side operand.  With the
+// accumulator in that orientation a warp's 32 lanes are 32 consecutive FEATURES of one row, so every global access of
+// the epilogue (stores of the activation derivative and of the outputs, loads of skip / Hadamard / gathered terms) is
+// a fully coalesced 128-byte line per warp instruction, and batch 64 (8186 edges) runs on 128 CTAs.
 //
 //   operand X      shared memory, exact three-way bf16 split (h + m + l == fp32 value), K-major SWIZZLE_128B, 48 KB
-//   weights        two 48 KB chunk slots filled by cp.async.bulk; the next layer's image streams in while the current
-//                  layer's epilogue runs
+//   weights        A operand of the MMA in TENSOR MEMORY (192 columns: 3 splits x K / 2): the tensor pipe then reads
+//                  only the activation tile from shared memory and runs at its N / 2-cycle floor per instruction.
+//                  The next layer's image streams into a 96 KB staging buffer (cp.async.bulk) while the current
+//                  layer runs and is moved to TMEM by four dedicated warps
 //   accumulators   TMEM: one main accumulator per K chunk + one correction accumulator (dense_tc.cu's numerics:
 //                  six significant products, the toward-zero rounding of the accumulator compensated)
-//   skip value     "carry": 64 more TMEM columns (tcgen05.st / tcgen05.ld): no registers, no shared memory
+//   skip value     "carry": TMEM columns next to the accumulators (tcgen05.st / tcgen05.ld)
 //
-// 512 threads, one CTA per SM, persistent over row tiles.  Every thread is a worker: operand fill from global memory
-// (coalesced; gathers and several summed terms allowed) and the epilogue of every step — thread (feature f = 32 q +
-// lane, rows 16 cg .. 16 cg + 15) reads its 16 accumulator values with one tcgen05.ld per accumulator, runs the
-// pointwise program stage by stage over them, stores what the backward pass needs and writes the next layer's operand
-// back into shared memory.  Thread 0 additionally issues the tcgen05.mma of each step once the operand is complete
-// (one __syncthreads per GEMM) and, as soon as a GEMM has completed (mbarrier acc_full), the cp.async.bulk of the NEXT
-// GEMM's weight image.  The step program is a kernel parameter (__grid_constant__).
+// Software pipeline.  A 64-row tile is processed as two 32-row halves: while the worker warps run the epilogue of one
+// half (and write that half's rows of the next operand), the tensor pipe runs the other half's GEMM.  Warp roles
+// (register budgets re-balanced with setmaxnreg):
+//   16 worker warps   operand fill from global memory (coalesced; gathers, Hadamard factors and several summed terms)
+//                     and the epilogue of every (step, half): thread (feature f = 32 q + lane, 8 rows) reads its
+//                     accumulator values with one tcgen05.ld per accumulator, runs the pointwise program stage by
+//                     stage over them, stores what the backward pass needs and writes the next layer's operand back
+//                     into shared memory; then the warp arrives on the half's `op_ready` mbarrier.  No block-wide
+//                     barrier inside the chain.
+//   1 issuer warp     waits for op_ready(half) (16 workers [+ the 4 movers for half 0]), issues the 48 tcgen05.mma of
+//                     the (step, half) from ONE ELECTED LANE WITH WARP-UNIFORM OPERANDS (under a thread-variant
+//                     predicate ptxas wraps every MMA in an election loop of ~66 cycles), commits to acc_full(half),
+//                     and starts the cp.async.bulk of the next weight image.
+//   4 mover warps     one TMEM lane quadrant each: staged weight image -> tensor memory as soon as the GEMM that reads
+//                     the previous image has completed (they observe acc_full of the last half).
+// A 16-row variant (one half, 4 values per thread) serves atom-level chains (762 atoms at batch 64 = 48 tiles).
+// The step program is a kernel parameter (__grid_constant__).  One CTA per SM, persistent over row tiles.
 #include <cuda_bf16.h>
 
 #include <type_traits>
@@ -38,9 +47,8 @@ namespace chain {
 
 using namespace tcx;
 
-// rows per tile (the N side of the MMA): 64, or 16 when that still gives at most one tile per SM (the atom-level
-// chains: 762 atoms at batch 64) — the MMAs of a step cost the same for any N <= 128, but the epilogue then has 4
-// instead of 16 values per thread.  Template parameter TR of the kernel; the shared-memory map is sized for 64.
+// rows per tile: 64 (two pipelined 32-row halves), or 16 when that still gives at most one tile per SM (the atom-level
+// chains: 762 atoms at batch 64).  Template parameter TR of the kernel; the shared-memory map is sized for 64.
 constexpr int X_BYTES = 2 * 3 * 64 * 128;      // 49152: operand, [chunk][split][row][128 B]
 // Warp roles (warp-specialised; register budgets re-balanced with setmaxnreg, warpgroup = 4 warps):
 //   warps  0..15  workers: operand fill + epilogue                                  (4 warpgroups, 104 registers)
@@ -98,7 +106,7 @@ struct ThreadTile {
   uint8_t* xf_base;               // operand element (tile row e_loc + j, k = f): xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4)
 };
 
-// values of feature f for rows rb .. rb+15 -> the next operand (element (row, k = f)); zero beyond Knext / M
+// values of feature f for rows rb .. rb + VPT - 1 -> the next operand (element (row, k = f)); zero beyond Knext / M
 // KC: the operand width when it is 128 or 64 (compile-time row stride: every access of the thread is then one base
 // pointer + an immediate), 0 = run-time stride
 template <bool kSave, int TR, int VPT, int KC>
@@ -124,8 +132,10 @@ __device__ __forceinline__ void operand_from(const ThreadTile& t, const float (&
 #pragma unroll
       for (int j = 0; j < VPT; ++j) w[j] *= __ldg(amul + (rb * Knext + fc) + j * Knext);
     }
+    if (!kv) {                                             // (warp-uniform for operand widths of 32, 64, 96, 128)
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) w[j] = kv ? w[j] : 0.f;
+      for (int j = 0; j < VPT; ++j) w[j] = 0.f;
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < VPT; ++j) w[j] = (kv && j < nv) ? vals[j] * s_a : 0.f;
@@ -139,8 +149,10 @@ __device__ __forceinline__ void operand_from(const ThreadTile& t, const float (&
     for (int j = 0; j < VPT; j += 2) {
       uint32_t h, m, l;
       split3(w[j], w[j + 1], h, m, l);
-      uint8_t* p0 = xf_base + j * 128 + ((xf_g ^ ((e_loc + j) & 7)) << 4);       // (e_loc % 8 is 0 or 4)
-      uint8_t* p1 = xf_base + (j + 1) * 128 + ((xf_g ^ ((e_loc + j + 1) & 7)) << 4);
+      // (the first row of a thread is a multiple of VPT: for VPT = 8 the row's swizzle term is the constant j & 7)
+      const int s0 = VPT % 8 == 0 ? (j & 7) : ((e_loc + j) & 7), s1 = VPT % 8 == 0 ? ((j + 1) & 7) : ((e_loc + j + 1) & 7);
+      uint8_t* p0 = xf_base + j * 128 + ((xf_g ^ s0) << 4);
+      uint8_t* p1 = xf_base + (j + 1) * 128 + ((xf_g ^ s1) << 4);
       *reinterpret_cast<uint16_t*>(p0) = (uint16_t)h;
       *reinterpret_cast<uint16_t*>(p1) = (uint16_t)(h >> 16);
       *reinterpret_cast<uint16_t*>(p0 + SPLIT_BYTES) = (uint16_t)m;
@@ -188,8 +200,9 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // the warp index as a warp-uniform value
   // diagnostics (gemnet_chain_set_profile_buffer): thread 0 of CTA 0 records clock64() at the phase boundaries
   int prof_n = 0;
+  const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
   auto stamp = [&]() {
-    if (prof != nullptr && blockIdx.x == 0 && tid == 0 && prof_n < 250) prof[prof_n++] = clock64();
+    if (profiling && prof_n < 250) prof[prof_n++] = clock64();
   };
   stamp();
   const int64_t M = prog.M;
@@ -213,7 +226,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
   const uint32_t tmem_base = *tmem_slot_ptr;
   stamp();  // 1: prologue done
 
-  const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (features 32q..32q+31), row group (16 rows)
+  const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant (features 32q..32q+31), row group (VPT rows of the half)
   const int f = q * 32 + lane;                  // feature (accumulator row = TMEM lane) of this thread
 
   // Weight image of one GEMM -> tensor memory, where the MMA reads its A operand (M = 128 features = the lanes): the
@@ -292,9 +305,9 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       tc_fence_after();
       stamp();  // accumulators of (s - 1, hf) complete
       // ------------------------------------------------------------------ epilogue of this step's GEMM
-      // thread = feature f, rows rb .. rb+15.  The pointwise program runs STAGE BY STAGE over the 16 values (feature
-      // tests outside the element loops): 16 independent dependency chains per stage, one uniform branch per
-      // disabled feature, and every global access is a coalesced line per warp (lanes = consecutive features).
+      // thread = feature f, rows rb .. rb + VPT - 1.  The pointwise program runs STAGE BY STAGE over the VPT values
+      // (feature tests outside the element loops): VPT independent dependency chains per stage, one uniform branch
+      // per disabled feature, and every global access is a coalesced line per warp (lanes = consecutive features).
       const int flags = st.flags;
       const int Knext = last ? 0 : prog.step[s].K;
       const float c0f = kShrinkPerStep * (float)min(4, (K + 15) / 16);
@@ -307,7 +320,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       }
       // a warp whose 32 features lie beyond this step's output AND the next operand has nothing to do
       const bool warp_idle = 32 * q >= N && (last || 32 * q >= (Knext > 64 ? 128 : 64));
-      // FULL (warp-uniform): all 16 rows and all 32 features of the warp are in range -> no clamps, no predicates
+      // FULL (warp-uniform): all VPT rows and all 32 features of the warp are in range -> no clamps, no predicates
       // n_tag: N when it is 128 or 64 (FULL only) — compile-time row stride, so the 16 accesses of an array are one
       // base pointer + immediates instead of four address instructions each; 0 = run-time stride
       auto epilogue = [&](auto full_tag, auto n_tag) {
@@ -504,7 +517,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       if (s == n_steps) continue;
 
       const gemnet_chain_step& st = prog.step[s];
-      const int K = st.K, N = st.N;
+      const int K = st.K;
       const int NKB = K > 64 ? 2 : 1;
       // ------------------------------------------------------------------ operand fill from global memory
       if (st.n_terms > 0) {
@@ -630,7 +643,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
       for (int hf = 0; hf < HALVES; ++hf) {
         {
           uint32_t& ready = hf ? ready1 : ready0;
-          mbar_wait(op_ready(hf), ready & 1u);     // every worker warp: operand rows (+ weight image) written
+          mbar_wait_idle(op_ready(hf), ready & 1u);     // every worker warp: operand rows (+ weight image) written
           ++ready;
         }
         tc_fence_after();
@@ -674,10 +687,10 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
     for (int s = 0; s < n_steps; ++s, ++g) {
       const int groups = prog.step[s].K > 64 ? 48 : 24;        // column groups of 4 (3 splits x K / 8)
       if (g > 0) {   // the GEMM that reads the previous image: its last half must be complete
-        mbar_wait(acc_full(HALVES - 1), (g - 1) & 1u);
+        mbar_wait_idle(acc_full(HALVES - 1), (g - 1) & 1u);
         tc_fence_after();
       }
-      mbar_wait(w_full, g & 1u);
+      mbar_wait_idle(w_full, g & 1u);
 #pragma unroll 1
       for (int i = 0; i < groups; i += 8) {
         uint4 r[8];
@@ -712,7 +725,7 @@ static int g_chain_rows = 0;
 static long long* g_chain_prof = nullptr;
 namespace gemnet { void segbil_fwd_tc_set_profile_buffer(long long* p); }
 GEMNET_API int gemnet_chain_set_tile_rows(int rows) {
-  GEMNET_REQUIRE(rows == 0 || rows == 16 || rows == 32 || rows == 64, "chain: tile rows must be 0 (automatic), 16 or 64");
+  GEMNET_REQUIRE(rows == 0 || rows == 16 || rows == 64, "chain: tile rows must be 0 (automatic), 16 or 64");
   g_chain_rows = rows;
   return 0;
 }
@@ -750,8 +763,6 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(chain::chain_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(chain::chain_tc_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
-    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(chain::chain_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("chain_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -763,8 +774,7 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   // 16-row tiles while they still fit one per SM (atom-level chains): same MMA time per step, a quarter of the epilogue
   const bool small = g_chain_rows ? g_chain_rows == 16 : ceil_div(p.M, 16) <= sms;
-  const bool mid = g_chain_rows == 32 && !save;   // (measurement only)
-  const int n_tiles = (int)ceil_div(p.M, small ? 16 : mid ? 32 : 64);
+  const int n_tiles = (int)ceil_div(p.M, small ? 16 : 64);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_tiles < sms ? n_tiles : sms);
   cfg.blockDim = dim3(chain::THREADS);
@@ -777,9 +787,7 @@ GEMNET_API int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const int settled = (flags & GEMNET_DENSE_WEIGHTS_SETTLED) ? 1 : 0;
   cudaError_t e;
-  if (mid)
-    e = cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false, 32>, p, n_tiles, settled, g_chain_prof);
-  else if (small)
+  if (small)
     e = save ? cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<true, 16>, p, n_tiles, settled, g_chain_prof)
              : cudaLaunchKernelEx(&cfg, chain::chain_tc_kernel<false, 16>, p, n_tiles, settled, g_chain_prof);
   else

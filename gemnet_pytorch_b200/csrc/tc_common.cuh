@@ -30,6 +30,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && spin > (1u << 22)) __trap();  // never hang the device on a protocol bug (seconds, not minutes)
   }
 }
+// the same for a warp with nothing else to do (issuer / mover roles): back off between polls so that the polling
+// instructions do not take issue slots from the warps that work on the same scheduler
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done) {
+      __nanosleep(40);
+      if (spin > (1u << 22)) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -182,8 +200,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 // k * silu(z) and k * d/dz silu(z) (k = 1/0.6 times the layer's output scale, folded by the caller); sigmoid and
 // 1 - sigmoid from exp(-|z|): no overflow / cancellation; ex2.approx and rcp.approx (2 ulp), no slow paths
+// exp(-|z|) as ONE multiply + ex2.approx.ftz (|z| * log2 e in (−inf, 0]: no range handling needed)
+__device__ __forceinline__ float exp_neg_abs(float z) {
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * -1.4426950408889634f));
+  return t;
+}
 __device__ __forceinline__ void scaled_silu(float z, float k, float& v, float& d) {
-  const float t = __expf(-fabsf(z));
+  const float t = exp_neg_abs(z);
   const float rr = rcp_approx(1.0f + t);      // 1 + t in (1, 2]
   const float p = t * rr;
   const float sg = z >= 0.f ? rr : p, oms = z >= 0.f ? p : rr;
@@ -192,7 +216,7 @@ __device__ __forceinline__ void scaled_silu(float z, float k, float& v, float& d
   d = sk * fmaf(z, oms, 1.0f);
 }
 __device__ __forceinline__ float scaled_silu_value(float z, float k) {
-  const float t = __expf(-fabsf(z));
+  const float t = exp_neg_abs(z);
   const float rr = rcp_approx(1.0f + t);
   return z * ((z >= 0.f ? rr : t * rr) * k);
 }

@@ -250,8 +250,11 @@ int gemnet_segment_sum_rows(const float* src, const int32_t* perm, const int32_t
  * fp32 in / fp32 out; both operands are split exactly into three bf16 terms and the six significant products are
  * accumulated in fp32 in TMEM (main and correction sums kept apart, the accumulator's toward-zero rounding
  * compensated), so the result is fp32-grade.  B is given pre-packed: gemnet_dense_pack_weight converts an (N x K) operand
- * with arbitrary element strides (so W, W^T and column slices of W all pack without copies) into the resident
- * shared-memory image (gemnet_dense_pack_floats(N, K) floats).  N, K multiples of 4 in [4, 128]; x rows have stride ldx.
+ * with arbitrary element strides (so W, W^T and column slices of W all pack without copies) into TWO images, one after
+ * the other in `packed` (gemnet_dense_pack_floats(N, K) floats in total): the resident shared-memory image of
+ * gemnet_dense_tc (K-major SWIZZLE_128B chunks of 64 k) and the tensor-memory image of gemnet_chain_tc (u32
+ * [split][K / 8 column groups][128 features][4 columns], column c = bf16 pair k = 2c, 2c + 1: that kernel's MMA reads
+ * the weights as its A operand from TMEM).  N, K multiples of 4 in [4, 128]; x rows have stride ldx.
  * flags: GEMNET_DENSE_WEIGHTS_SETTLED = the packed image was NOT produced by the kernel launched immediately before
  * this call on `stream` (weights are packed once and reused): the kernel is then launched as a programmatic
  * dependent of its predecessor and fetches the image while the predecessor is still running.
@@ -281,10 +284,11 @@ int gemnet_dense_tc(const float* x, const float* xmul, int64_t M, int32_t K, int
  * (atom_update_block.py:55-72, 157-193), EdgeEmbedding without the concat (embedding_block.py:70-74) — and the
  * input-gradient of each of them (forces are -dE/dR, gemnet.py:598-613).
  *
- * A 128-row tile of the activation stays on chip for the whole chain: the operand lives in shared memory as an
- * exact three-way bf16 split (gemnet_dense_tc's numerics), the accumulators in TMEM, a skip-connection value
- * ("carry") in registers; only what the backward pass needs (activation derivatives) and the chain's outputs go to
- * HBM.  The chain is described by a small program of up to GEMNET_CHAIN_MAX_STEPS steps; every step is
+ * A 64-row tile (16 rows for atom-level chains) of the activation stays on chip for the whole chain: the operand
+ * lives in shared memory as an exact three-way bf16 split (gemnet_dense_tc's numerics), the weights, the accumulators
+ * and a skip-connection value ("carry") in tensor memory; only what the backward pass needs (activation derivatives)
+ * and the chain's outputs go to HBM.  The two 32-row halves of a tile are software-pipelined: epilogue of one half
+ * under the GEMM of the other (csrc/chain_tc.cu).  The chain is described by a small program of up to GEMNET_CHAIN_MAX_STEPS steps; every step is
  *
  *   1. (optional) operand fill   v[r,:] = sum_t scale_t * src_t[idx_t ? idx_t[r] : r, :] (* mul_t[r,:])   t < n_terms
  *                                (kind 1: v[r,c] = scale * src[r] * mul[c], an outer product: the N=1 output layer's
@@ -359,7 +363,7 @@ typedef struct {
 
 int gemnet_chain_tc(const gemnet_chain_program* program_host, int32_t flags, void* stream);
 /* rows per tile of the following launches: 0 (default) = automatic — 16-row tiles while ceil(M / 16) <= the SM count
- * (atom-level chains; a quarter of the epilogue per step at the same MMA time), else 64; 16 / 64 force one variant
+ * (atom-level chains: one 16-row tile per SM), else 64 (two pipelined 32-row halves); 16 / 64 force one variant
  * (tests, measurements).  Results do not depend on it beyond fp32 summation order of the dot epilogue. */
 int gemnet_chain_set_tile_rows(int32_t rows);
 /* diagnostics: when non-NULL, thread 0 of CTA 0 of every following gemnet_chain_tc launch writes clock64() stamps of its
