@@ -241,6 +241,7 @@ chain_tc_kernel(const __grid_constant__ gemnet_chain_program prog, int n_tiles, 
     const size_t smem_image = (size_t)NKB * 3 * (st.N > 64 ? 128 : 64) * 128;   // the dense_tc image comes first
     const uint8_t* src = reinterpret_cast<const uint8_t*>(st.Wp) + smem_image;
     const uint32_t split_bytes = 16384u * NKB;
+    fence_proxy_async();   // (the movers' generic-proxy reads of the old image were ordered before this by op_ready)
     mbar_arrive_expect_tx(w_full, 3 * split_bytes);
     for (int sp = 0; sp < 3; ++sp) bulk_g2s(w_stage + sp * split_bytes, src + (size_t)sp * split_bytes, split_bytes, w_full);
   };

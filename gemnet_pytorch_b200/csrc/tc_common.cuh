@@ -17,8 +17,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// a wait that lasts longer than this is a protocol bug: trap instead of hanging the device.  (Wall time, not a spin
+// count: under compute-sanitizer the other warps run orders of magnitude slower than a failing try_wait.)
+constexpr uint64_t kWaitLimitNs = 20ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  uint64_t t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -27,13 +36,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && spin > (1u << 22)) __trap();  // never hang the device on a protocol bug (seconds, not minutes)
+    if (!done && (spin & 0xFFFu) == 0xFFFu) {
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kWaitLimitNs) __trap();
+    }
   }
 }
 // the same for a warp with nothing else to do (issuer / mover roles): back off between polls so that the polling
 // instructions do not take issue slots from the warps that work on the same scheduler
 __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  uint64_t t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -44,7 +58,11 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
         : "memory");
     if (!done) {
       __nanosleep(40);
-      if (spin > (1u << 22)) __trap();
+      if ((spin & 0xFFFu) == 0xFFFu) {
+        const uint64_t t = globaltimer_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > kWaitLimitNs) __trap();
+      }
     }
   }
 }
