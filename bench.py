@@ -433,6 +433,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--large-batch", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index-build", default="both", choices=["host", "device", "both"],
+                    help="where the e2e path constructs the index arrays (row H0 on host threads / row N2 on the GPU); "
+                         "'both' measures the two and reports the faster one as e2e, the other under e2e.other_path")
     ap.add_argument("--eager", action="store_true", help="time the eager step instead of its CUDA-graph replay")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train = BASELINE configs[3]: GemNet-dT direct-force training step (fp32), molecule-sharded, "
@@ -528,38 +531,50 @@ def main():
     #   e2e.latency_ms  one batch at a time, index construction inline (what an MD step pays)
     mol_batches = [(Rl, Zl)] + [synthetic_molecules(args.batch, 1234 + rank + 1000 * j) for j in range(1, 8)]
     max_atoms = max(sum(len(z) for z in Zb) for _, Zb in mol_batches) + 64
-    server = model.make_molecule_server(args.batch, max_atoms, workers=3)
-    for Rb, Zb in mol_batches:               # warm-up: captures the graph of every capacity bucket these batches need
-        server(Rb, Zb)
-    for _ in server.stream(mol_batches[:4]):
-        pass
-    h2d, d2h = server.h2d_bytes, server.d2h_bytes
-    if server.pool is None:
-        hb = server.build(Rl, Zl)
-        h2d = sum(v.numel() * v.element_size() for v in hb.values())
 
     def flushed(batches):
         for b in batches:
             flush()
             yield b
 
-    barrier()
-    t0 = time.perf_counter()
-    n_done = 0
-    for E_h, F_h in server.stream(flushed(mol_batches[j % 8] for j in range(args.steps))):
-        n_done += 1
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    if server.pool is None:
-        d2h = E_h.numel() * 4 + F_h.numel() * 4
-    lat = []
-    for j in range(min(args.steps, 10)):
-        flush()
-        torch.cuda.synchronize()
+    def measure_server(srv):
+        """(seconds for args.steps batches through stream(), median latency of single calls, H2D / D2H bytes per step)"""
+        for Rb, Zb in mol_batches:           # warm-up: captures the graph of every capacity bucket these batches need
+            srv(Rb, Zb)
+        for _ in srv.stream(mol_batches[:4]):
+            pass
+        h2d_, d2h_ = srv.h2d_bytes, srv.d2h_bytes
+        barrier()
         t0 = time.perf_counter()
-        server(*mol_batches[j % 8])
-        lat.append(time.perf_counter() - t0)
-    t_lat = float(np.median(lat))
+        for E_h, F_h in srv.stream(flushed(mol_batches[j % 8] for j in range(args.steps))):
+            pass
+        torch.cuda.synchronize()
+        t_stream = time.perf_counter() - t0
+        if srv.pool is None:
+            d2h_ = E_h.numel() * 4 + F_h.numel() * 4
+            if srv.index_build == "host":
+                hb = srv.build(Rl, Zl)
+                h2d_ = sum(v.numel() * v.element_size() for v in hb.values())
+            else:  # coordinates (float64), atomic numbers, molecule sizes, the size header
+                h2d_ = sum(len(z) for z in Zl) * (24 + 8) + len(Zl) * (4 + 8) + 64
+                d2h_ += 2 * 64
+        lat_ = []
+        for j in range(min(args.steps, 10)):
+            flush()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            srv(*mol_batches[j % 8])
+            lat_.append(time.perf_counter() - t0)
+        return t_stream, float(np.median(lat_)), int(h2d_), int(d2h_)
+
+    server = model.make_molecule_server(args.batch, max_atoms, workers=3, index_build="host")
+    t_e2e, t_lat, h2d, d2h = measure_server(server)
+    e2e_paths = {"host": (t_e2e, t_lat, h2d, d2h)}
+    if args.index_build in ("device", "both"):
+        server_dev = model.make_molecule_server(args.batch, max_atoms, index_build="device")
+        e2e_paths["device"] = measure_server(server_dev)
+    chosen = args.index_build if args.index_build != "both" else min(e2e_paths, key=lambda k: e2e_paths[k][0])
+    t_e2e, t_lat, h2d, d2h = e2e_paths[chosen]
     # the reference-format host batch (indices already built) through the serving pool alone, and through eager predict
     host_batches = [server.build(*mb) for mb in mol_batches[:4]]
     t_serv = t_e2e_eager = None
@@ -600,11 +615,23 @@ def main():
         "e2e": {"value": mols / t_e2e, "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3,
                 "latency_ms": t_lat * 1e3, "host_index_build_ms": t_index * 1e3,
-                "index_construction": "INCLUDED (row H0, native builder on 3 worker threads, pipelined by stream())",
+                "index_construction": ("INCLUDED (row H0, native builder on 3 worker threads, pipelined by stream())"
+                                       if chosen == "host" else
+                                       "INCLUDED (row N2, on the GPU: only float64 coordinates, atomic numbers and molecule "
+                                       "sizes cross PCIe; the host counts edges / triplets to pick the capacity bucket)"),
+                "index_build": chosen,
+                "other_path": {k: {"ms_per_step": v[0] / args.steps * 1e3, "latency_ms": v[1] * 1e3,
+                                   "h2d_bytes_per_step": v[2], "d2h_bytes_per_step": v[3]}
+                               for k, v in e2e_paths.items() if k != chosen},
                 "clock": "host perf_counter between synchronisations; the per-step L2 flush kernel is inside the region",
-                "path": ("GemNet.make_molecule_server: host (R, Z) lists -> H0 -> static-shape CUDA graph pool (H2D, "
-                         f"index plan, E+F, D2H), capacity buckets (edges, triplets) = {sorted(server.pool.runners)}")
-                if server.pool is not None else "GemNet.make_molecule_server: H0 -> GemNet.predict (eager)",
+                "path": (("GemNet.make_molecule_server(index_build='host'): host (R, Z) lists -> H0 -> static-shape CUDA "
+                          "graph pool (H2D, index plan, E+F, D2H)" if chosen == "host" else
+                          "GemNet.make_molecule_server(index_build='device'): host (R, Z) lists -> static-shape CUDA graph "
+                          "pool (H2D of coordinates, index construction kernels + pad, index plan, E+F, D2H)")
+                         + f", capacity buckets (edges, triplets) = {sorted(k[:2] for k in (server if chosen == 'host' else server_dev).pool.runners)}")
+                if server.pool is not None else
+                ("GemNet.make_molecule_server: H0 -> GemNet.predict (eager)" if chosen == "host" else
+                 "GemNet.make_molecule_server(index_build='device'): coordinates -> index kernels -> GemNet.predict (eager)"),
                 "serving_pool_only_ms_per_step": None if t_serv is None else t_serv / args.steps * 1e3,
                 "eager_ms_per_step": None if t_e2e_eager is None else t_e2e_eager / args.steps * 1e3},
         "gpu_launches": int(launches),

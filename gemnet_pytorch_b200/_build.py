@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libgemnet_b200.so")
-SOURCES = ["prep.cu", "geometry.cu", "basis.cu", "scatter.cu", "segbilinear.cu", "segbilinear_tc.cu", "segbilinear_bwd_tc.cu", "dense_tc.cu", "chain_tc.cu", "rbf_fan.cu", "quad.cu", "pointwise.cu", "graph_host.cpp"]
+SOURCES = ["prep.cu", "geometry.cu", "basis.cu", "scatter.cu", "segbilinear.cu", "segbilinear_tc.cu", "segbilinear_bwd_tc.cu", "dense_tc.cu", "chain_tc.cu", "rbf_fan.cu", "quad.cu", "pointwise.cu", "graph_device.cu", "graph_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "--fmad=true", "-shared"]
 
@@ -21,7 +21,7 @@ def needs_build():
     t = os.path.getmtime(LIB)
     deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(PKG, "..", "include", "gemnet_b200.h"),
                         os.path.abspath(__file__)]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

@@ -17,7 +17,8 @@ _SIGNATURES = {
     "gemnet_abi_version": [],
     "gemnet_last_error": [],
     "gemnet_csr_from_sorted": [_P, _I64, _I64, _P, _P, _P],
-    "gemnet_csr_by_key": [_P, _I64, _I64, _P, _P, _P, _P],
+    "gemnet_csr_by_key": [_P, _I64, _I64, _P, _P, _P, _P, _P],
+    "gemnet_index_range_check": [_P, _P, _P, _I32, _P, _P],
     "gemnet_edge_geometry_fwd": [_P, _P, _P, _I64, _P, _P, _P],
     "gemnet_edge_geometry_bwd": [_P, _P, _P, _P, _I64, _P, _P, _P, _P],
     "gemnet_bessel_rbf_fwd": [_P, _P, _I64, _I32, _F, _I32, _P, _P],
@@ -68,6 +69,11 @@ _SIGNATURES = {
     "gemnet_graph_copy_host_i64": [_P, ctypes.c_char_p, _P],
     "gemnet_graph_free": [_P],
     "gemnet_pad_batch_host": [_P] * 10 + [_I64] * 8 + [_P] * 10,
+    "gemnet_graph_device_count": [_P, _P],
+    "gemnet_graph_device_edges": [_P, _P],
+    "gemnet_graph_device_quads": [_P, _P],
+    "gemnet_graph_device_pad": [_P, _P, _P, _P],
+    "gemnet_graph_count_host": [_P, _P, _I64, _D, _P, _P],
 }
 _RESTYPES = {
     "gemnet_last_error": ctypes.c_char_p,

@@ -299,6 +299,42 @@ extern "C" __attribute__((visibility("default"))) int gemnet_graph_build_host(co
   return 0;
 }
 
+// Sizes of a batch without building it: per-atom in-degree from the same distance test as directed_pairs; every
+// directed edge r = (c -> a) carries deg(a) - 1 triplets.
+extern "C" __attribute__((visibility("default"))) int gemnet_graph_count_host(const double* R, const int32_t* n_per_mol,
+                                                                               int64_t n_mol, double cutoff,
+                                                                               int64_t* n_edges, int64_t* n_triplets) {
+  if (n_mol < 0 || (n_mol > 0 && (!R || !n_per_mol)) || !n_edges || !n_triplets) {
+    gemnet::set_error("gemnet_graph_count_host: bad arguments");
+    return 1;
+  }
+  int64_t off = 0, ne = 0, nt = 0;
+  for (int64_t m = 0; m < n_mol; ++m) {
+    const int32_t n = n_per_mol[m];
+    if (n < 0) {
+      gemnet::set_error("gemnet_graph_count_host: negative molecule size");
+      return 1;
+    }
+    for (int32_t i = 0; i < n; ++i) {
+      const double* ri = R + 3 * (off + i);
+      int64_t deg = 0;
+      for (int32_t j = 0; j < n; ++j) {
+        if (i == j) continue;
+        const double* rj = R + 3 * (off + j);
+        const double dx = ri[0] - rj[0], dy = ri[1] - rj[1], dz = ri[2] - rj[2];
+        volatile double sx = dx * dx, sy = dy * dy, sz = dz * dz;
+        deg += std::sqrt((sx + sy) + sz) <= cutoff;
+      }
+      ne += deg;
+      nt += deg * (deg - 1);
+    }
+    off += n;
+  }
+  *n_edges = ne;
+  *n_triplets = nt;
+  return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int64_t gemnet_graph_size(const gemnet_graph* g, const char* name) {
   if (!g || !name) return -1;
   auto it = g->arrays.find(name);

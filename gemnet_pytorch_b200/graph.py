@@ -84,6 +84,11 @@ class Molecule:
         return build_batch([self.R], [self.Z], self.cutoff, self.int_cutoff, self.triplets_only)
 
 
+INDEX_ERROR = ("index tensors are not grouped/sorted as the reference DataContainer produces them (batch_seg, "
+               "id3_reduce_ca, id4_reduce_ca must be non-decreasing) or an index lies outside its table "
+               "(atom ids < n_atoms, edge ids < n_edges, ...)")
+
+
 class GraphPlan:
     def __init__(self, inputs, triplets_only, check=_CHECK_SORTED):
         dev = inputs["R"].device
@@ -106,9 +111,12 @@ class GraphPlan:
         flags = []
         self.mol_rowptr, f = ops.csr_from_sorted(self.batch_seg, self.n_mol)
         flags.append(f)
-        self.atom_rowptr, self.atom_perm = ops.csr_by_key(self.id_a, self.n_atoms)   # edges by target atom
-        self.src_rowptr, self.src_perm = ops.csr_by_key(self.id_c, self.n_atoms)     # edges by source atom
-        self.swap_rowptr, self.swap_perm = ops.csr_by_key(self.id_swap, self.n_edges)  # inverse of id_swap
+        # one flag for every range check of the gather / scatter lists (an id outside its table is skipped + reported)
+        rng = torch.zeros(1, dtype=torch.int32, device=dev)
+        flags.append(rng)
+        self.atom_rowptr, self.atom_perm = ops.csr_by_key(self.id_a, self.n_atoms, rng)   # edges by target atom
+        self.src_rowptr, self.src_perm = ops.csr_by_key(self.id_c, self.n_atoms, rng)     # edges by source atom
+        self.swap_rowptr, self.swap_perm = ops.csr_by_key(self.id_swap, self.n_edges, rng)  # inverse of id_swap
 
         self.id3_reduce, self.id3_expand = i32("id3_reduce_ca"), i32("id3_expand_ba")
         self.n_triplets = int(self.id3_reduce.numel())
@@ -119,7 +127,7 @@ class GraphPlan:
             self.id4_reduce_ca = i32("id4_reduce_ca")
             self.id4_reduce_cab, self.id4_expand_abd = i32("id4_reduce_cab"), i32("id4_expand_abd")
             self.id4_expand_intm_db = i32("id4_expand_intm_db")
-            self.intm_db_rowptr, self.intm_db_perm = ops.csr_by_key(self.id4_expand_intm_db, self.n_edges)
+            self.intm_db_rowptr, self.intm_db_perm = ops.csr_by_key(self.id4_expand_intm_db, self.n_edges, rng)
             self.n_quads = int(self.id4_reduce_ca.numel())
             self.rowptr4, f = ops.csr_from_sorted(self.id4_reduce_ca, self.n_edges)
             flags.append(f)
@@ -137,13 +145,18 @@ class GraphPlan:
             self.cab_center = inputs["id_a"][r_ca].to(torch.int32).contiguous()
             self.cab_first = ib[r_ab].to(torch.int32).contiguous()
             self.cab_second = inputs["id_c"][r_ca].to(torch.int32).contiguous()
-        self.flags = flags  # int32[1] each, non-zero = not grouped/sorted; read by callers that skip the check here
+        # the gather lists that no CSR construction has looked at (one launch)
+        lists = [(self.id3_expand, self.n_edges)]
+        if not triplets_only:
+            lists += [(self.id4_reduce_cab, inputs["id4_reduce_intm_ca"].numel()),
+                      (self.id4_expand_abd, self.id4_expand_intm_db.numel()),
+                      (self.id4_int_a, self.n_atoms), (self.id4_int_b, self.n_atoms)]
+        ops.index_range_check(lists, rng)
+        self.flags = flags  # int32[1] each, non-zero = not grouped/sorted/in range; read by callers that skip the check here
         if check:
             bad = torch.cat(flags).max().item()
             if bad:
-                raise _lib.GemnetB200Error(
-                    "index tensors are not grouped/sorted as the reference DataContainer produces them "
-                    "(batch_seg, id3_reduce_ca, id4_reduce_ca must be non-decreasing and in range)")
+                raise _lib.GemnetB200Error(INDEX_ERROR)
 
 
 _plans = {}  # (pointers, sizes, model kind) -> (weakref of the id_c tensor, plan); a few entries, least recent out
@@ -339,3 +352,229 @@ def pad_batch(inputs, cap, out=None, check=_CHECK_SORTED):
         o["id3_reduce_ca"][T:] = E + r_local
         o["id3_expand_ba"][T:] = E + tb["partner"][r_local]
     return out, (A, E, T, M)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N2: index construction on the device (csrc/graph_device.cu; include/gemnet_b200.h, gemnet_device_graph).
+class DeviceGraphDesc(ctypes.Structure):
+    """ctypes mirror of `gemnet_device_graph`."""
+    _fields_ = ([("R", ctypes.c_void_p), ("n_per_mol", ctypes.c_void_p), ("hdr", ctypes.c_void_p),
+                 ("cutoff", ctypes.c_double), ("int_cutoff", ctypes.c_double), ("triplets_only", ctypes.c_int32)]
+                + [(k, ctypes.c_int64) for k in ("cap_atoms", "cap_molecules", "cap_edges", "cap_triplets", "cap_int_edges",
+                                       "cap_intm", "cap_quads")]
+                + [(k, ctypes.c_void_p) for k in ("mol_off", "atom_cnt", "upper_off", "in_ptr", "int_off", "incoming", "incoming_pos",
+                                     "intm_off_a", "intm_off_b", "quad_ptr", "R32", "batch_seg", "id_c", "id_a",
+                                     "id_undir", "id_swap", "id3_expand_ba", "id3_reduce_ca", "Kidx3", "rowptr3",
+                                     "id4_int_a", "id4_int_b", "id4_reduce_intm_ca", "id4_reduce_intm_ab",
+                                     "id4_expand_intm_db", "id4_expand_intm_ab", "id4_reduce_ca", "id4_expand_db",
+                                     "id4_reduce_cab", "id4_expand_abd", "Kidx4")])
+
+
+HDR_WORDS = 16
+HDR_ATOMS, HDR_MOLS, HDR_UPPER, HDR_EDGES, HDR_TRIPLETS, HDR_INT_EDGES, HDR_INTM, HDR_QUADS, HDR_OVERFLOW = range(9)
+_I32_MAX = 2 ** 31 - 1
+_EDGE_ARRAYS = ("id_c", "id_a", "id_undir", "id_swap", "incoming", "incoming_pos")
+_TRIPLET_ARRAYS = ("id3_expand_ba", "id3_reduce_ca", "Kidx3")
+_INT_ARRAYS = ("id4_int_a", "id4_int_b")
+_INTM_ARRAYS = ("id4_reduce_intm_ca", "id4_reduce_intm_ab", "id4_expand_intm_db", "id4_expand_intm_ab")
+_QUAD_ARRAYS = ("id4_reduce_ca", "id4_expand_db", "id4_reduce_cab", "id4_expand_abd", "Kidx4")
+
+
+class _CudaBackend:
+    """Arrays are torch CUDA tensors, the stages are the C-ABI entry points on the current stream."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.GemnetB200Error("the device index builder needs a CUDA device; there is no CPU fallback "
+                                       "(graph.build_batch is the host builder)")
+        self.lib = _lib.load()
+
+    def empty(self, n, dtype=torch.int32):
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]  # never a null pointer
+
+    @staticmethod
+    def host_buffer(n, dtype=torch.int32):
+        return torch.zeros(max(int(n), 1), dtype=dtype).pin_memory()[:int(n)]
+
+    @staticmethod
+    def np_view(t):
+        return t.numpy()
+
+    @staticmethod
+    def copy_(dst, src):
+        dst.copy_(src, non_blocking=True)
+
+    def upload(self, arr):
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+
+    @staticmethod
+    def ptr(t):
+        return t.data_ptr() or None
+
+    @staticmethod
+    def host(t):
+        return t.cpu().numpy()
+
+    @staticmethod
+    def widen(t):
+        return t.to(torch.int64)
+
+    def run(self, stage, desc, *extra):
+        fn = getattr(self.lib, "gemnet_graph_device_" + stage)
+        kernels = {"count": 3, "edges": 4 if desc.triplets_only else 6, "quads": 1, "pad": 1}[stage]
+        _lib.check(fn(ctypes.byref(desc), *extra, ops._stream()), "gemnet_graph_device_" + stage, kernels=kernels)
+
+
+def _device_graph_build(be, R64, N, cutoff, int_cutoff, triplets_only):
+    """Dynamic-shape use of the device builder (count -> allocate -> edges -> allocate -> quads) on backend `be`.
+    Returns (arrays dict, header as numpy)."""
+    A, M = int(R64.shape[0]), int(N.shape[0])
+    a = {"R64": be.upload(R64.reshape(-1)), "n_per_mol": be.upload(N.astype(np.int32)),
+         "hdr": be.upload(np.array([A, M] + [0] * (HDR_WORDS - 2), dtype=np.int32)),
+         "mol_off": be.empty(M + 1), "atom_cnt": be.empty(3 * A), "upper_off": be.empty(A + 1), "in_ptr": be.empty(A + 1),
+         "int_off": be.empty(A + 1), "R32": be.empty(3 * A, torch.float32), "batch_seg": be.empty(A)}
+    d = DeviceGraphDesc()
+    d.R, d.n_per_mol, d.hdr = be.ptr(a["R64"]), be.ptr(a["n_per_mol"]), be.ptr(a["hdr"])
+    d.cutoff, d.int_cutoff, d.triplets_only = float(cutoff), float(int_cutoff), int(bool(triplets_only))
+    d.cap_atoms, d.cap_molecules = A, M
+    d.cap_edges = d.cap_triplets = d.cap_int_edges = d.cap_intm = d.cap_quads = _I32_MAX  # sizes not known yet
+    for k in ("mol_off", "atom_cnt", "upper_off", "in_ptr", "int_off", "R32", "batch_seg"):
+        setattr(d, k, be.ptr(a[k]))
+    be.run("count", d)
+    hdr = be.host(a["hdr"])
+    if hdr[HDR_OVERFLOW]:
+        raise _lib.GemnetB200Error(f"device index builder: inconsistent sizes (flags {int(hdr[HDR_OVERFLOW])}): the atoms "
+                                   "per molecule do not add up to the number of coordinates, or a count exceeds 2^31-1")
+    nE, nT, nI, nIm = (int(hdr[k]) for k in (HDR_EDGES, HDR_TRIPLETS, HDR_INT_EDGES, HDR_INTM))
+    sizes = [(_EDGE_ARRAYS, nE), (_TRIPLET_ARRAYS, nT)]
+    if not triplets_only:
+        sizes += [(_INT_ARRAYS, nI), (_INTM_ARRAYS, nIm)]
+        a["intm_off_a"], a["intm_off_b"], a["quad_ptr"] = be.empty(nI + 1), be.empty(nI + 1), be.empty(nE + 1)
+    a["rowptr3"] = be.empty(nE + 1)
+    for names, n in sizes:
+        for k in names:
+            a[k] = be.empty(n)
+    d.cap_edges, d.cap_triplets, d.cap_int_edges, d.cap_intm = nE, nT, nI, nIm
+    for k in a:
+        if k not in ("R64", "n_per_mol", "hdr"):
+            setattr(d, k, be.ptr(a[k]))
+    be.run("edges", d)
+    if not triplets_only:
+        hdr = be.host(a["hdr"])
+        if hdr[HDR_OVERFLOW]:
+            raise _lib.GemnetB200Error("device index builder: more than 2^31-1 quadruplets in one batch")
+        nQ = int(hdr[HDR_QUADS])
+        for k in _QUAD_ARRAYS:
+            a[k] = be.empty(nQ)
+            setattr(d, k, be.ptr(a[k]))
+        d.cap_quads = nQ
+        be.run("quads", d)
+    return a, hdr
+
+
+def build_batch_device(R_list, Z_list, cutoff=5.0, int_cutoff=10.0, triplets_only=True, device="cuda",
+                       index_dtype=torch.int32, _backend=None):
+    """Index construction ON THE GPU: the drop-in for DataContainer.__getitem__ /
+    ase_calculator.Molecule.get (data_container.py:156-408) that uploads only the coordinates (float64, as the
+    reference's distance test uses them), atomic numbers and molecule sizes, and builds every index array of the
+    reference's input dict with the kernels of csrc/graph_device.cu — the same arrays, element for element, as
+    `build_batch` (tests/test_gpu_graph_device.py).  Returns the dict on `device`: float32 R, `index_dtype` index
+    tensors (int32 = what the kernels consume; torch.int64 = the reference's dtype, data_container.py:505-512).
+    Two device->host reads of the 64-byte size header (one for triplet models) are the only synchronisations."""
+    if index_dtype not in (None, torch.int32, torch.int64):
+        raise ValueError("index_dtype must be torch.int32 or torch.int64")
+    be = _backend or _CudaBackend(device)
+    N = np.array([len(z) for z in Z_list], dtype=np.int32)
+    R64 = (np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, 3) for r in R_list], axis=0) if len(R_list)
+           else np.zeros((0, 3)))
+    a, _ = _device_graph_build(be, np.ascontiguousarray(R64), N, cutoff, int_cutoff, triplets_only)
+    Z = np.concatenate([np.asarray(z) for z in Z_list]).astype(np.int64) if len(Z_list) else np.zeros(0, np.int64)
+    out = {"N": be.upload(N.astype(np.int64)), "Z": be.upload(Z), "R": a["R32"].reshape(-1, 3)}
+    keys = ("batch_seg",) + TRIPLET_KEYS + (() if triplets_only else QUAD_KEYS)
+    for k in keys:
+        out[k] = a[k] if index_dtype in (None, torch.int32) else be.widen(a[k])
+    return out
+
+
+def count_batch(R_list, Z_list, cutoff):
+    """(n_edges, n_triplets) of a batch from the host coordinates alone (gemnet_graph_count_host: the distance test
+    without any index emission) — what a static-shape launch needs to pick its capacity bucket."""
+    N = np.array([len(z) for z in Z_list], dtype=np.int32)
+    R64 = (np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, 3) for r in R_list], axis=0))
+           if len(R_list) else np.zeros((0, 3)))
+    ne, nt = ctypes.c_int64(), ctypes.c_int64()
+    rc = _lib.load().gemnet_graph_count_host(R64.ctypes.data, N.ctypes.data, len(N), float(cutoff), ctypes.byref(ne),
+                                             ctypes.byref(nt))
+    _lib.check(rc, "gemnet_graph_count_host", kernels=0)
+    return int(ne.value), int(nt.value)
+
+
+class DeviceStaticBuilder:
+    """Static-shape use of the device builder for triplet models: capacity-sized device arrays, three stage calls
+    (count, edges, pad) that read every size from the device header, so ONE captured CUDA graph builds the padded input
+    dict of `pad_batch` for any batch that fits the capacity.  Per batch the host only writes coordinates, atomic
+    numbers and molecule sizes into the pinned staging buffers (`stage`); `enqueue` issues the H2D copies and the
+    kernels on the current stream (this is what gets captured)."""
+
+    def __init__(self, cap, cutoff, device="cuda", backend=None):
+        be = self.be = backend or _CudaBackend(device)
+        self.cap, self.cutoff = cap, float(cutoff)
+        A, E, T, M = cap.atoms, cap.edges, cap.triplets, cap.molecules
+        f64 = torch.float64
+        self.host = {"R64": be.host_buffer(3 * A, f64), "Z": be.host_buffer(A), "n_per_mol": be.host_buffer(M),
+                     "hdr": be.host_buffer(HDR_WORDS)}
+        self.host_np = {k: be.np_view(v) for k, v in self.host.items()}
+        for v in self.host_np.values():
+            v[...] = 0
+        a = self.a = {"R64": be.empty(3 * A, f64), "Z": be.empty(A), "n_per_mol": be.empty(M), "hdr": be.empty(HDR_WORDS),
+                      "mol_off": be.empty(M + 1), "atom_cnt": be.empty(3 * A), "upper_off": be.empty(A + 1),
+                      "in_ptr": be.empty(A + 1), "R32": be.empty(3 * A, torch.float32), "batch_seg": be.empty(A),
+                      "rowptr3": be.empty(E + 1), "N": be.empty(M + 1)}
+        for k in _EDGE_ARRAYS:
+            a[k] = be.empty(E)
+        for k in _TRIPLET_ARRAYS:
+            a[k] = be.empty(T)
+        d = self.desc = DeviceGraphDesc()
+        d.R, d.n_per_mol, d.hdr = be.ptr(a["R64"]), be.ptr(a["n_per_mol"]), be.ptr(a["hdr"])
+        d.cutoff, d.int_cutoff, d.triplets_only = self.cutoff, 0.0, 1
+        d.cap_atoms, d.cap_molecules, d.cap_edges, d.cap_triplets = A, M, E, T
+        d.cap_int_edges = d.cap_intm = d.cap_quads = 0
+        for k in a:
+            if k not in ("R64", "n_per_mol", "hdr", "Z", "N"):
+                setattr(d, k, be.ptr(a[k]))
+        self.sizes = (0, 0)
+
+    def stage(self, R_list, Z_list):
+        """host side of one batch: coordinates (float64), atomic numbers, atoms per molecule, (n_atoms, n_molecules)"""
+        h = self.host_np
+        M = len(Z_list)
+        A = 0
+        for r, z in zip(R_list, Z_list):
+            n = len(z)
+            if A + n + BatchCapacity.PAD_ATOMS > self.cap.atoms or M > self.cap.molecules:
+                raise _lib.GemnetB200Error(f"batch exceeds {self.cap}")
+            h["R64"][3 * A:3 * (A + n)] = np.asarray(r, dtype=np.float64).reshape(-1)
+            h["Z"][A:A + n] = z
+            A += n
+        h["n_per_mol"][:M] = [len(z) for z in Z_list]
+        h["hdr"][0], h["hdr"][1] = A, M
+        self.sizes = (A, M)
+        return A, M
+
+    def enqueue(self):
+        be, a, d = self.be, self.a, self.desc
+        for k in ("R64", "Z", "n_per_mol", "hdr"):
+            be.copy_(a[k], self.host[k])
+        be.run("count", d)
+        be.run("edges", d)
+        be.run("pad", d, be.ptr(a["Z"]), be.ptr(a["N"]))
+
+    def inputs(self):
+        a = self.a
+        out = {k: a[k] for k in SERVING_KEYS if k not in ("R",)}
+        out["R"] = a["R32"].reshape(-1, 3)
+        return out
+
+    def header(self):
+        return self.be.host(self.a["hdr"])

@@ -111,6 +111,10 @@ class GemNet(torch.nn.Module):
         ]
         self.out_blocks = torch.nn.ModuleList(out_blocks)
         self.int_blocks = torch.nn.ModuleList(int_blocks)
+        # after the reference's own argument checks (same exceptions as gemnet.py / basis_layers.py for what IT rejects)
+        _check_supported_shapes(num_spherical, num_radial, emb_size_atom, emb_size_edge, emb_size_trip, emb_size_quad,
+                                emb_size_rbf, emb_size_cbf, emb_size_sbf, emb_size_bil_trip, emb_size_bil_quad,
+                                triplets_only)
 
     # ------------------------------------------------------------------------------------------ weight caches
     def invalidate_caches(self):
@@ -249,11 +253,12 @@ class GemNet(torch.nn.Module):
         `inputs["R"]` first)."""
         return GraphedGemNet(self, inputs, warmup)
 
-    def make_serving(self, capacity, warmup=3):
+    def make_serving(self, capacity, warmup=3, device_build=False):
         """Static-shape serving: ONE CUDA graph (H2D of the batch, index plan, energy+force evaluation, D2H of E and
         F) that serves every batch fitting `capacity` (graph.BatchCapacity).  Returns a ServingGemNet; its call
-        takes the reference-format HOST batch and returns (E, F) on the host."""
-        return ServingGemNet(self, capacity, warmup)
+        takes the reference-format HOST batch and returns (E, F) on the host.  `device_build=True`: the graph starts
+        from raw coordinates instead (`call_molecules(R_list, Z_list)`; index construction on the GPU, row N2)."""
+        return ServingGemNet(self, capacity, warmup, device_build)
 
     def make_serving_pool(self, molecules, max_atoms, growth=1.12, max_graphs=16, warmup=2):
         """Serving for a stream of batches of unknown size: capacities on a geometric ladder (each batch runs in
@@ -261,19 +266,48 @@ class GemNet(torch.nn.Module):
         graph per bucket, captured on first use.  Returns a ServingPool (same call convention as ServingGemNet)."""
         return ServingPool(self, molecules, max_atoms, growth, max_graphs, warmup)
 
-    def make_molecule_server(self, molecules, max_atoms, workers=2, **pool_kwargs):
+    def make_molecule_server(self, molecules, max_atoms, workers=2, index_build="host", **pool_kwargs):
         """Serving from raw molecules: (R_list, Z_list) on the host -> (E, F) on the host.  The index construction
-        (row H0: the native builder behind graph.build_batch, data_container.py:156-489) runs on `workers` host threads
-        and is pipelined with the GPU evaluation by MoleculeServer.stream(); the evaluation is the static-shape CUDA
-        graph pool of make_serving_pool.  This is what ase_calculator.py:148-170 does per MD step (rebuild indices,
-        predict) as one call."""
-        return MoleculeServer(self, molecules, max_atoms, workers, **pool_kwargs)
+        (data_container.py:156-489) runs either on the host (`index_build="host"`, row H0: the native builder behind
+        graph.build_batch on `workers` threads, pipelined with the GPU evaluation by MoleculeServer.stream()) or on the
+        GPU (`index_build="device"`, row N2: csrc/graph_device.cu — inside the captured graph for triplet models); the
+        evaluation is the static-shape CUDA graph pool of make_serving_pool.  This is what ase_calculator.py:148-170 does
+        per MD step (rebuild indices, predict) as one call."""
+        return MoleculeServer(self, molecules, max_atoms, workers, index_build, **pool_kwargs)
 
     def load_weights(self, path):
         self.load_state_dict(torch.load(path))
 
     def save_weights(self, path):
         torch.save(self.state_dict(), path)
+
+
+def _check_supported_shapes(num_spherical, num_radial, emb_size_atom, emb_size_edge, emb_size_trip, emb_size_quad,
+                            emb_size_rbf, emb_size_cbf, emb_size_sbf, emb_size_bil_trip, emb_size_bil_quad, triplets_only):
+    """The reference accepts any hyperparameters (gemnet.py:82-113); this library's kernels are compiled for the
+    published GemNet configurations.  Fail at construction with the list of what is built, not at the first forward
+    after the weights were loaded."""
+    bad = []
+    if not 1 <= num_spherical <= 8:
+        bad.append(f"num_spherical={num_spherical} (register-resident Legendre / Y_lm recurrences: 1..8)")
+    if not 1 <= num_radial <= 16:
+        bad.append(f"num_radial={num_radial} (radial-basis kernels: 1..16)")
+    trip = (num_spherical, emb_size_trip, emb_size_cbf, emb_size_bil_trip)
+    if trip != (7, 64, 16, 64):
+        bad.append(f"(num_spherical, emb_size_trip, emb_size_cbf, emb_size_bil_trip)={trip}: the triplet bilinear "
+                   "kernels (segbilinear*.cu) are built for (7, 64, 16, 64)")
+    if not triplets_only:
+        quad = (num_spherical ** 2, emb_size_quad, emb_size_sbf, emb_size_bil_quad)
+        if quad != (49, 32, 32, 32):
+            bad.append(f"(num_spherical^2, emb_size_quad, emb_size_sbf, emb_size_bil_quad)={quad}: the quadruplet "
+                       "bilinear kernels are built for (49, 32, 32, 32)")
+    for name, v in (("emb_size_atom", emb_size_atom), ("emb_size_edge", emb_size_edge), ("emb_size_rbf", emb_size_rbf),
+                    ("emb_size_trip", emb_size_trip), ("emb_size_quad", emb_size_quad),
+                    ("emb_size_bil_trip", emb_size_bil_trip), ("emb_size_bil_quad", emb_size_bil_quad)):
+        if not (4 <= v <= 128 and v % 4 == 0):
+            bad.append(f"{name}={v} (tcgen05 dense kernels: multiples of 4 in [4, 128])")
+    if bad:
+        raise _lib.GemnetB200Error("GemNet (B200): unsupported hyperparameters — " + "; ".join(bad))
 
 
 class _EngineTrainFn(torch.autograd.Function):
@@ -328,22 +362,36 @@ class ServingGemNet:
     edge->atom orderings) with the plan kernels, evaluates energies and forces and copies E and F to pinned host
     buffers.  One cudaGraphLaunch per batch; the pad rows are cut off on return."""
 
-    def __init__(self, model, capacity, warmup=3):
+    def __init__(self, model, capacity, warmup=3, device_build=False):
         assert not model.training, "serving capture is for inference (model.eval())"
         if not model.triplets_only:
             raise NotImplementedError("static-shape serving is built for triplets_only models (GemNet-T / dT)")
         self.model, self.cap = model, capacity
         dev = next(model.parameters()).device
-        self.host = graph.serving_buffers(capacity, pin_memory=True)
-        self.dev = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
-        empty = {k: v[:0] for k, v in self.host.items()}
-        graph.pad_batch(empty, capacity, out=self.host)  # an all-pad batch for warm-up and capture
+        self.builder = None
+        if device_build:
+            # row N2: the captured graph starts from coordinates — H2D of (R float64, Z, atoms per molecule, sizes), the
+            # index-construction kernels (csrc/graph_device.cu) and the pad kernel write the capacity-sized input dict
+            self.builder = graph.DeviceStaticBuilder(capacity, model.cutoff, device=dev)
+            self.builder.stage([], [])  # an all-pad batch for warm-up and capture
+            self.host = self.builder.host
+            self.hdr_host = torch.zeros(graph.HDR_WORDS, dtype=torch.int32).pin_memory()
+        else:
+            self.host = graph.serving_buffers(capacity, pin_memory=True)
+            self.dev = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
+            empty = {k: v[:0] for k, v in self.host.items()}
+            graph.pad_batch(empty, capacity, out=self.host)  # an all-pad batch for warm-up and capture
         self.E_host = self.F_host = self.flag_host = None
 
         def step():
-            for k, h in self.host.items():
-                self.dev[k].copy_(h, non_blocking=True)
-            inputs = dict(self.dev)  # a fresh dict: the index plan is rebuilt (inside the graph) for every batch
+            if self.builder is not None:
+                self.builder.enqueue()
+                inputs = self.builder.inputs()
+                self.hdr_host.copy_(self.builder.a["hdr"], non_blocking=True)
+            else:
+                for k, h in self.host.items():
+                    self.dev[k].copy_(h, non_blocking=True)
+                inputs = dict(self.dev)  # a fresh dict: the index plan is rebuilt (inside the graph) for every batch
             inputs[graph._VALIDATED_KEY] = True
             inputs[graph._REBUILD_KEY] = True   # same device buffers, new contents: the plan kernels are part of the graph
             E, F = model(inputs)
@@ -369,17 +417,33 @@ class ServingGemNet:
         with torch.cuda.graph(self.graph):
             step()
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
-        self.d2h_bytes = self.E_host.numel() * 4 + self.F_host.numel() * 4
+        self.d2h_bytes = self.E_host.numel() * 4 + self.F_host.numel() * 4 + (0 if self.builder is None else 64)
+
+    def call_molecules(self, R_list, Z_list):
+        """(R_list, Z_list) on the HOST -> (E, F) host tensors; the index construction runs inside the captured graph
+        (needs device_build=True).  Raises if the batch did not fit the capacity (the index arrays are then untouched)."""
+        if self.builder is None:
+            raise _lib.GemnetB200Error("this runner was captured for host-built batches (device_build=False)")
+        A, M = self.builder.stage(R_list, Z_list)
+        self.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        ov = int(self.hdr_host[graph.HDR_OVERFLOW])
+        if ov:
+            raise _lib.GemnetB200Error(
+                f"device index builder: batch does not fit {self.cap} (flags {ov}: 1 sizes inconsistent, 2 edges, "
+                f"4 triplets, 64 no room for the pad molecule); counted edges {int(self.hdr_host[graph.HDR_EDGES])}, "
+                f"triplets {int(self.hdr_host[graph.HDR_TRIPLETS])}")
+        return self.E_host[:M].clone(), self.F_host[:A].clone()
 
     def __call__(self, inputs):
         """inputs: reference-format batch on the HOST (torch CPU tensors or numpy arrays) -> (E, F) host tensors."""
+        if self.builder is not None:
+            raise _lib.GemnetB200Error("this runner builds its indices on the device: use call_molecules(R_list, Z_list)")
         _, (A, _, _, M) = graph.pad_batch(inputs, self.cap, out=self.host, check=False)
         self.graph.replay()
         torch.cuda.current_stream().synchronize()
         if self.flag_host.any():  # the plan kernels validate what the host-side check would (no extra sync: same D2H)
-            raise _lib.GemnetB200Error(
-                "index tensors are not grouped/sorted as the reference DataContainer produces them "
-                "(batch_seg, id3_reduce_ca must be non-decreasing and in range)")
+            raise _lib.GemnetB200Error(graph.INDEX_ERROR)
         return self.E_host[:M].clone(), self.F_host[:A].clone()
 
 
@@ -414,6 +478,20 @@ class ServingPool:
         self.runners[key] = runner
         return runner(inputs)
 
+    def call_molecules(self, R_list, Z_list):
+        """Raw molecules on the host -> (E, F): the bucket is chosen from the host's edge / triplet COUNT (one pass
+        over the distance tests, graph.count_batch), the index arrays themselves are built inside the captured graph."""
+        n_edges, n_triplets = graph.count_batch(R_list, Z_list, self.model.cutoff)
+        cap = self.capacity_for(n_edges, n_triplets)
+        key = (cap.edges, cap.triplets, "device")
+        runner = self.runners.pop(key, None)
+        if runner is None:
+            while len(self.runners) >= self.max_graphs:
+                self.runners.pop(next(iter(self.runners)))
+            runner = ServingGemNet(self.model, cap, self.warmup, device_build=True)
+        self.runners[key] = runner
+        return runner.call_molecules(R_list, Z_list)
+
     @property
     def h2d_bytes(self):
         return max((r.h2d_bytes for r in self.runners.values()), default=0)
@@ -431,9 +509,11 @@ class MoleculeServer:
                                    `workers` batches overlaps the GPU evaluation of the current one (the native builder
                                    releases the GIL), results are yielded in order"""
 
-    def __init__(self, model, molecules, max_atoms, workers=2, **pool_kwargs):
+    def __init__(self, model, molecules, max_atoms, workers=2, index_build="host", **pool_kwargs):
         from concurrent.futures import ThreadPoolExecutor
-        self.model = model
+        if index_build not in ("host", "device"):
+            raise ValueError("index_build must be 'host' or 'device'")
+        self.model, self.index_build = model, index_build
         if model.triplets_only:
             self.pool = ServingPool(model, molecules, max_atoms, **pool_kwargs)
         else:
@@ -452,9 +532,20 @@ class MoleculeServer:
         return self.model.predict({k: v.to(self.dev, non_blocking=True) for k, v in host_batch.items()})
 
     def __call__(self, R_list, Z_list):
+        if self.index_build == "device":
+            # row N2: only coordinates / atomic numbers / molecule sizes cross PCIe.  Triplet models: index kernels inside
+            # the captured graph; quadruplet models: dynamic shapes (two reads of the 64-byte size header), eager evaluation
+            if self.pool is not None:
+                return self.pool.call_molecules(R_list, Z_list)
+            m = self.model
+            return m.predict(graph.build_batch_device(R_list, Z_list, m.cutoff, m.int_cutoff, m.triplets_only, self.dev))
         return self.evaluate(self.build(R_list, Z_list))
 
     def stream(self, batches):
+        if self.index_build == "device":  # nothing left on the host to overlap: coordinates in, one launch, results out
+            for R_list, Z_list in batches:
+                yield self(R_list, Z_list)
+            return
         import collections
         pending = collections.deque()
         it = iter(batches)

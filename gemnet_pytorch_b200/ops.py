@@ -56,15 +56,29 @@ def csr_from_sorted(sorted_ids, n_rows):
     return rowptr, flag
 
 
-def csr_by_key(ids, n_rows):
-    """(rowptr int32[n_rows+1], perm int32[n]) — stable counting sort of positions by id."""
+def csr_by_key(ids, n_rows, flag=None):
+    """(rowptr int32[n_rows+1], perm int32[n]) — stable counting sort of positions by id.  `flag` (int32[1], zeroed by
+    the caller) is raised by an id outside [0, n_rows) (such entries are skipped, not written out of bounds)."""
     ids = _i32(ids)
     rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=ids.device)
     perm = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
     ws = torch.empty(n_rows + 1 + ids.numel(), dtype=torch.int32, device=ids.device)
-    _check(_L().gemnet_csr_by_key(_p(ids), ids.numel(), n_rows, _p(rowptr), _p(perm), _p(ws), _stream()),
+    _check(_L().gemnet_csr_by_key(_p(ids), ids.numel(), n_rows, _p(rowptr), _p(perm), _p(ws), _p(flag), _stream()),
            "gemnet_csr_by_key", kernels=5)
     return rowptr, perm
+
+
+def index_range_check(lists, flag):
+    """lists: [(int32 CUDA tensor, bound), ...] (at most 12); raises `flag` (int32[1]) if an id lies outside [0, bound)."""
+    import ctypes
+    lists = [(_i32(t), b) for t, b in lists if t.numel()]
+    if not lists:
+        return
+    n = len(lists)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t, _ in lists])
+    sizes = (ctypes.c_int64 * n)(*[t.numel() for t, _ in lists])
+    bounds = (ctypes.c_int64 * n)(*[int(b) for _, b in lists])
+    _check(_L().gemnet_index_range_check(ptrs, sizes, bounds, n, _p(flag), _stream()), "gemnet_index_range_check")
 
 
 # ----------------------------------------------------------------------------- H1

@@ -43,9 +43,18 @@ int gemnet_csr_from_sorted(const int32_t* sorted_ids, int64_t n, int64_t n_rows,
 
 /* Stable counting sort of `ids` (values in [0, n_rows)): perm = positions ordered by (id, position),
  * rowptr as above.  workspace: int32[n_rows + 1 + n] (cursor + unordered placement).  Used for the edge->atom CSR (id_a) and the
- * transposed triplet CSR (id3_expand_ba). */
+ * transposed triplet CSR (id3_expand_ba).  An id outside [0, n_rows) is skipped and sets `flag` (int32[1],
+ * zero-initialised by the caller, may be NULL) to 1: a malformed index list is reported, never written out of bounds. */
 int gemnet_csr_by_key(const int32_t* ids, int64_t n, int64_t n_rows, int32_t* rowptr, int32_t* perm,
-                      int32_t* workspace, void* stream);
+                      int32_t* workspace, int32_t* flag, void* stream);
+
+/* Range check of the remaining gather lists (id3_expand_ba, id4_expand_*, id4_int_*, ... : the reference indexes
+ * tensors with them and torch raises on an invalid index; here the kernels would read out of bounds): `flag` (int32[1],
+ * zero-initialised by the caller) is set to 1 if any id of list l lies outside [0, bounds_host[l]).  The three arrays
+ * are HOST arrays of n_lists <= GEMNET_RANGE_CHECK_MAX_LISTS entries (device list pointers, sizes, bounds); one launch. */
+#define GEMNET_RANGE_CHECK_MAX_LISTS 12
+int gemnet_index_range_check(const int32_t* const* lists_host, const int64_t* sizes_host, const int64_t* bounds_host,
+                             int32_t n_lists, int32_t* flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * H1  GemNet.calculate_interatomic_vectors (gemnet/model/gemnet.py:262-286)
@@ -409,6 +418,72 @@ int gemnet_graph_copy_host(const gemnet_graph* g, const char* name, int32_t* dst
 /* the same, widened to the int64 the reference's tensors use (data_container.py:505-512); multi-threaded */
 int gemnet_graph_copy_host_i64(const gemnet_graph* g, const char* name, int64_t* dst_host);
 void gemnet_graph_free(gemnet_graph* g);
+
+/* ------------------------------------------------------------------------------------------------
+ * N2  DEVICE index builder: the same arrays as gemnet_graph_build_host (DataContainer.__getitem__ /
+ *     get_triplets / get_quadruplets, gemnet/training/data_container.py:156-408, 411-489), element for element,
+ *     produced on the GPU from the coordinates: count -> exclusive scan -> emission at the final position; no
+ *     atomics, no sort, deterministic.  Nothing allocates or synchronises: the caller owns every array below and
+ *     passes CAPACITIES; the real sizes appear in the device header `hdr`.  Two ways to use it:
+ *       dynamic shapes   count -> read hdr -> allocate the edge-level arrays -> edges -> (quadruplet models) read
+ *                        hdr[QUADS] -> allocate -> quads
+ *       static shapes    (CUDA-graph serving of triplet models) count, edges, pad back to back on capacity-sized
+ *                        arrays; hdr[OVERFLOW] != 0 afterwards means a capacity was too small and the index arrays
+ *                        were left untouched (gemnet_graph_count_host gives the host the sizes beforehand).
+ *     All index arrays are int32.  `hdr` is device int32[GEMNET_GRAPH_HDR_WORDS]:
+ *       [0] n_atoms and [1] n_molecules are WRITTEN BY THE CALLER (device memory, so that a captured graph serves
+ *       batches of any size); gemnet_graph_device_count writes [2] upper-triangle pairs, [3] n_edges, [4] n_triplets,
+ *       [5] interaction edges, [6] intermediate triplets (each of the two lists), [8] overflow bits
+ *       (1 atoms/molecules inconsistent, 2 edges, 4 triplets, 8 interaction edges, 16 intermediate, 32 quadruplets,
+ *       64 no room for the pad molecule),
+ *       [9] bits of max |float(R)|; gemnet_graph_device_edges writes [7] n_quadruplets.
+ * ---------------------------------------------------------------------------------------------- */
+#define GEMNET_GRAPH_HDR_WORDS 16
+typedef struct gemnet_device_graph {
+  /* inputs */
+  const double* R;           /* (cap_atoms, 3) float64; rows >= n_atoms are not read */
+  const int32_t* n_per_mol;  /* (cap_molecules) atoms per molecule; entries >= n_molecules are not read */
+  int32_t* hdr;              /* int32[GEMNET_GRAPH_HDR_WORDS], see above */
+  double cutoff, int_cutoff;
+  int32_t triplets_only;
+  /* capacities, in elements; an array that a stage does not touch may be NULL with capacity 0 */
+  int64_t cap_atoms, cap_molecules, cap_edges, cap_triplets, cap_int_edges, cap_intm, cap_quads;
+  /* workspace */
+  int32_t* mol_off;       /* cap_molecules + 1 */
+  int32_t* atom_cnt;      /* 3 * cap_atoms */
+  int32_t* upper_off;     /* cap_atoms + 1 */
+  int32_t* in_ptr;        /* cap_atoms + 1: CSR of the edges by TARGET atom (row x of the reference's edge_ids) */
+  int32_t* int_off;       /* cap_atoms + 1 (quadruplet models) */
+  int32_t* incoming;      /* cap_edges: edge ids by target atom, ascending source atom */
+  int32_t* incoming_pos;  /* cap_edges: position of an edge in its target's list */
+  int32_t* intm_off_a;    /* cap_int_edges + 1 */
+  int32_t* intm_off_b;    /* cap_int_edges + 1 */
+  int32_t* quad_ptr;      /* cap_edges + 1: CSR of the quadruplets by reduce edge (= rowptr of id4_reduce_ca) */
+  /* outputs (reference key names, data_container.py:186-228) */
+  float* R32;             /* (cap_atoms, 3) float32 copy of R (the model input), may be NULL */
+  int32_t* batch_seg;     /* cap_atoms */
+  int32_t *id_c, *id_a, *id_undir, *id_swap;            /* cap_edges */
+  int32_t *id3_expand_ba, *id3_reduce_ca, *Kidx3;       /* cap_triplets (Kidx3 may be NULL) */
+  int32_t* rowptr3;                                     /* cap_edges + 1: CSR of the triplets by reduce edge */
+  int32_t *id4_int_a, *id4_int_b;                       /* cap_int_edges */
+  int32_t *id4_reduce_intm_ca, *id4_reduce_intm_ab, *id4_expand_intm_db, *id4_expand_intm_ab; /* cap_intm */
+  int32_t *id4_reduce_ca, *id4_expand_db, *id4_reduce_cab, *id4_expand_abd, *Kidx4;           /* cap_quads */
+} gemnet_device_graph;
+
+/* stage 1: molecule offsets, batch_seg, R32, per-atom neighbour counts, their scans, the sizes in hdr */
+int gemnet_graph_device_count(const gemnet_device_graph* g, void* stream);
+/* stage 2: edges, incoming lists, triplets (+ rowptr3); quadruplet models: interaction edges, intermediate
+ * triplets, quadruplet counts per reduce edge (quad_ptr) and hdr[7] */
+int gemnet_graph_device_edges(const gemnet_device_graph* g, void* stream);
+/* stage 3 (quadruplet models): the five quadruplet arrays */
+int gemnet_graph_device_quads(const gemnet_device_graph* g, void* stream);
+/* static-shape serving of triplet models: fills everything behind the real entries with the inert pad pattern of
+ * gemnet_pad_batch_host.  Z (cap_atoms, in place) and N_out (cap_molecules + 1) complete the model's input dict. */
+int gemnet_graph_device_pad(const gemnet_device_graph* g, int32_t* Z, int32_t* N_out, void* stream);
+/* HOST: the edge and triplet counts of a batch (one pass over the per-molecule distance tests, the cheapest part of
+ * H0), for choosing the capacity bucket before a static-shape launch */
+int gemnet_graph_count_host(const double* R_host, const int32_t* n_per_mol_host, int64_t n_mol, double cutoff,
+                            int64_t* n_edges, int64_t* n_triplets);
 
 /* ------------------------------------------------------------------------------------------------
  * N4  static-shape serving: HOST function.  Writes a reference-format triplet batch (int64 index lists as

@@ -243,4 +243,9 @@ def test_fuse_ok_rejects_other_structures():
     assert engine.fuse_ok(GemNet(**kw))
     assert not engine.fuse_ok(GemNet(**dict(kw, num_before_skip=0)))
     assert not engine.fuse_ok(GemNet(**dict(kw, num_concat=2)))
-    assert not engine.fuse_ok(GemNet(**dict(kw, emb_size_trip=20, emb_size_bil_trip=20)))
+    # hyperparameters no kernel is built for are refused by the constructor, with the list of what is supported
+    from gemnet_pytorch_b200 import _lib
+    with pytest.raises(_lib.GemnetB200Error, match="built for"):
+        GemNet(**dict(kw, emb_size_trip=20, emb_size_bil_trip=20))
+    with pytest.raises(_lib.GemnetB200Error, match="num_spherical"):
+        GemNet(**dict(kw, num_spherical=9))

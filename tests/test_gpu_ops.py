@@ -77,6 +77,29 @@ def test_csr_preparation_bit_exact(ops, dev):
     bad = torch.tensor([0, 2, 1], dtype=torch.int32, device=dev)
     assert ops.csr_from_sorted(bad, 3)[1].item() == 1
     assert ops.csr_from_sorted(torch.tensor([0, 7], dtype=torch.int32, device=dev), 3)[1].item() == 1
+    # ids outside [0, n_rows) raise the flag and are skipped (no out-of-bounds write): the valid ids still form the CSR
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    rp, perm = ops.csr_by_key(torch.tensor([2, -1, 0, 9, 2], dtype=torch.int32, device=dev), 3, flag)
+    assert flag.item() == 1 and rp.cpu().tolist() == [0, 1, 1, 3] and perm.cpu().tolist()[:3] == [2, 0, 4]
+    flag.zero_()
+    ops.csr_by_key(torch.tensor([2, 0, 1], dtype=torch.int32, device=dev), 3, flag)
+    ok = torch.arange(5, dtype=torch.int32, device=dev)
+    ops.index_range_check([(ok, 5), (ok[:0], 0), (ok, 7)], flag)
+    assert flag.item() == 0
+    ops.index_range_check([(ok, 5), (ok, 4)], flag)
+    assert flag.item() == 1
+
+
+def test_malformed_index_lists_are_reported(dev):
+    """a hand-built batch whose gather lists point outside their tables raises instead of reading out of bounds"""
+    from gemnet_pytorch_b200 import _lib, build_batch, graph
+    base = build_batch(*H.molecules([3, 4]), 5.0, 10.0, True)
+    for key, val in (("id_swap", 10 ** 6), ("id_a", -1), ("id3_expand_ba", 10 ** 6)):
+        b = {k: v.clone().to(dev) for k, v in base.items()}
+        b[key][1] = val
+        with pytest.raises(_lib.GemnetB200Error, match="outside its table"):
+            graph.GraphPlan(b, True)
+    graph.GraphPlan({k: v.to(dev) for k, v in base.items()}, True)
 
 
 # ----------------------------------------------------------------------------- H1
