@@ -41,9 +41,30 @@ BASE_KW = dict(num_spherical=7, num_radial=6, num_blocks=4, emb_size_atom=128, e
                forces_coupled=False, output_init="HeOrthogonal", activation="swish", scale_file=None)
 
 
+MOLECULE_KIND = ["coll"]  # "coll" (configs[1-3]) or "clusters" (configs[4]); set by --molecules
+
+
+def cluster_molecules(n_mol, seed, n_atoms=18, radius=3.5, dmin=0.9):
+    """BASELINE configs[4] input (SURVEY §8d input 3): 18-atom clusters, atoms uniform in a 3.5 A ball with rejection-
+    sampled minimum distance 0.9 A — at cutoff 8 A every pair is an edge: 306 edges, 4 896 triplets per molecule."""
+    rng = np.random.default_rng(seed)
+    Rl, Zl = [], []
+    for _ in range(n_mol):
+        pts = []
+        while len(pts) < n_atoms:
+            p = rng.uniform(-radius, radius, size=3)
+            if p @ p <= radius * radius and all(np.linalg.norm(p - q) >= dmin for q in pts):
+                pts.append(p)
+        Rl.append(np.array(pts))
+        Zl.append(rng.choice([1, 6, 8], size=n_atoms, p=[0.543, 0.330, 0.127]).astype(np.int64))
+    return Rl, Zl
+
+
 def synthetic_molecules(n_mol, seed):
     """COLL-shaped synthetic molecules: resample (with replacement) from the 256 committed COLL test molecules and
-    jitter the coordinates by N(0, 0.05 A) (SURVEY §8d input 2)."""
+    jitter the coordinates by N(0, 0.05 A) (SURVEY §8d input 2).  With --molecules clusters: cluster_molecules."""
+    if MOLECULE_KIND[0] == "clusters":
+        return cluster_molecules(n_mol, seed)
     sub = dict(np.load(os.path.join(GOLDEN, "coll_subset.npz")))
     N = sub["N"].astype(np.int64)
     off = np.concatenate([[0], np.cumsum(N)])
@@ -417,8 +438,9 @@ def run_train(args, kw, rank, local_rank, world):
 
 def workload_config(args, kw):
     name = "GemNet-T" if kw["triplets_only"] else "GemNet-Q"
-    return {"workload": f"{name} energy+force inference (forces = -dE/dR), COLL-shaped synthetic batch={args.batch} "
-                        f"molecules/GPU, emb_size=128, cutoff 5 A",
+    shape = "COLL-shaped synthetic" if MOLECULE_KIND[0] == "coll" else "synthetic 18-atom clusters (configs[4])"
+    return {"workload": f"{name} energy+force inference (forces = -dE/dR), {shape} batch={args.batch} "
+                        f"molecules/GPU, emb_size=128, cutoff {kw['cutoff']:g} A",
             "batch_per_gpu": args.batch, "l2": "flushed (256 MiB write) between timed iterations",
             "weights": "seeded synthetic (random-init architecture weights)"}
 
@@ -436,6 +458,9 @@ def main():
     ap.add_argument("--index-build", default="both", choices=["host", "device", "both"],
                     help="where the e2e path constructs the index arrays (row H0 on host threads / row N2 on the GPU); "
                          "'both' measures the two and reports the faster one as e2e, the other under e2e.other_path")
+    ap.add_argument("--cutoff", type=float, default=5.0, help="embedding cutoff in A (BASELINE configs[4]: 8)")
+    ap.add_argument("--molecules", default="coll", choices=["coll", "clusters"],
+                    help="coll = COLL-shaped synthetic molecules; clusters = the 18-atom clusters of configs[4]")
     ap.add_argument("--eager", action="store_true", help="time the eager step instead of its CUDA-graph replay")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train = BASELINE configs[3]: GemNet-dT direct-force training step (fp32), molecule-sharded, "
@@ -445,7 +470,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    kw = dict(BASE_KW, triplets_only=(args.model == "T"))
+    kw = dict(BASE_KW, triplets_only=(args.model == "T"), cutoff=args.cutoff)
+    MOLECULE_KIND[0] = args.molecules
 
     if args.impl == "reference":
         run_reference(args, kw, rank, world)

@@ -219,8 +219,8 @@ using namespace gemnet::gd;
 
 GEMNET_API int gemnet_graph_device_count(const gemnet_device_graph* g, void* stream) {
   GD_REQUIRE_COMMON(g);
-  GEMNET_REQUIRE(g->mol_off && g->atom_cnt && g->upper_off && g->in_ptr && g->batch_seg, "null workspace / output");
-  GEMNET_REQUIRE(g->cap_atoms == 0 || g->R != nullptr, "null R");
+  GEMNET_REQUIRE(g->mol_off && g->upper_off && g->in_ptr, "null workspace");
+  GEMNET_REQUIRE(g->cap_atoms == 0 || (g->R && g->atom_cnt && g->batch_seg), "null atom-level array");
   GEMNET_REQUIRE(g->cap_molecules == 0 || g->n_per_mol != nullptr, "null n_per_mol");
   GEMNET_REQUIRE(g->triplets_only || g->int_off != nullptr, "null int_off");
   cudaStream_t st = as_stream(stream);
@@ -232,7 +232,8 @@ GEMNET_API int gemnet_graph_device_count(const gemnet_device_graph* g, void* str
 
 GEMNET_API int gemnet_graph_device_edges(const gemnet_device_graph* g, void* stream) {
   GD_REQUIRE_COMMON(g);
-  GEMNET_REQUIRE(g->mol_off && g->upper_off && g->in_ptr && g->batch_seg && g->rowptr3, "null workspace / output");
+  GEMNET_REQUIRE(g->mol_off && g->upper_off && g->in_ptr && g->rowptr3, "null workspace / output");
+  GEMNET_REQUIRE(g->cap_atoms == 0 || (g->R && g->batch_seg), "null atom-level array");
   if (g->cap_edges > 0)
     GEMNET_REQUIRE(g->incoming && g->incoming_pos && g->id_c && g->id_a && g->id_undir && g->id_swap, "null edge array");
   if (g->cap_triplets > 0) GEMNET_REQUIRE(g->id3_expand_ba && g->id3_reduce_ca, "null triplet array");
@@ -259,7 +260,8 @@ GEMNET_API int gemnet_graph_device_edges(const gemnet_device_graph* g, void* str
 GEMNET_API int gemnet_graph_device_quads(const gemnet_device_graph* g, void* stream) {
   GD_REQUIRE_COMMON(g);
   GEMNET_REQUIRE(!g->triplets_only, "quadruplets were not requested (triplets_only)");
-  GEMNET_REQUIRE(g->int_off && g->intm_off_a && g->intm_off_b && g->quad_ptr && g->incoming_pos, "null workspace");
+  GEMNET_REQUIRE(g->int_off && g->intm_off_a && g->intm_off_b && g->quad_ptr, "null workspace");
+  GEMNET_REQUIRE(g->cap_edges == 0 || (g->incoming_pos && g->id_a && g->id_c), "null edge array");
   if (g->cap_quads > 0)
     GEMNET_REQUIRE(g->id4_reduce_ca && g->id4_expand_db && g->id4_reduce_cab && g->id4_expand_abd && g->Kidx4,
                    "null quadruplet array");

@@ -410,7 +410,8 @@ class _CudaBackend:
 
     @staticmethod
     def ptr(t):
-        return t.data_ptr() or None
+        # an empty view has a null data_ptr: hand the library the (never empty) allocation behind it instead
+        return t.data_ptr() or t.untyped_storage().data_ptr() or None
 
     @staticmethod
     def host(t):
@@ -497,17 +498,33 @@ def build_batch_device(R_list, Z_list, cutoff=5.0, int_cutoff=10.0, triplets_onl
     return out
 
 
-def count_batch(R_list, Z_list, cutoff):
-    """(n_edges, n_triplets) of a batch from the host coordinates alone (gemnet_graph_count_host: the distance test
-    without any index emission) — what a static-shape launch needs to pick its capacity bucket."""
-    N = np.array([len(z) for z in Z_list], dtype=np.int32)
-    R64 = (np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, 3) for r in R_list], axis=0))
-           if len(R_list) else np.zeros((0, 3)))
+def concat_molecules(R_list, Z_list):
+    """(R float64 (A,3) contiguous, Z (A,), N int32 (M,)) of a list of molecules"""
+    M = len(Z_list)
+    if M == 0:
+        return np.zeros((0, 3)), np.zeros(0, np.int64), np.zeros(0, np.int32)
+    N = np.fromiter((len(z) for z in Z_list), dtype=np.int32, count=M)
+    R64 = np.concatenate(R_list, axis=0) if M > 1 else np.asarray(R_list[0])
+    R64 = np.ascontiguousarray(R64, dtype=np.float64).reshape(-1, 3)
+    Z = np.concatenate(Z_list) if M > 1 else np.asarray(Z_list[0])
+    if R64.shape[0] != Z.shape[0] or int(N.sum()) != Z.shape[0]:
+        raise ValueError("R_list and Z_list disagree on the number of atoms")
+    return R64, Z, N
+
+
+def count_arrays(R64, N, cutoff):
+    """(n_edges, n_triplets) of a concatenated batch (gemnet_graph_count_host: the per-molecule distance tests without
+    any index emission) — what a static-shape launch needs to pick its capacity bucket."""
     ne, nt = ctypes.c_int64(), ctypes.c_int64()
     rc = _lib.load().gemnet_graph_count_host(R64.ctypes.data, N.ctypes.data, len(N), float(cutoff), ctypes.byref(ne),
                                              ctypes.byref(nt))
     _lib.check(rc, "gemnet_graph_count_host", kernels=0)
     return int(ne.value), int(nt.value)
+
+
+def count_batch(R_list, Z_list, cutoff):
+    R64, _, N = concat_molecules(R_list, Z_list)
+    return count_arrays(R64, N, cutoff)
 
 
 class DeviceStaticBuilder:
@@ -547,17 +564,16 @@ class DeviceStaticBuilder:
 
     def stage(self, R_list, Z_list):
         """host side of one batch: coordinates (float64), atomic numbers, atoms per molecule, (n_atoms, n_molecules)"""
+        return self.stage_arrays(*concat_molecules(R_list, Z_list))
+
+    def stage_arrays(self, R64, Z, N):
         h = self.host_np
-        M = len(Z_list)
-        A = 0
-        for r, z in zip(R_list, Z_list):
-            n = len(z)
-            if A + n + BatchCapacity.PAD_ATOMS > self.cap.atoms or M > self.cap.molecules:
-                raise _lib.GemnetB200Error(f"batch exceeds {self.cap}")
-            h["R64"][3 * A:3 * (A + n)] = np.asarray(r, dtype=np.float64).reshape(-1)
-            h["Z"][A:A + n] = z
-            A += n
-        h["n_per_mol"][:M] = [len(z) for z in Z_list]
+        A, M = int(Z.shape[0]), int(N.shape[0])
+        if A + BatchCapacity.PAD_ATOMS > self.cap.atoms or M > self.cap.molecules:
+            raise _lib.GemnetB200Error(f"batch (atoms={A}, molecules={M}) exceeds {self.cap}")
+        h["R64"][:3 * A] = R64.reshape(-1)
+        h["Z"][:A] = Z
+        h["n_per_mol"][:M] = N
         h["hdr"][0], h["hdr"][1] = A, M
         self.sizes = (A, M)
         return A, M

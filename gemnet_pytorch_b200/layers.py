@@ -127,34 +127,7 @@ class EdgeEmbedding(torch.nn.Module):
 
 
 # ----------------------------------------------------------------------------- scaling (scaling.py:150-174)
-class ScalingFactor(torch.nn.Module):
-    """y * scale_factor.  The value is read from `scale_file` (JSON, key = name) when given and is stored in /
-    loaded from the state_dict.  The variance-fitting machinery of the reference (AutomaticFit) is an offline
-    tool outside the hot path; in the kernels the factor is folded into epilogues (row H13)."""
-
-    def __init__(self, scale_file, name, device=None):
-        super().__init__()
-        self.scale_factor = torch.nn.Parameter(torch.tensor(1.0, device=device), requires_grad=False)
-        self._name = name
-        if scale_file is not None:
-            if not scale_file.endswith(".json"):
-                raise UserWarning(f"Path {scale_file} is not a json-path.")
-            with open(scale_file, "r") as f:
-                content = json.load(f)
-            if name in content:
-                with torch.no_grad():
-                    self.scale_factor.copy_(torch.tensor(content[name]))
-        self._cached = None
-
-    def value(self):
-        """Python float of the factor (for kernel epilogues); cached per parameter version (one sync)."""
-        v = self.scale_factor._version
-        if self._cached is None or self._cached[0] != v or self._cached[2] != self.scale_factor.data_ptr():
-            self._cached = (v, float(self.scale_factor.detach().cpu()), self.scale_factor.data_ptr())
-        return self._cached[1]
-
-    def forward(self, x_ref, y):
-        return y * self.scale_factor
+from .scaling import ScalingFactor  # noqa: E402,F401  (the module tree keeps `layers.ScalingFactor`)
 
 
 # ----------------------------------------------------------------------------- basis layers (basis_layers.py)
@@ -246,6 +219,7 @@ class AtomUpdateBlock(torch.nn.Module):
     def forward(self, h, m, rbf, plan):
         x = ops.edge_to_atom(m, self.dense_rbf(rbf), plan.id_a, plan.atom_perm, plan.atom_rowptr,
                              scale=self.scale_sum.value())
+        self.scale_sum.observe(m, x)  # atom_update_block.py:68 (a no-op unless this factor is being fitted)
         for layer in self.layers:
             x = layer(x)
         return x
@@ -289,6 +263,9 @@ class OutputBlock(AtomUpdateBlock):
         else:
             x_E = ops.edge_to_atom(m, r, plan.id_a, plan.atom_perm, plan.atom_rowptr, scale=self.scale_sum.value())
             x_F = 0
+        self.scale_sum.observe(m, x_E)        # atom_update_block.py:173
+        if self.direct_forces:
+            self.scale_rbf.observe(m, x_F)    # :181
         for layer in self.seq_energy:
             x_E = layer(x_E)
         x_E = self.out_energy(x_E)
@@ -315,11 +292,13 @@ class TripletInteraction(torch.nn.Module):
         self.up_projection_ac = Dense(emb_size_bilinear, emb_size_edge, activation=activation, bias=False)
 
     def forward(self, m, rbf3, rbf_W1, sph3, plan, algo=0):
-        x_ba = self.dense_ba(m)
-        x_ba = ops.mul_scale(x_ba, self.mlp_rbf(rbf3), self.scale_rbf.value())
+        x_in = self.dense_ba(m)
+        x_ba = ops.mul_scale(x_in, self.mlp_rbf(rbf3), self.scale_rbf.value())
+        self.scale_rbf.observe(x_in, x_ba)     # interaction_block.py:663
         x_ba = self.down_projection(x_ba)  # (E, emb_size_trip) — NOT gathered: the kernel gathers
         x = self.mlp_cbf(rbf_W1, sph3, x_ba, plan.id3_expand, plan.rowptr3, scale=self.scale_cbf_sum.value(),
                          algo=algo)
+        self.scale_cbf_sum.observe(lambda: x_ba[plan.id3_expand.long()], x)  # :682 (x_ref = the gathered rows)
         x_ca = self.up_projection_ca(x)
         x_ac = ops.gather_rows(self.up_projection_ac(x), plan.id_swap, plan.swap_perm, plan.swap_rowptr)
         return ops.add_scale(INV_SQRT_2, x_ca, x_ac)
@@ -342,14 +321,17 @@ class QuadrupletInteraction(torch.nn.Module):
         self.up_projection_ac = Dense(emb_size_bilinear, emb_size_edge, activation=activation, bias=False)
 
     def forward(self, m, rbf4, cbf4, rbf_W1, ylm, plan, algo=0):
-        x_db = self.dense_db(m)
-        x_db = ops.mul_scale(x_db, self.mlp_rbf(rbf4), self.scale_rbf.value())
+        x_in = self.dense_db(m)
+        x_db = ops.mul_scale(x_in, self.mlp_rbf(rbf4), self.scale_rbf.value())
+        self.scale_rbf.observe(x_in, x_db)     # interaction_block.py:535
         x_db = self.down_projection(x_db)
-        x_db = ops.gather_rows(x_db, plan.id4_expand_intm_db, plan.intm_db_perm, plan.intm_db_rowptr)  # (M, C4)
-        x_db = ops.mul_scale(x_db, self.mlp_cbf(cbf4), self.scale_cbf.value())
+        x_in = ops.gather_rows(x_db, plan.id4_expand_intm_db, plan.intm_db_perm, plan.intm_db_rowptr)  # (M, C4)
+        x_db = ops.mul_scale(x_in, self.mlp_cbf(cbf4), self.scale_cbf.value())
+        self.scale_cbf.observe(x_in, x_db)     # :549
         # second gather (id4_expand_abd) happens inside the kernel
         x = self.mlp_sbf(rbf_W1, ylm, x_db, plan.id4_expand_abd, plan.rowptr4, scale=self.scale_sbf_sum.value(),
                          algo=algo)
+        self.scale_sbf_sum.observe(lambda: x_db[plan.id4_expand_abd.long()], x)  # :555
         x_ca = self.up_projection_ca(x)
         x_ac = ops.gather_rows(self.up_projection_ac(x), plan.id_swap, plan.swap_perm, plan.swap_rowptr)
         return ops.add_scale(INV_SQRT_2, x_ca, x_ac)

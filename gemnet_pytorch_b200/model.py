@@ -12,7 +12,7 @@ fp64, scatters are CSR segment sums without atomics, and scale factors are folde
 """
 import torch
 
-from . import _lib, dense_ops, engine, graph, layers, ops
+from . import _lib, dense_ops, engine, graph, layers, ops, scaling
 from .layers import (AtomEmbedding, BesselBasisLayer, Dense, EdgeEmbedding, EfficientInteractionDownProjection,
                      InteractionBlock, InteractionBlockTripletsOnly, OutputBlock, SphericalBasisLayer,
                      TensorBasisLayer)
@@ -147,6 +147,10 @@ class GemNet(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs):
+        if scaling.fitting_active():
+            # fit_scaling.py: a scale factor is collecting Var(x_ref) / Var(y) — only the layer-by-layer path has those
+            # tensors in HBM
+            return self.forward_autograd(inputs)
         if self.use_engine and self.training and torch.is_grad_enabled() and engine.trainable(self):
             # training step of a direct-force model on the engine: the chain-fused kernels forward and backward, weight
             # gradients from the operands they saved (library GEMMs over the rows), bridged into torch.autograd so that
@@ -422,9 +426,13 @@ class ServingGemNet:
     def call_molecules(self, R_list, Z_list):
         """(R_list, Z_list) on the HOST -> (E, F) host tensors; the index construction runs inside the captured graph
         (needs device_build=True).  Raises if the batch did not fit the capacity (the index arrays are then untouched)."""
+        return self.call_arrays(*graph.concat_molecules(R_list, Z_list))
+
+    def call_arrays(self, R64, Z, N):
+        """the same from the concatenated batch (R float64 (A,3), Z (A,), N int32 (M,))"""
         if self.builder is None:
             raise _lib.GemnetB200Error("this runner was captured for host-built batches (device_build=False)")
-        A, M = self.builder.stage(R_list, Z_list)
+        A, M = self.builder.stage_arrays(R64, Z, N)
         self.graph.replay()
         torch.cuda.current_stream().synchronize()
         ov = int(self.hdr_host[graph.HDR_OVERFLOW])
@@ -481,7 +489,8 @@ class ServingPool:
     def call_molecules(self, R_list, Z_list):
         """Raw molecules on the host -> (E, F): the bucket is chosen from the host's edge / triplet COUNT (one pass
         over the distance tests, graph.count_batch), the index arrays themselves are built inside the captured graph."""
-        n_edges, n_triplets = graph.count_batch(R_list, Z_list, self.model.cutoff)
+        R64, Z, N = graph.concat_molecules(R_list, Z_list)
+        n_edges, n_triplets = graph.count_arrays(R64, N, self.model.cutoff)
         cap = self.capacity_for(n_edges, n_triplets)
         key = (cap.edges, cap.triplets, "device")
         runner = self.runners.pop(key, None)
@@ -490,7 +499,7 @@ class ServingPool:
                 self.runners.pop(next(iter(self.runners)))
             runner = ServingGemNet(self.model, cap, self.warmup, device_build=True)
         self.runners[key] = runner
-        return runner.call_molecules(R_list, Z_list)
+        return runner.call_arrays(R64, Z, N)
 
     @property
     def h2d_bytes(self):

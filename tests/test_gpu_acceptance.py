@@ -129,3 +129,56 @@ def test_molecule_server_streams_in_order(dev):
     for (E1, F1), (E2, F2) in zip(single, streamed):
         assert torch.equal(E1, E2) and F1.shape == F2.shape
         assert float((F1 - F2).abs().max()) <= 1e-6 * float(F1.abs().max())   # force atomics: not bitwise
+
+
+@pytest.mark.parametrize("name,blocks,n_mol,n_batches", [("dT", 2, 6, 2), ("dQ", 1, 3, 1)])
+def test_scale_fitting_matches_reference(name, blocks, n_mol, n_batches, dev, tmp_path):
+    """the fit_scaling.py protocol (fit_scaling.py:93-160 — set2fitmode, build the model, per factor: run
+    batches, fit(), next) on this package's GemNet (GPU kernels + ScalingFactor.observe hooks) gives the factors the
+    UNMODIFIED reference gives on its own CPU forward, factor by factor (every later factor depends on the earlier ones)."""
+    import importlib
+    import json
+    _reference()
+    from gemnet.model.gemnet import GemNet as RefGemNet
+    ref_scaling = importlib.import_module("gemnet.model.layers.scaling")
+    from gemnet_pytorch_b200 import GemNet, build_batch, scaling
+    kw = dict(H.model_kwargs(H.load_npz(f"model_{name}.npz")), num_blocks=blocks)
+    id_sets = [list(range(40, 40 + n_mol)), list(range(120, 120 + n_mol))][:n_batches]
+    batches = [build_batch(*H.molecules(ids), kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]) for ids in id_sets]
+
+    def fit(cls, mod, path, device):
+        with open(path, "w") as f:
+            json.dump({"comment": "acceptance test"}, f)
+        mod.AutomaticFit.set2fitmode()
+        try:
+            torch.manual_seed(11)
+            model = cls(**dict(kw, scale_file=path)).to(device).eval()
+            rounds = 0
+            while not mod.AutomaticFit.fitting_completed():
+                with torch.no_grad():
+                    for b in batches:
+                        model({k: v.to(device) for k, v in b.items()})
+                mod.AutomaticFit.activeVar.fit()
+                rounds += 1
+                assert rounds < 100
+        finally:
+            mod.AutomaticFit.reset()
+            mod.AutomaticFit.queue = None
+            mod.AutomaticFit.fitting_mode = False
+        with open(path) as f:
+            return json.load(f), rounds, model
+
+    want, r_ref, _ = fit(RefGemNet, ref_scaling, str(tmp_path / "ref.json"), torch.device("cpu"))
+    got, r_mine, model = fit(GemNet, scaling, str(tmp_path / "mine.json"), dev)
+    assert r_mine == r_ref == len(want) - 1 and list(got) == list(want)   # same factors in the same (creation) order
+    worst = max(abs(got[k] - want[k]) / abs(want[k]) for k in want if k != "comment")
+    print(f"[{name}] {r_mine} factors fitted, worst relative difference {worst:.2e}")
+    assert worst <= 2e-4, worst
+    # the fitted factors are what the fused engine path uses afterwards, and a model built from the file loads them
+    assert not scaling.fitting_active()
+    again = GemNet(**dict(kw, scale_file=str(tmp_path / "mine.json"))).to(dev).eval()
+    again.load_state_dict(model.state_dict(), strict=True)
+    b = {k: v.to(dev) for k, v in batches[0].items()}
+    E1, F1 = model.predict(dict(b))
+    E2, F2 = again.predict(dict(b))
+    assert torch.allclose(E1, E2, rtol=0, atol=1e-5 * float(E2.abs().max()))

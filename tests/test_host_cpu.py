@@ -164,3 +164,65 @@ def test_seeded_synthetic_weights_are_deterministic_and_reference_format():
     assert any(not torch.equal(a[k], c[k]) for k in a)
     assert set(a.keys()) == set(go.synthetic_state_dict(kw).keys())
     GemNet(**kw).load_state_dict(a, strict=True)
+
+
+def _fit_protocol(mod, tmp, seed):
+    """drive a scaling module (ours or the reference's) through fit_scaling.py's protocol on CPU tensors"""
+    import json
+    path = os.path.join(tmp, f"scales_{mod.__name__.replace('.', '_')}.json")
+    with open(path, "w") as f:
+        json.dump({"comment": "test", "pre_fitted": 0.25}, f)
+    mod.AutomaticFit.set2fitmode()
+    names = ["a_sum", "pre_fitted", "b_had", "c_sum"]
+    facs = [mod.ScalingFactor(scale_file=path, name=n) for n in names]
+    g = torch.Generator().manual_seed(seed)
+    data = [[(torch.randn(50 + 7 * b, 8, generator=g), torch.randn(50 + 7 * b, 5, generator=g) * (1 + k)) for b in range(3)]
+            for k in range(len(names))]
+    rounds = 0
+    while not mod.AutomaticFit.fitting_completed():
+        for b in range(3):
+            for k, f in enumerate(facs):  # every factor sees every batch; only the active one records
+                x, y = data[k][b]
+                out = f(x, y)
+                assert torch.equal(out, y * f.scale_factor)
+        mod.AutomaticFit.activeVar.fit()
+        rounds += 1
+    with open(path) as f:
+        return json.load(f), rounds
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="needs the reference (or its staged copy)")
+def test_scale_fit_protocol_matches_reference(tmp_path):
+    """N4: gemnet_pytorch_b200.scaling (AutomaticFit / AutoScaleFit / ScalingFactor) against the unmodified
+    gemnet/model/layers/scaling.py driven the way fit_scaling.py:93-160 drives it: same fitting order (creation order,
+    file-provided factors skipped), same fitted values, same JSON file."""
+    ref_shims.install()
+    import importlib
+    ref = importlib.import_module("gemnet.model.layers.scaling")
+    from gemnet_pytorch_b200 import scaling as mine
+    try:
+        got, r1 = _fit_protocol(mine, str(tmp_path), 5)
+    finally:
+        mine.AutomaticFit.leave_fitmode()
+    want, r2 = _fit_protocol(ref, str(tmp_path), 5)
+    ref.AutomaticFit.fitting_mode = False
+    assert r1 == r2 == 3 and set(got) == set(want)
+    for k in want:
+        if k != "comment":
+            assert abs(got[k] - want[k]) <= 1e-6 * abs(want[k]), k
+    assert got["pre_fitted"] == 0.25
+
+
+def test_scale_factor_module_without_fitting(tmp_path):
+    from gemnet_pytorch_b200 import scaling
+    assert not scaling.fitting_active()
+    f = scaling.ScalingFactor(scale_file=None, name="x")
+    y = torch.randn(4, 3)
+    assert torch.equal(f(torch.randn(4, 3), y), y) and f.value() == 1.0
+    p = str(tmp_path / "s.json")
+    scaling.write_json(p, {"x": 1.5})
+    f = scaling.ScalingFactor(scale_file=p, name="x")
+    assert f.value() == 1.5 and torch.equal(f(y, y), y * 1.5)
+    with pytest.raises(UserWarning):
+        scaling.ScalingFactor(scale_file=str(tmp_path / "s.txt"), name="x")
