@@ -542,8 +542,10 @@ class DeviceStaticBuilder:
         self.host = {"R64": be.host_buffer(3 * A, f64), "Z": be.host_buffer(A), "n_per_mol": be.host_buffer(M),
                      "hdr": be.host_buffer(HDR_WORDS)}
         self.host_np = {k: be.np_view(v) for k, v in self.host.items()}
-        for v in self.host_np.values():
-            v[...] = 0
+        for k, v in self.host_np.items():
+            # Z = 1 behind the real atoms: when a batch overflows its capacity the pad kernel does not run, and the
+            # evaluation that still follows inside the captured graph must only ever see valid atomic numbers
+            v[...] = 1 if k == "Z" else 0
         a = self.a = {"R64": be.empty(3 * A, f64), "Z": be.empty(A), "n_per_mol": be.empty(M), "hdr": be.empty(HDR_WORDS),
                       "mol_off": be.empty(M + 1), "atom_cnt": be.empty(3 * A), "upper_off": be.empty(A + 1),
                       "in_ptr": be.empty(A + 1), "R32": be.empty(3 * A, torch.float32), "batch_seg": be.empty(A),

@@ -202,3 +202,6 @@ def test_emulated_static_build_reports_overflow(emu):
     sb.stage(Rl, Zl)
     sb.enqueue()
     assert sb.header()[graph.HDR_OVERFLOW] & 6
+    # the evaluation that still follows in the captured graph must see valid atomic numbers everywhere (Z - 1 indexes
+    # the embedding table): the pad kernel did not run, the staging default covers the rows behind the real atoms
+    assert (np.asarray(sb.inputs()["Z"]) >= 1).all()
