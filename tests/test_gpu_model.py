@@ -166,16 +166,17 @@ def test_edge_cases(dev):
 
 @pytest.mark.parametrize("M", ["T", "Q"])
 def test_pretrained_checkpoint_parity(M, dev):
-    """With the shipped checkpoints (travel git-ignored under tests/golden/_local, made by oracle/make_golden.py)."""
-    local = os.path.join(H.GOLDEN, "_local")
-    wpath, fpath = os.path.join(local, f"weights_{M}.npz"), os.path.join(local, f"model_{M}_pretrained.npz")
-    if not (os.path.exists(wpath) and os.path.exists(fpath)):
-        pytest.skip("pretrained fixtures not present (generated only where /root/reference exists)")
-    fx = dict(np.load(fpath))
+    """The SHIPPED checkpoints (pretrained/GemNet-{T,Q}/model.pth, strict-loaded from the staged reference,
+    oracle/build_ref.sh) against the unmodified reference's own outputs with them (tests/golden/model_*_pretrained.npz,
+    oracle/make_golden_pretrained.py).  Fails — does not skip — when the staged reference did not travel with the tree."""
+    from oracle import ref_shims
+    ck = os.path.join(ref_shims.REFERENCE_ROOT, "pretrained", f"GemNet-{M}", "model.pth")
+    assert os.path.exists(ck), (
+        f"{ck} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference exists "
+        "(it stages the reference and its checkpoints into the git-ignored oracle/_ref, which travels to the GPU box)")
+    fx = H.load_npz(f"model_{M}_pretrained.npz")
     kw = H.model_kwargs(fx)
-    uniq = {k: torch.tensor(v) for k, v in np.load(wpath).items()}
-    sd = go.expand_aliases(uniq)
-    model = make_model(kw, sd, dev)
+    model = make_model(kw, torch.load(ck, map_location="cpu"), dev)
     from gemnet_pytorch_b200 import build_batch
     inputs = build_batch(*H.molecules(fx["mol_ids"].tolist()), kw["cutoff"], kw["int_cutoff"], kw["triplets_only"])
     E, F = model(to_dev(inputs, dev))

@@ -221,7 +221,9 @@ def test_quadruplet_geometry_and_ylm(ops, dev):
     assert (ylm.double().cpu() - ref64).abs().mean() < 1e-6
 
     # backward of the whole geometry chain R -> (cbf4 angular part, Y_lm)
-    g1, g2 = torch.randn_like(sph_abd), torch.randn_like(ylm)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    g1 = torch.randn(sph_abd.shape, device=dev, generator=gen)
+    g2 = torch.randn(ylm.shape, device=dev, generator=gen)
 
     def kern(Rr):
         s, bd = ops.quad_intermediate(Rr, plan.abd_center, plan.abd_first, plan.abd_second, 7, True)
@@ -236,7 +238,9 @@ def test_quadruplet_geometry_and_ylm(ops, dev):
 
     (gR,) = kernel_grads(kern, [R], (g1, g2))
     (gR0,) = oracle_grads(oracle, [cpu["R"]], (g1, g2))
-    assert relerr(gR, gR0) < 1e-3  # float32 sums of ~1e4 ill-conditioned dihedral terms per atom
+    # measured 5e-7 (profiles/probe_quad_grad.py: the same with the gradient masked to well-conditioned dihedrals,
+    # sin of both polar angles >= 0.1 / 0.3 / 0.5, gives 3e-7 .. 7e-7): the analytic backward has no weak term
+    assert relerr(gR, gR0) < 5e-5
 
 
 # ----------------------------------------------------------------------------- H6
