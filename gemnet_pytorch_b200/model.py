@@ -430,10 +430,19 @@ class ServingGemNet:
 
     def call_arrays(self, R64, Z, N):
         """the same from the concatenated batch (R float64 (A,3), Z (A,), N int32 (M,))"""
+        self.launch_arrays(R64, Z, N)
+        return self.finish()
+
+    def launch_arrays(self, R64, Z, N):
+        """first half of call_arrays: stage the batch and start the graph (asynchronous); `finish()` returns the result.
+        Between the two the host is free — MoleculeServer.stream prepares the next batch there."""
         if self.builder is None:
             raise _lib.GemnetB200Error("this runner was captured for host-built batches (device_build=False)")
-        A, M = self.builder.stage_arrays(R64, Z, N)
+        self._sizes = self.builder.stage_arrays(R64, Z, N)
         self.graph.replay()
+
+    def finish(self):
+        A, M = self._sizes
         torch.cuda.current_stream().synchronize()
         ov = int(self.hdr_host[graph.HDR_OVERFLOW])
         if ov:
@@ -489,6 +498,12 @@ class ServingPool:
     def call_molecules(self, R_list, Z_list):
         """Raw molecules on the host -> (E, F): the bucket is chosen from the host's edge / triplet COUNT (one pass
         over the distance tests, graph.count_batch), the index arrays themselves are built inside the captured graph."""
+        runner, arrays = self.prepare_molecules(R_list, Z_list)
+        return runner.call_arrays(*arrays)
+
+    def prepare_molecules(self, R_list, Z_list):
+        """host work of a device-built batch that does not touch the staging buffers: concatenate, count edges and
+        triplets, pick (or capture) the runner of the capacity bucket.  Returns (runner, (R64, Z, N))."""
         R64, Z, N = graph.concat_molecules(R_list, Z_list)
         n_edges, n_triplets = graph.count_arrays(R64, N, self.model.cutoff)
         cap = self.capacity_for(n_edges, n_triplets)
@@ -499,7 +514,7 @@ class ServingPool:
                 self.runners.pop(next(iter(self.runners)))
             runner = ServingGemNet(self.model, cap, self.warmup, device_build=True)
         self.runners[key] = runner
-        return runner.call_arrays(R64, Z, N)
+        return runner, (R64, Z, N)
 
     @property
     def h2d_bytes(self):
@@ -551,9 +566,25 @@ class MoleculeServer:
         return self.evaluate(self.build(R_list, Z_list))
 
     def stream(self, batches):
-        if self.index_build == "device":  # nothing left on the host to overlap: coordinates in, one launch, results out
-            for R_list, Z_list in batches:
-                yield self(R_list, Z_list)
+        if self.index_build == "device":
+            if self.pool is None:  # quadruplet models: dynamic shapes, evaluated eagerly
+                for R_list, Z_list in batches:
+                    yield self(R_list, Z_list)
+                return
+            # triplet models: while the graph of batch n runs, the host concatenates / counts batch n + 1 (the staging
+            # buffers are only written after batch n's results have been read)
+            it = iter(batches)
+            nxt = next(it, None)
+            prep = None if nxt is None else self.pool.prepare_molecules(*nxt)
+            while prep is not None:
+                runner, arrays = prep
+                runner.launch_arrays(*arrays)
+                nxt = next(it, None)
+                try:
+                    prep = None if nxt is None else self.pool.prepare_molecules(*nxt)
+                finally:
+                    out = runner.finish()  # (also when preparing the next batch raised: never leave a replay un-synchronised)
+                yield out
             return
         import collections
         pending = collections.deque()
