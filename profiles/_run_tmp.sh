@@ -2,5 +2,11 @@
 # scratch driver for one gpurun call
 O=gpurun_out
 mkdir -p $O
-timeout 400 python -m pytest "tests/test_gpu_graph_device.py::test_device_build_runner_reports_a_batch_that_does_not_fit" tests/test_gpu_acceptance.py "tests/test_gpu_ops.py::test_csr_preparation_bit_exact" "tests/test_gpu_ops.py::test_malformed_index_lists_are_reported" -q -m gpu -s > $O/pytest_new.log 2>&1; grep -v "Warning\|IndexKernelUtils" $O/pytest_new.log | tail -25
-timeout 100 python profiles/probe_quad_grad.py > $O/probe_quad_grad.txt 2>&1; tail -5 $O/probe_quad_grad.txt
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scan_kernel|atom_count|edges_kernel|incoming_kernel|triplets_kernel|quad_count|quad_ptr|quad_emit|pad_kernel" -c 400 --csv \
+  --log-file $O/launches_r02b_graph_device.csv python profiles/time_graph_device.py Q 64 > $O/ncu_gd.log 2>&1
+timeout 150 ncu --set full --import-source on --clock-control none -k regex:segbil_fwd_tc_kernel --launch-skip 4 -c 1 \
+  -o $O/prof_r02b_h7_tc_b64 -f python profiles/time_h7.py 64 --seed 1234 > $O/ncu_h7.log 2>&1
+GEMNET_B200_LANES=0 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
+  --log-file $O/launches_r02b_Q.csv python bench.py --model Q --eager --steps 1 --warmup 3 --no-cpu-baseline --large-batch 0 --index-build host \
+  > $O/ncu_bench_Q.log 2>&1
+tail -2 $O/ncu_gd.log $O/ncu_h7.log $O/ncu_bench_Q.log

@@ -16,7 +16,7 @@ def main(path, top=30):
         v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(row["Metric Unit"], 1.0)
         agg[row["Kernel Name"]][0] += 1
         agg[row["Kernel Name"]][1] += v
-    tot = sum(v[1] for v in agg.values())
+    tot = sum(v[1] for v in agg.values()) or 1.0
     n = sum(v[0] for v in agg.values())
     print(f"{n} launches, {tot / 1e6:.3f} ms total GPU time (cold-cache, serialised: compare shares)")
     ours = sum(v[1] for k, v in agg.items() if "gemnet::" in k)

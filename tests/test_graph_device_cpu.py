@@ -205,3 +205,28 @@ def test_emulated_static_build_reports_overflow(emu):
     # the evaluation that still follows in the captured graph must see valid atomic numbers everywhere (Z - 1 indexes
     # the embedding table): the pad kernel did not run, the staging default covers the rows behind the real atoms
     assert (np.asarray(sb.inputs()["Z"]) >= 1).all()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_emulated_device_builder_random_molecules(emu, seed):
+    """random point clouds (1-45 atoms per molecule, incl. molecules larger than a warp, empty molecules, atoms exactly
+    at the cutoff distance, coincident atoms) — the emulated device builder equals the host builder array for array"""
+    rng = np.random.default_rng(100 + seed)
+    Rl, Zl = [], []
+    for _ in range(int(rng.integers(1, 9))):
+        n = int(rng.choice([0, 1, 2, 3, 7, 20, 33, 45]))
+        box = float(rng.choice([2.0, 4.0, 9.0]))
+        R = rng.uniform(0.0, box, size=(n, 3))
+        if n >= 3:
+            R[1] = R[0] + np.array([3.0, 0.0, 0.0])   # a pair at exactly the cutoff (3.0, representable): <= keeps it
+            R[2] = R[0]                               # coincident atoms: distance 0 is an edge as in the reference
+        Rl.append(R)
+        Zl.append(rng.integers(1, 9, size=n))
+    if sum(len(z) for z in Zl) == 0:
+        Rl.append(np.zeros((1, 3)))
+        Zl.append(np.array([1]))
+    for trip_only in (True, False):
+        host = build_batch(Rl, Zl, 3.0, 4.5, trip_only, as_torch=False)
+        dev = emulated_batch(emu, Rl, Zl, 3.0, 4.5, trip_only)
+        for k, v in host.items():
+            assert np.array_equal(np.asarray(dev[k]).reshape(v.shape), v), (k, trip_only, seed)
