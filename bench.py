@@ -239,11 +239,10 @@ def time_chain(M, dev, flush, reps):
     return float(np.mean(times)), 4 * M * 128 * (3 + 7 + 1) + 7 * 6 * 128 * 128, 7 * 2 * M * 128 * 128
 
 
-def ncu_traffic_large(n_mol):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the H7 tcgen05 kernel on the 2048-molecule batch, from the
-    committed `ncu --set full` capture of the same launch (profiles/final_run.sh); None for any other size."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_r01_final_segbil_fwd_tc_large.txt")
-    if n_mol != 2048 or not os.path.exists(path):
+def _ncu_dram_bytes(fname):
+    """dram__bytes_read.sum + dram__bytes_write.sum from a committed `ncu --set full` summary (profiles/ncu_summary.py)"""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", fname)
+    if not os.path.exists(path):
         return None
     tot = 0.0
     for ln in open(path):
@@ -251,6 +250,20 @@ def ncu_traffic_large(n_mol):
         if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
     return tot or None
+
+
+def ncu_traffic_large(n_mol):
+    """DRAM traffic of the H7 tcgen05 kernel on the 2048-molecule batch, from the committed `ncu --set full` capture of
+    the same launch (profiles/final_run.sh); None for any other size."""
+    return _ncu_dram_bytes("ncu_r01_final_segbil_fwd_tc_large.txt") if n_mol == 2048 else None
+
+
+def ncu_traffic_bench_batch(args, kw, rank):
+    """DRAM traffic of the H7 tcgen05 kernel on the batch this bench times by default (64 COLL-shaped molecules of seed
+    1234, cutoff 5 A: 8 186 edges, 95 444 triplets), from the committed capture `python profiles/time_h7.py 64 --seed 1234`
+    under `ncu --set full` (output written stays in L2: the figure is the DRAM reads); None for any other workload."""
+    default = args.batch == 64 and rank == 0 and MOLECULE_KIND[0] == "coll" and kw["cutoff"] == 5.0
+    return _ncu_dram_bytes("ncu_r02b_segbil_fwd_tc_b64.txt") if default else None
 
 
 def pick_cpu_threads(fn):
@@ -673,7 +686,8 @@ def main():
     t_k0, _, _ = time_bilinear(plan, dev, flush, 30, algo=0)
     line["roofline"] = {"kernel": "segbil_fwd_tc_kernel (H7 triplets, tcgen05 bf16x3 + weight pack kernel)",
                         "bound": "hbm", "achieved": bts / t_k / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": bts / t_k / 1e9 / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                        "frac": bts / t_k / 1e9 / hbm_peak, "traffic": ncu_traffic_bench_batch(args, kw, rank),
+                        "peak_kind": peak_kind,
                         "bytes_per_launch": bts, "us_per_launch": t_k * 1e6, "tflops": fl / t_k / 1e12,
                         "tensor_frac_of_bf16_peak": 3 * 2 * plan.n_edges * 1024 * 64 / t_k / 1e12 / tc_peak,
                         "bytes_per_triplet": bts / max(plan.n_triplets, 1),

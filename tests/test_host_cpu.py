@@ -226,3 +226,13 @@ def test_scale_factor_module_without_fitting(tmp_path):
     assert f.value() == 1.5 and torch.equal(f(y, y), y * 1.5)
     with pytest.raises(UserWarning):
         scaling.ScalingFactor(scale_file=str(tmp_path / "s.txt"), name="x")
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/gemnet_b200.h is the C ABI: it must compile as C99 on its own (no C++-isms, no torch types)"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "gemnet_b200.h"\nint main(void) { gemnet_device_graph g; gemnet_chain_program p; (void)g; (void)p; '
+                   'return GEMNET_B200_ABI_VERSION - 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-fsyntax-only",
+                    str(src)], check=True)
