@@ -6,10 +6,12 @@ base_layers.py:24-27), OutputBlock aliases `layers` as `seq_energy` (atom_update
 ScalingFactor is a scalar non-trainable Parameter (scaling.py:165-167).  Construction order and initialisers
 follow the reference so that a seeded random init gives the same weights.
 
-The dense GEMMs (Dense / ResidualLayer / embeddings) stay torch (cuBLAS): SURVEY §8f row N1.  Everything else
-calls the CUDA kernels in ops.py.
+These `forward` methods are the LAYER-BY-LAYER path (`GemNet.forward_autograd`: torch.autograd over one kernel per
+op from ops.py, dense layers as library GEMMs): used with `use_engine=False`, while a scale factor is being fitted
+(scaling.py: the observed tensors must exist in HBM) and as the cross-check of the engine in the tests.  Inference and
+direct-force training run on the tape engine instead (engine.py / fused.py: chain-fused tcgen05 kernels),
+which reads the same modules' parameters.
 """
-import json
 
 import numpy as np
 import torch
