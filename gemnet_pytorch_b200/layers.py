@@ -8,7 +8,7 @@ follow the reference so that a seeded random init gives the same weights.
 
 These `forward` methods are the LAYER-BY-LAYER path (`GemNet.forward_autograd`: torch.autograd over one kernel per
 op from ops.py, dense layers as library GEMMs): used with `use_engine=False`, while a scale factor is being fitted
-(scaling.py: the observed tensors must exist in HBM) and as the cross-check of the engine in the tests.  Inference and
+(scale_fit.py: the observed tensors must exist in HBM) and as the cross-check of the engine in the tests.  Inference and
 direct-force training run on the tape engine instead (engine.py / fused.py: chain-fused tcgen05 kernels),
 which reads the same modules' parameters.
 """
@@ -129,7 +129,7 @@ class EdgeEmbedding(torch.nn.Module):
 
 
 # ----------------------------------------------------------------------------- scaling (scaling.py:150-174)
-from .scaling import ScalingFactor  # noqa: E402,F401  (the module tree keeps `layers.ScalingFactor`)
+from .scale_fit import ScalingFactor  # noqa: E402,F401  (the module tree keeps `layers.ScalingFactor`)
 
 
 # ----------------------------------------------------------------------------- basis layers (basis_layers.py)

@@ -12,7 +12,7 @@ fp64, scatters are CSR segment sums without atomics, and scale factors are folde
 """
 import torch
 
-from . import _lib, dense_ops, engine, graph, layers, ops, scaling
+from . import _lib, dense_ops, engine, graph, layers, ops, scale_fit
 from .layers import (AtomEmbedding, BesselBasisLayer, Dense, EdgeEmbedding, EfficientInteractionDownProjection,
                      InteractionBlock, InteractionBlockTripletsOnly, OutputBlock, SphericalBasisLayer,
                      TensorBasisLayer)
@@ -147,7 +147,7 @@ class GemNet(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs):
-        if scaling.fitting_active():
+        if scale_fit.fitting_active():
             # fit_scaling.py: a scale factor is collecting Var(x_ref) / Var(y) — only the layer-by-layer path has those
             # tensors in HBM
             return self.forward_autograd(inputs)

@@ -141,7 +141,8 @@ def test_scale_fitting_matches_reference(name, blocks, n_mol, n_batches, dev, tm
     _reference()
     from gemnet.model.gemnet import GemNet as RefGemNet
     ref_scaling = importlib.import_module("gemnet.model.layers.scaling")
-    from gemnet_pytorch_b200 import GemNet, build_batch, scaling
+    from gemnet_pytorch_b200 import GemNet, build_batch
+    from gemnet_pytorch_b200 import scale_fit as scaling
     kw = dict(H.model_kwargs(H.load_npz(f"model_{name}.npz")), num_blocks=blocks)
     id_sets = [list(range(40, 40 + n_mol)), list(range(120, 120 + n_mol))][:n_batches]
     batches = [build_batch(*H.molecules(ids), kw["cutoff"], kw["int_cutoff"], kw["triplets_only"]) for ids in id_sets]

@@ -194,13 +194,13 @@ def _fit_protocol(mod, tmp, seed):
 @pytest.mark.reference
 @pytest.mark.skipif(not ref_shims.reference_available(), reason="needs the reference (or its staged copy)")
 def test_scale_fit_protocol_matches_reference(tmp_path):
-    """N4: gemnet_pytorch_b200.scaling (AutomaticFit / AutoScaleFit / ScalingFactor) against the unmodified
+    """N4: gemnet_pytorch_b200.scale_fit (AutomaticFit / AutoScaleFit / ScalingFactor) against the unmodified
     gemnet/model/layers/scaling.py driven the way fit_scaling.py:93-160 drives it: same fitting order (creation order,
     file-provided factors skipped), same fitted values, same JSON file."""
     ref_shims.install()
     import importlib
     ref = importlib.import_module("gemnet.model.layers.scaling")
-    from gemnet_pytorch_b200 import scaling as mine
+    from gemnet_pytorch_b200 import scale_fit as mine
     try:
         got, r1 = _fit_protocol(mine, str(tmp_path), 5)
     finally:
@@ -215,7 +215,7 @@ def test_scale_fit_protocol_matches_reference(tmp_path):
 
 
 def test_scale_factor_module_without_fitting(tmp_path):
-    from gemnet_pytorch_b200 import scaling
+    from gemnet_pytorch_b200 import scale_fit as scaling
     assert not scaling.fitting_active()
     f = scaling.ScalingFactor(scale_file=None, name="x")
     y = torch.randn(4, 3)
