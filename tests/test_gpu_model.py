@@ -1,7 +1,8 @@
 """GPU parity of the whole hot path behind the reference boundary: GemNet.forward energies and forces against
   (a) the committed fixtures produced by the unmodified reference (tests/golden/model_*.npz, synthetic weights),
   (b) the CPU oracle on other batches (incl. COLL molecules 64-255, larger cutoff, edge cases),
-  (c) the reference's outputs with the shipped pretrained checkpoints when tests/golden/_local travelled with the tree.
+  (c) the reference's outputs with the shipped pretrained checkpoints (tracked fixtures; the checkpoints themselves come
+      with the staged reference, oracle/_ref).
 Gate (north_star): |dE| <= 1e-4 |E|max, |dF| <= 1e-4 |F|max per batch (SURVEY §6 last row); we assert 2e-5.
 """
 import os
