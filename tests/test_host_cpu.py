@@ -236,3 +236,34 @@ def test_public_header_is_plain_c(tmp_path):
                    'return GEMNET_B200_ABI_VERSION - 1; }\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-fsyntax-only",
                     str(src)], check=True)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="needs the reference (or its staged copy)")
+def test_integration_aliases_resolve_for_the_reference_scripts():
+    """with `gemnet.model.gemnet` and `gemnet.model.layers.scaling` aliased to this package, the import
+    lines of the reference's own scripts (fit_scaling.py:21-32, train_seml.py:12-19) resolve to this package's classes
+    while the rest of the reference (Trainer, utils) is still the reference's."""
+    import sys
+    import types
+
+    import gemnet_pytorch_b200
+    from gemnet_pytorch_b200 import scale_fit
+    ref_shims.install()
+    saved = {k: sys.modules.get(k) for k in ("gemnet.model.gemnet", "gemnet.model.layers.scaling")}
+    try:
+        mod = types.ModuleType("gemnet.model.gemnet")
+        mod.GemNet = gemnet_pytorch_b200.GemNet
+        sys.modules["gemnet.model.gemnet"] = mod
+        sys.modules["gemnet.model.layers.scaling"] = scale_fit
+        from gemnet.model.gemnet import GemNet as G
+        from gemnet.model.layers.scaling import AutomaticFit as AF
+        from gemnet.model.utils import write_json  # noqa: F401  (the reference's own)
+        from gemnet.training.trainer import Trainer  # noqa: F401
+        assert G is gemnet_pytorch_b200.GemNet and AF is scale_fit.AutomaticFit
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
